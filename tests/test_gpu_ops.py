@@ -1,0 +1,258 @@
+"""GPU parity tests of the individual C-ABI entry points against the oracle / golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _nms(boxes, scores, thr):
+    from tinyfaces_b200 import ops
+    d = _dev()
+    keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr)
+    return keep[: int(count.item())].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_case_f32"])
+def test_nms_golden_bit_exact(name):
+    g = np.load(os.path.join(G, name + ".npz"))
+    assert np.array_equal(_nms(g["boxes"], g["scores"], float(g["thr"])), g["keep"])
+
+
+def test_nms_known_answers():
+    with open(os.path.join(G, "nms_known.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        k = _nms(np.array(c["boxes"], np.float64), np.array(c["scores"], np.float64), c["thr"])
+        assert k.tolist() == c["keep"], c
+    from tinyfaces_b200 import ops
+    keep, count = ops.nms_device(torch.zeros((0, 4), dtype=torch.float64, device=_dev()),
+                                 torch.zeros(0, dtype=torch.float64, device=_dev()), 0.3)
+    assert keep.numel() == 0 and keep.dtype == torch.int64 and int(count.item()) == 0
+
+
+@pytest.mark.parametrize("n,extent,thr", [(1, 10.0, 0.3), (63, 50.0, 0.3), (4097, 600.0, 0.3), (20000, 1500.0, 0.5),
+                                          (40000, 1800.0, 0.3)])
+def test_nms_vs_c_oracle(n, extent, thr):
+    """bit-exact keep indices incl. the multi-block path (n > 32768), ties and duplicates."""
+    from oracle import nms_oracle, synth
+    boxes, scores = synth.synthetic_boxes(n, seed=n, extent=extent, dup_frac=0.02)
+    scores = np.round(scores, 3)            # many exact score ties
+    assert np.array_equal(_nms(boxes, scores, thr), nms_oracle.nms(boxes, scores, thr))
+
+
+def test_nms_degenerate_nothing_suppressed():
+    from oracle import nms_oracle
+    r = np.random.RandomState(5)
+    boxes = np.repeat(r.rand(3000, 2) * 100, 2, axis=1)[:, [0, 2, 1, 3]]     # zero-area boxes: 0/0 -> NaN
+    scores = r.rand(3000)
+    k = _nms(boxes, scores, 0.3)
+    assert np.array_equal(k, nms_oracle.nms(boxes, scores, 0.3)) and len(k) == 3000
+
+
+# ------------------------------------------------------------------------------------------- decode
+def _decode_nhwc(g, bug_compat=True):
+    from oracle import decode_oracle, synth
+    from tinyfaces_b200 import ops
+    d = _dev()
+    tpl = synth.load_templates()
+    sc, reg, prob = (torch.from_numpy(g[k]).to(d) for k in ("score_cls", "score_reg", "prob_cls"))
+    B, H, W, T = sc.shape
+    inv = decode_oracle.invalid_ids(tpl, float(g["scale"]))
+    mask = 0
+    for i in inv:
+        mask |= 1 << int(i)
+    boxes, scores, src, count = ops.decode_device(sc, reg, prob, (H * W * T, W * T, T, 1), (H * W * 4 * T, W * 4 * T, 4 * T, 1),
+                                                  B, H, W, T, tpl, float(g["thresh"]), mask if bug_compat else 0,
+                                                  0 if bug_compat else mask, synth.RF, float(g["scale"]), want_src=True)
+    n = int(count.item())
+    return boxes[:n].cpu().numpy(), scores[:n].cpu().numpy(), src[:n].cpu().numpy()
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_decode_golden(case):
+    g = np.load(os.path.join(G, "decode_case%d.npz" % case))
+    boxes, scores, src = _decode_nhwc(g)
+    assert boxes.shape == g["boxes"].shape                                  # same candidate count
+    assert np.array_equal(scores.astype(np.float32), g["scores"][:, 0])    # same candidates, same (b,y,x,c) order
+    flat = np.flatnonzero(g["prob_after"].reshape(-1) > np.float32(g["thresh"]))
+    assert np.array_equal(src, flat)
+    # boxes: float64 arithmetic in the reference's order; only the float32 exp may differ by an ulp
+    np.testing.assert_allclose(boxes, g["boxes"], rtol=2e-7, atol=1e-9)
+
+
+def test_decode_known_answer_and_nchw_sigmoid():
+    from oracle import decode_oracle, synth
+    from tinyfaces_b200 import ops
+    d = _dev()
+    tpl = synth.load_templates()
+    r = np.random.RandomState(3)
+    B, H, W, T = 1, 37, 53, 25
+    out = (1.5 * r.randn(B, 5 * T, H, W)).astype(np.float32)
+    out[:, T:] *= 0.2
+    sc = np.ascontiguousarray(out[:, :T].transpose(0, 2, 3, 1))
+    reg = np.ascontiguousarray(out[:, T:].transpose(0, 2, 3, 1))
+    to = torch.from_numpy(out).to(d)
+    prob = torch.sigmoid(to[:, :T]).permute(0, 2, 3, 1).contiguous().cpu().numpy()
+    thr = 0.7
+    # keep away from razor-edge probabilities so that sigmoid rounding cannot flip membership
+    edge = np.abs(prob - np.float32(thr)) < 1e-5
+    assert not edge.any()
+    for scale in (0.5, 1.0, 2.0):
+        rb, rs = decode_oracle.get_bboxes(sc, reg, prob.copy(), tpl, thr, synth.RF, scale)
+        inv = decode_oracle.invalid_ids(tpl, scale)
+        mask = sum(1 << int(i) for i in inv)
+        hw = H * W
+        boxes, scores, _, count = ops.decode_device(to, to[:, T:], None, (5 * T * hw, W, 1, hw), (5 * T * hw, W, 1, hw),
+                                                    B, H, W, T, tpl, thr, mask, 0, synth.RF, scale)
+        n = int(count.item())
+        assert n == rb.shape[0]
+        assert np.array_equal(scores[:n].cpu().numpy().astype(np.float32), rs[:, 0])
+        np.testing.assert_allclose(boxes[:n].cpu().numpy(), rb, rtol=2e-7, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------- loss
+@pytest.mark.parametrize("case", [0, 1])
+def test_loss_kernels_golden(case):
+    from oracle import loss_oracle
+    from tinyfaces_b200 import ops
+    d = _dev()
+    g = np.load(os.path.join(G, "loss_case%d.npz" % case))
+    rw = float(g["reg_weight"]) if "reg_weight" in g.files else 1.0
+    out = torch.from_numpy(g["output"]).to(d)
+    cm = torch.from_numpy(g["class_map"].copy()).to(d)
+    ops.detloss_ohem_(out, cm)
+    cm_ref = g["class_map"].copy()
+    loss_oracle.hard_negative_mining(g["output"][:, :25], cm_ref)
+    assert np.array_equal(cm.cpu().numpy(), cm_ref)                          # OHEM, bit exact
+    np.random.seed(int(g["np_seed"]))
+    orc = loss_oracle.criterion(g["output"], g["class_map"].copy(), g["regression_map"], reg_weight=rw)
+    labels = torch.from_numpy(orc["labels"]).to(d)
+    sums, grad = ops.detloss_fwd_bwd(out, labels, torch.from_numpy(g["regression_map"]).to(d), rw)
+    sums = sums.cpu().numpy()
+    assert abs(sums[0] - g["cls_sum"]) <= 1e-5 * abs(g["cls_sum"])
+    assert abs(sums[1] - g["reg_sum"]) <= 1e-5 * abs(g["reg_sum"])
+    assert abs(sums[0] + rw * sums[1] - g["total"]) <= 1e-5 * abs(g["total"])
+    np.testing.assert_allclose(grad.cpu().numpy(), g["grad"], rtol=1e-5, atol=1e-6)
+
+
+def test_loss_device_sampler_counts():
+    from tinyfaces_b200 import ops
+    d = _dev()
+    r = np.random.RandomState(0)
+    B, T, H, W = 3, 25, 40, 50
+    u = r.rand(B, T, H, W)
+    lab = np.zeros((B, T, H, W), np.float32)
+    lab[u < 0.9] = -1
+    lab[u > 0.99] = 1
+    lab[2][lab[2] > 0] = 0                       # image 2: no positives
+    lab[1][(lab[1] < 0) & (r.rand(T, H, W) < 0.9995)] = 0   # image 1: few negatives
+    t = torch.from_numpy(lab.copy()).to(d)
+    ops.detloss_sample_device_(t, 128, 128, seed=1234)
+    s = t.cpu().numpy()
+    assert np.all((s == lab) | (s == 0))        # only ever zeroes labels
+    for b in range(B):
+        assert (s[b] > 0).sum() == min(128, (lab[b] > 0).sum())
+        assert (s[b] < 0).sum() == min(128, (lab[b] < 0).sum())
+    t2 = torch.from_numpy(lab.copy()).to(d)
+    ops.detloss_sample_device_(t2, 128, 128, seed=99)
+    assert not np.array_equal(t2.cpu().numpy(), s)           # a different seed picks a different subset
+
+
+# ------------------------------------------------------------------------------------------- conv GEMMs
+def _tf32(t):
+    """round fp32 -> tf32 (10 explicit mantissa bits) so that tensor-core products are exact."""
+    i = t.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k
+    (1, 8, 16, 32, 64, 1),
+    (2, 17, 23, 64, 128, 1),
+    (1, 30, 40, 256, 256, 1),
+    (2, 15, 20, 1024, 256, 1),
+    (1, 13, 29, 256, 1024, 1),
+    (1, 8, 16, 32, 64, 3),
+    (2, 17, 23, 64, 64, 3),
+    (1, 30, 40, 128, 128, 3),
+    (2, 15, 20, 256, 256, 3),
+    (1, 63, 63, 128, 128, 3),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", CONV_CASES)
+def test_conv2d_nhwc_vs_torch_cpu(B, H, W, Cin, Cout, k):
+    from tinyfaces_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(B * 1000 + H * 10 + Cin + k)
+    x = _tf32(torch.randn(B, Cin, H, W, generator=gen))
+    w = _tf32(torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, generator=gen)
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), bias.double(), padding=k // 2).float()
+    xn = x.permute(0, 2, 3, 1).contiguous().to(d)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous().to(d)
+    y = ops.conv2d_nhwc(xn, wp, k, bias=bias.to(d))
+    torch.cuda.synchronize()
+    assert ops.gemm_error_flag() == 0
+    got = y.cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, "rel err %g" % err
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", CONV_CASES)
+def test_conv2d_wgrad_vs_torch_cpu(B, H, W, Cin, Cout, k):
+    from tinyfaces_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(7 + B * 1000 + H * 10 + Cin + k)
+    x = _tf32(torch.randn(B, Cin, H, W, generator=gen))
+    dy = _tf32(torch.randn(B, Cout, H, W, generator=gen))
+    w = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x.double(), w, padding=k // 2).backward(dy.double())
+    ref = w.grad.float()
+    xn = x.permute(0, 2, 3, 1).contiguous().to(d)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(d)
+    dw = ops.conv2d_wgrad_nhwc(xn, dyn, k)
+    torch.cuda.synchronize()
+    assert ops.gemm_error_flag() == 0
+    got = dw.cpu().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, "rel err %g" % err
+
+
+def test_conv2d_3xtf32_parity_mode():
+    """hi/lo split operands through the 3-segment K loop recover fp32-level accuracy on arbitrary fp32 data."""
+    from tinyfaces_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(11)
+    B, H, W, Cin, Cout, k = 2, 15, 20, 256, 256, 3
+    x = torch.randn(B, Cin, H, W, generator=gen)
+    w = torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5
+    ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=1).float()
+
+    def split(t):
+        hi = (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+        return hi, t - hi
+
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous()
+    xh, xl = split(xn)
+    wh, wl = split(wp)
+    y1 = ops.conv2d_nhwc(xh.to(d), wh.to(d), k)
+    y3 = ops.conv2d_nhwc(xh.to(d), wh.to(d), k, x_lo=xl.to(d), w_lo=wl.to(d))
+    torch.cuda.synchronize()
+    e1 = (y1.cpu().permute(0, 3, 1, 2) - ref).abs().max().item() / ref.abs().max().item()
+    e3 = (y3.cpu().permute(0, 3, 1, 2) - ref).abs().max().item() / ref.abs().max().item()
+    assert e3 < 5e-6 and e3 < e1 / 20, (e1, e3)

@@ -1,0 +1,536 @@
+// tcgen05 / TMA implicit-GEMM convolution kernels for NHWC fp32 activations (TF32 tensor-core math,
+// fp32 accumulation in TMEM).  They stand in for the 96 nn.Conv2d calls on the reference's hot path
+// (/root/reference/tinyfaces/models/model.py:90-106 -> torchvision resnet.py Bottleneck convs) and for the
+// dgrad / wgrad GEMMs autograd runs for them (/root/reference/tinyfaces/trainer.py:86).
+//
+//  conv_gemm_kernel  (fprop + dgrad):  D[pixel, co] = sum_{tap, ci} A[pixel (+) tap, ci] * Wp[co, tap, ci]
+//      A tiles: 128 pixels x 32 channels (128 B rows, SWIZZLE_128B) fetched by TMA straight from the NHWC
+//      tensor -- a 2-D map for 1x1 convs, a 4-D map (C, W, H, B) for 3x3 where the tap shift is just a
+//      coordinate offset and the zero padding is TMA's out-of-bounds fill.  Both operands K-major.
+//      Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 tcgen05.mma issuer (one thread),
+//      warps 2-5 epilogue (tcgen05.ld -> swizzled smem -> TMA store).  Two TMEM accumulator stages so the
+//      epilogue of tile i overlaps the MMAs of tile i+1.
+//  conv_wgrad_kernel:  dW[co, tap, ci] += sum_{pixel} dY[pixel, co] * X[pixel (+) tap, ci]
+//      Both operands MN-major (channels contiguous, reduction over pixels), split-K over pixel blocks,
+//      epilogue = TMA reduce-add (fp32) into the packed gradient.
+//
+// A K loop may run over up to 3 (A, B) tensor-map pairs ("segments"): the 3xTF32 parity mode feeds
+// (A_hi,B_hi), (A_lo,B_hi), (A_hi,B_lo) through the same accumulator.
+#include "tf_common.cuh"
+#include "tf_umma.cuh"
+#include <mutex>
+
+using namespace tfu;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;                 // fp32 elements = 128 bytes = one swizzle row
+constexpr int A_STAGE_BYTES = BLOCK_M * 128;
+constexpr int EPI_BUF_BYTES = 128 * 128;    // 128 rows x 32 fp32
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_SEG = 3;
+constexpr int MAX_TAPS = 9;
+
+struct GemmMaps {
+    CUtensorMap a[MAX_SEG];
+    CUtensorMap b[MAX_SEG];
+    CUtensorMap d;
+};
+
+struct GemmParams {
+    int num_m_tiles, num_n_tiles;
+    int spatial;                  // 0: A/D are 2-D [pixels, C]; 1: 4-D (C, W, H, B) with spatial tiles
+    int tiles_x, tiles_y, tw, th; // spatial tiling of one image (tw * th == 128)
+    int taps, kblocks, nseg;      // K loop = nseg x taps x kblocks blocks of 32 channels
+    const float* bias;            // optional per-output-channel bias
+    int* err_flag;
+};
+
+template <int BN> struct GemmCfg {
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int B_STAGE_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+// 3x3 taps are enumerated row-major: tap = (dy+1)*3 + (dx+1)
+__device__ __forceinline__ int tap_dx(int taps, int tap) { return taps == 9 ? tap % 3 - 1 : 0; }
+__device__ __forceinline__ int tap_dy(int taps, int tap) { return taps == 9 ? tap / 3 - 1 : 0; }
+
+__device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void store_row_swizzled(uint8_t* buf, int row, const uint32_t (&r)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 v = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        *reinterpret_cast<uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi + 2 * EPI_BUF_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&maps.a[s]); prefetch_tmap(&maps.b[s]); }
+        prefetch_tmap(&maps.d);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n0 = (tile % p.num_n_tiles) * BN;
+                const int mt = tile / p.num_n_tiles;
+                int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
+                if (p.spatial) {
+                    img = mt / tiles_per_img;
+                    const int r = mt % tiles_per_img;
+                    y0 = (r / p.tiles_x) * p.th;
+                    x0 = (r % p.tiles_x) * p.tw;
+                }
+                for (int seg = 0; seg < p.nseg; ++seg)
+                    for (int tap = 0; tap < p.taps; ++tap)
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 1);
+                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                            uint8_t* sb = sa + A_STAGE_BYTES;
+                            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                            if (p.spatial)
+                                tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                            else
+                                tma_load_2d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, m0);
+                            tma_load_2d(sb, &maps.b[seg], &full[stage], (tap * p.kblocks + kb) * BLOCK_K, n0);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN, MAJOR_K, MAJOR_K);
+            const int kiters = p.nseg * p.taps * p.kblocks;
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1, p.err_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < kiters; ++k) {
+                    mbar_wait(&full[stage], phase, p.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / 8; ++j) {
+                        const uint64_t ad = make_smem_desc(sa + j * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc(sb + j * 32, 16, 1024);
+                        mma_tf32(d_tmem, ad, bd, idesc, (k | j) != 0);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[acc]);
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (warps 2..5)
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const bool store_thread = threadIdx.x == 64;
+        int it = 0, ebuf = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n0 = (tile % p.num_n_tiles) * BN;
+            const int mt = tile / p.num_n_tiles;
+            int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
+            if (p.spatial) {
+                img = mt / tiles_per_img;
+                const int r = mt % tiles_per_img;
+                y0 = (r / p.tiles_x) * p.th;
+                x0 = (r % p.tiles_x) * p.tw;
+            }
+            mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
+            tc_fence_after();
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chunk * 32, r);
+                tmem_ld_wait();
+                if (chunk == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + n0 + chunk * 32 + j));
+                }
+                uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
+                if (store_thread) tma_store_wait_read<1>();      // the store that last used this buffer has drained
+                named_bar_sync_epi();
+                store_row_swizzled(buf, row, r);
+                fence_proxy_async();
+                named_bar_sync_epi();
+                if (store_thread) {
+                    if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0, y0, img);
+                    else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                    tma_store_commit();
+                }
+                ebuf ^= 1;
+            }
+        }
+        if (store_thread) tma_store_wait_all<0>();
+    }
+    __syncthreads();
+    if (warp == 1) { __syncwarp(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradMaps { CUtensorMap a, b, d; };     // a: dY (Cout, pixels), b: X (Cin, pixels), d: dW [Cout, taps*Cin]
+struct WgradParams {
+    int m_tiles, n_tiles, taps, splits;
+    int spatial, tiles_x, tiles_y, tw, th;     // pixel blocks of 32: flat or (tw x th) patches of one image
+    int num_pblocks;                            // total pixel blocks
+    int cin;                                    // column offset of a tap in dW = tap * cin
+    int* err_flag;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi + 2 * EPI_BUF_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&maps.a); prefetch_tmap(&maps.b); prefetch_tmap(&maps.d);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(&tfull[0], 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<BN < 32 ? 32 : BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int units = p.m_tiles * p.n_tiles * p.taps;
+    const int unit = blockIdx.x % units, split = blockIdx.x / units;
+    const int tap = unit % p.taps;
+    const int n0 = ((unit / p.taps) % p.n_tiles) * BN;
+    const int m0 = (unit / (p.taps * p.n_tiles)) * BLOCK_M;
+    const int pb0 = (int)((long long)p.num_pblocks * split / p.splits);
+    const int pb1 = (int)((long long)p.num_pblocks * (split + 1) / p.splits);
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (pb1 > pb0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0; uint32_t phase = 0;
+                for (int pb = pb0; pb < pb1; ++pb) {
+                    mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 11);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    if (p.spatial) {
+                        const int img = pb / tiles_per_img, r = pb % tiles_per_img;
+                        const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
+#pragma unroll
+                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_4d(sa + i * 4096, &maps.a, &full[stage], m0 + i * 32, x0, y0, img);
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &maps.b, &full[stage], n0 + j * 32, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(sa + i * 4096, &maps.a, &full[stage], m0 + i * 32, pb * 32);
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &maps.b, &full[stage], n0 + j * 32, pb * 32);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN, MAJOR_MN, MAJOR_MN);
+                int stage = 0; uint32_t phase = 0;
+                for (int pb = pb0; pb < pb1; ++pb) {
+                    mbar_wait(&full[stage], phase, p.err_flag, 13);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {       // 32 pixels = 4 MMAs of K = 8
+                        const uint64_t ad = make_smem_desc(sa + j * 1024, 4096, 1024);
+                        const uint64_t bd = make_smem_desc(sb + j * 1024, 4096, 1024);
+                        mma_tf32(tmem_base, ad, bd, idesc, (pb != pb0) || j != 0);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[0]);
+            }
+        } else {
+            const int q = warp & 3;
+            const int row = q * 32 + lane;
+            const bool store_thread = threadIdx.x == 64;
+            mbar_wait(&tfull[0], 0, p.err_flag, 14);
+            tc_fence_after();
+            int ebuf = 0;
+#pragma unroll 1
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + chunk * 32, r);
+                tmem_ld_wait();
+                uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
+                if (store_thread) tma_store_wait_read<1>();
+                named_bar_sync_epi();
+                store_row_swizzled(buf, row, r);
+                fence_proxy_async();
+                named_bar_sync_epi();
+                if (store_thread) {
+                    tma_reduce_add_2d(&maps.d, buf, tap * p.cin + n0 + chunk * 32, m0);
+                    tma_store_commit();
+                }
+                ebuf ^= 1;
+            }
+            if (store_thread) tma_store_wait_all<0>();
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc<BN < 32 ? 32 : BN>(tmem_base); }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    });
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch = pitch_elems), box (box_cols<=32, box_rows)
+int encode_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t box_cols,
+              uint32_t box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 4};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(2d cols=%llu rows=%llu pitch=%llu box=%u,%u) failed: %d",
+                                          (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems, box_cols, box_rows, (int)r); return TF_ERR_CUDA; }
+    return TF_OK;
+}
+// 4-D NHWC fp32 tensor viewed as (C, W, H, B), box (bc<=32, bw, bh, 1)
+int encode_4d(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t bc, uint32_t bw,
+              uint32_t bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
+    cuuint32_t box[4] = {bc, bw, bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(4d C=%llu W=%llu H=%llu B=%llu box=%u,%u,%u) failed: %d",
+                                          (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, bc, bw, bh, (int)r); return TF_ERR_CUDA; }
+    return TF_OK;
+}
+
+void pick_tile(int W, int H, int area, int* tw, int* th) {
+    long long best = -1;
+    for (int w = area; w >= 1; w >>= 1) {
+        const int h = area / w;
+        if (w > 256 || h > 256) continue;
+        const long long cover = (long long)((W + w - 1) / w) * w * ((H + h - 1) / h) * h;
+        if (best < 0 || cover < best || (cover == best && w > *tw && w <= 32)) { best = cover; *tw = w; *th = h; }
+    }
+}
+
+int g_num_sms = 0;
+int* g_err_flag = nullptr;
+int ensure_device_state() {
+    if (g_num_sms == 0) {
+        int dev;
+        TF_CHECK_CUDA(cudaGetDevice(&dev));
+        TF_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        TF_CHECK_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
+        TF_CHECK_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+    }
+    return TF_OK;
+}
+
+template <int BN>
+int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+template <int BN>
+int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = p.m_tiles * p.n_tiles * p.taps * p.splits;
+    conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+}  // namespace
+
+// y[B,H,W,Cout] = conv(x[B,H,W,Cin], w) with stride 1 and "same" zero padding, NHWC fp32.
+//   w_packed : [Cout][ksize*ksize][Cin]  (tap-major K), Cout and Cin multiples of 32 (Cout multiple of 64)
+//   x_lo / w_lo (both or neither): low-order TF32 split parts for the 3-product parity mode
+//   bias: optional [Cout].  Also serves as dgrad (flipped taps, transposed weights) and as a plain
+//   row-major GEMM  y[M,Cout] = x[M,Cin] * w[Cout,Cin]^T  (ksize 1, B=1, H=1, W=M).
+TF_API int tf_conv2d_nhwc(const float* x, const float* x_lo, int B, int H, int W, int Cin, const float* w_packed,
+                          const float* w_lo, int Cout, int ksize, const float* bias, float* y, void* stream) {
+    TF_REQUIRE(x && w_packed && y, "tf_conv2d_nhwc: null pointer");
+    TF_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "tf_conv2d_nhwc: x_lo and w_lo must be given together");
+    TF_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 32 == 0 && Cout >= 64 && Cout % 64 == 0,
+               "tf_conv2d_nhwc: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
+    TF_REQUIRE(ksize == 1 || ksize == 3, "tf_conv2d_nhwc: ksize must be 1 or 3");
+    int rc = ensure_device_state();
+    if (rc) return rc;
+    const int BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
+    const int taps = ksize * ksize;
+    GemmMaps maps;
+    GemmParams p = {};
+    p.taps = taps; p.kblocks = Cin / 32; p.nseg = x_lo ? 3 : 1;
+    p.bias = bias; p.err_flag = g_err_flag;
+    p.num_n_tiles = Cout / BN;
+    const float* as[3] = {x, x_lo, x};
+    const float* bs[3] = {w_packed, w_packed, w_lo};
+    const long long M = (long long)B * H * W;
+    if (ksize == 1) {
+        p.spatial = 0;
+        p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+        p.tiles_x = p.tiles_y = 1; p.tw = 128; p.th = 1;
+        for (int s = 0; s < p.nseg; ++s)
+            if ((rc = encode_2d(&maps.a[s], as[s], Cin, M, Cin, 32, BLOCK_M))) return rc;
+        if ((rc = encode_2d(&maps.d, y, Cout, M, Cout, 32, BLOCK_M))) return rc;
+    } else {
+        p.spatial = 1;
+        pick_tile(W, H, BLOCK_M, &p.tw, &p.th);
+        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
+        p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+        for (int s = 0; s < p.nseg; ++s)
+            if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th))) return rc;
+        if ((rc = encode_4d(&maps.d, y, Cout, W, H, B, 32, p.tw, p.th))) return rc;
+    }
+    for (int s = 0; s < p.nseg; ++s)
+        if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN == 256) return launch_gemm<256>(maps, p, st);
+    if (BN == 128) return launch_gemm<128>(maps, p, st);
+    return launch_gemm<64>(maps, p, st);
+}
+
+// dw_packed[Cout][ksize*ksize][Cin] += sum_pixels dy[pixel, co] * x[pixel (+) tap, ci]   (caller zeroes dw_packed)
+TF_API int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
+                                float* dw_packed, void* stream) {
+    TF_REQUIRE(x && dy && dw_packed, "tf_conv2d_wgrad_nhwc: null pointer");
+    TF_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0,
+               "tf_conv2d_wgrad_nhwc: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
+    TF_REQUIRE(ksize == 1 || ksize == 3, "tf_conv2d_wgrad_nhwc: ksize must be 1 or 3");
+    int rc = ensure_device_state();
+    if (rc) return rc;
+    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+    WgradMaps maps;
+    WgradParams p = {};
+    p.taps = ksize * ksize; p.cin = Cin; p.err_flag = g_err_flag;
+    p.m_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = (Cin + BN - 1) / BN;
+    const long long M = (long long)B * H * W;
+    if (ksize == 1) {
+        p.spatial = 0; p.tiles_x = p.tiles_y = 1; p.tw = 32; p.th = 1;
+        p.num_pblocks = (int)((M + 31) / 32);
+        if ((rc = encode_2d(&maps.a, dy, Cout, M, Cout, 32, 32))) return rc;
+        if ((rc = encode_2d(&maps.b, x, Cin, M, Cin, 32, 32))) return rc;
+    } else {
+        p.spatial = 1;
+        pick_tile(W, H, 32, &p.tw, &p.th);
+        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
+        p.num_pblocks = B * p.tiles_x * p.tiles_y;
+        if ((rc = encode_4d(&maps.a, dy, Cout, W, H, B, 32, p.tw, p.th))) return rc;
+        if ((rc = encode_4d(&maps.b, x, Cin, W, H, B, 32, p.tw, p.th))) return rc;
+    }
+    if ((rc = encode_2d(&maps.d, dw_packed, (uint64_t)p.taps * Cin, Cout, (uint64_t)p.taps * Cin, 32, BLOCK_M))) return rc;
+    const int units = p.m_tiles * p.n_tiles * p.taps;
+    int splits = (2 * g_num_sms + units - 1) / units;
+    if (splits > p.num_pblocks) splits = p.num_pblocks;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (BN == 256) return launch_wgrad<256>(maps, p, st);
+    if (BN == 128) return launch_wgrad<128>(maps, p, st);
+    return launch_wgrad<64>(maps, p, st);
+}
+
+// Reads (and clears) the device-side pipeline error flag set by a timed-out mbarrier wait.
+TF_API int tf_gemm_error_flag(int* value) {
+    TF_REQUIRE(value, "tf_gemm_error_flag: null");
+    *value = 0;
+    if (!g_err_flag) return TF_OK;
+    TF_CHECK_CUDA(cudaMemcpy(value, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    TF_CHECK_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+    return TF_OK;
+}

@@ -1,0 +1,286 @@
+// Greedy NMS, bit-exact with torchvision.ops.nms on CPU (the op the reference calls at
+// /root/reference/tinyfaces/evaluation.py:84 on float64 CPU tensors).
+//
+//   1. stable descending radix sort of the scores (payload = original index)
+//   2. score-sorted boxes are processed in blocks of NB:
+//        a. boxes of the block are tested against every box kept by earlier blocks
+//        b. the block's upper-triangular suppression bit-matrix is built in parallel
+//        c. one CTA walks the block in 64-box chunks: the diagonal 64x64 bit block is
+//           resolved serially, the kept rows are OR-ed into the running "removed" vector
+//   3. kept original indices are emitted in descending-score order.
+//
+// Every IoU is evaluated with the reference's operation order in the input precision with
+// explicit round-to-nearest intrinsics (no FMA contraction), so keep indices are identical.
+// HBM-bound for N <~ 1e4, pair-test (ALU) bound above.
+#include "tf_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+constexpr int NB = 32768;        // sorted boxes per block
+constexpr int COLS_PER_CTA = 256;
+
+template <typename T> struct Arith;
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+
+template <typename T> struct alignas(4 * sizeof(T)) Box { T x1, y1, x2, y2; };
+
+// torchvision nms_kernel_impl: ovr = inter / (iarea + jarea - inter); suppress iff ovr > thr
+template <typename T>
+__device__ __forceinline__ bool suppresses(const Box<T>& a, T aa, const Box<T>& b, T ba, double thr,
+                                           bool prefilter) {
+    using A = Arith<T>;
+    T xx1 = a.x1 > b.x1 ? a.x1 : b.x1;       // std::max(ix1, x1[j])
+    T yy1 = a.y1 > b.y1 ? a.y1 : b.y1;
+    T xx2 = b.x2 < a.x2 ? b.x2 : a.x2;       // std::min(ix2, x2[j])
+    T yy2 = b.y2 < a.y2 ? b.y2 : a.y2;
+    T w = A::sub(xx2, xx1), h = A::sub(yy2, yy1);
+    // thr >= 0: a pair without positive overlap has ovr == 0 or NaN and can never suppress
+    if (prefilter && !(w > (T)0 && h > (T)0)) return false;
+    w = w > (T)0 ? w : (T)0;                 // std::max(0, w)
+    h = h > (T)0 ? h : (T)0;
+    T inter = A::mul(w, h);
+    T ovr = A::div(inter, A::sub(A::add(aa, ba), inter));
+    return (double)ovr > thr;
+}
+
+__global__ void iota_kernel(int* v, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+
+template <typename T>
+__global__ void gather_sorted_kernel(const T* __restrict__ boxes, const int* __restrict__ order, int n,
+                                     Box<T>* __restrict__ sb, T* __restrict__ area) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Box<T> b = reinterpret_cast<const Box<T>*>(boxes)[order[i]];
+    sb[i] = b;
+    area[i] = Arith<T>::mul(Arith<T>::sub(b.x2, b.x1), Arith<T>::sub(b.y2, b.y1));
+}
+
+// (a) test the block's boxes against everything kept so far (count read from device memory)
+template <typename T>
+__global__ void suppress_by_kept_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area, int start,
+                                        int nb, const Box<T>* __restrict__ kept, const T* __restrict__ kept_area,
+                                        const int* __restrict__ kept_count, unsigned char* __restrict__ dead,
+                                        double thr, bool prefilter) {
+    __shared__ Box<T> s_box[256];
+    __shared__ T s_area[256];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = *kept_count;
+    Box<T> me = {};
+    T ma = 0;
+    if (j < nb) { me = sb[start + j]; ma = area[start + j]; }
+    bool gone = false;
+    for (int base = 0; base < K; base += 256) {
+        const int cnt = min(256, K - base);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) { s_box[threadIdx.x] = kept[base + threadIdx.x]; s_area[threadIdx.x] = kept_area[base + threadIdx.x]; }
+        __syncthreads();
+        if (j < nb && !gone) {
+            for (int k = 0; k < cnt; ++k)
+                if (suppresses<T>(s_box[k], s_area[k], me, ma, thr, prefilter)) { gone = true; break; }
+        }
+        if (__syncthreads_and(gone || j >= nb)) break;
+    }
+    if (j < nb) dead[j] = gone ? 1 : 0;
+}
+
+// (b) upper-triangular suppression bit matrix of the block: mask[row][word], 64 rows x 256 columns per CTA
+template <typename T>
+__global__ void __launch_bounds__(64) mask_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area,
+                                                  int start, int nb, const unsigned char* __restrict__ dead,
+                                                  unsigned long long* __restrict__ mask, int words_per_row,
+                                                  double thr, bool prefilter) {
+    const int rc = blockIdx.y, cg = blockIdx.x;
+    if (cg * COLS_PER_CTA + COLS_PER_CTA - 1 < rc * 64) return;       // strictly below the diagonal
+    __shared__ Box<T> s_box[COLS_PER_CTA];
+    __shared__ T s_area[COLS_PER_CTA];
+    for (int c = threadIdx.x; c < COLS_PER_CTA; c += 64) {
+        int j = cg * COLS_PER_CTA + c;
+        if (j < nb) { s_box[c] = sb[start + j]; s_area[c] = area[start + j]; }
+    }
+    __syncthreads();
+    const int r = rc * 64 + threadIdx.x;
+    if (r >= nb || dead[r]) return;            // rows of dead boxes are never read by the scan
+    const Box<T> me = sb[start + r];
+    const T ma = area[start + r];
+    unsigned long long w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned long long bits = 0;
+        const int j0 = cg * COLS_PER_CTA + q * 64;
+        if (j0 + 63 > r) {
+            const int lim = min(64, nb - j0);
+            for (int c = 0; c < lim; ++c) {
+                if (j0 + c > r && suppresses<T>(me, ma, s_box[q * 64 + c], s_area[q * 64 + c], thr, prefilter))
+                    bits |= 1ull << c;
+            }
+        }
+        w[q] = bits;
+    }
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(mask + (size_t)r * words_per_row + cg * 4);
+    dst[0] = make_ulonglong2(w[0], w[1]);
+    dst[1] = make_ulonglong2(w[2], w[3]);
+}
+
+// (c) sequential resolve of one block, 64-box chunk at a time (single CTA)
+template <typename T>
+__global__ void __launch_bounds__(1024) scan_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area,
+                                                    const int* __restrict__ order, int start, int nb,
+                                                    const unsigned char* __restrict__ dead,
+                                                    const unsigned long long* __restrict__ mask, int words_per_row,
+                                                    long long* __restrict__ keep_out, Box<T>* __restrict__ kept,
+                                                    T* __restrict__ kept_area, int* __restrict__ kept_count) {
+    __shared__ unsigned long long removed[NB / 64];
+    __shared__ unsigned long long diag[64];
+    __shared__ unsigned long long s_kept;
+    const int tid = threadIdx.x;
+    const int nchunks = (nb + 63) / 64;
+    for (int wd = tid; wd < nchunks; wd += blockDim.x) {
+        unsigned long long bits = 0;
+        for (int b = 0; b < 64; ++b) {
+            int j = wd * 64 + b;
+            if (j >= nb || dead[j]) bits |= 1ull << b;
+        }
+        removed[wd] = bits;
+    }
+    int K = *kept_count;
+    for (int c = 0; c < nchunks; ++c) {
+        __syncthreads();
+        if (removed[c] == ~0ull) continue;                 // whole chunk already gone (uniform branch)
+        if (tid < 64) {
+            int r = c * 64 + tid;
+            diag[tid] = (r < nb && !((removed[c] >> tid) & 1ull)) ? mask[(size_t)r * words_per_row + c] : 0ull;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long word = removed[c], kb = 0;
+            for (int i = 0; i < 64; ++i)
+                if (!((word >> i) & 1ull)) { kb |= 1ull << i; word |= diag[i]; }
+            s_kept = kb;
+        }
+        __syncthreads();
+        const unsigned long long kb = s_kept;
+        if (tid < 64 && ((kb >> tid) & 1ull)) {
+            const int pos = K + __popcll(kb & ((1ull << tid) - 1ull));
+            const int g = start + c * 64 + tid;
+            keep_out[pos] = order[g];
+            kept[pos] = sb[g];
+            kept_area[pos] = area[g];
+        }
+        for (int wd = c + 1 + tid; wd < nchunks; wd += blockDim.x) {
+            unsigned long long acc = removed[wd], rest = kb;
+            while (rest) {
+                const int i = __ffsll((long long)rest) - 1;
+                rest &= rest - 1;
+                acc |= mask[(size_t)(c * 64 + i) * words_per_row + wd];
+            }
+            removed[wd] = acc;
+        }
+        K += __popcll(kb);
+    }
+    __syncthreads();
+    if (tid == 0) *kept_count = K;
+}
+
+__global__ void count_to_i64_kernel(const int* c, long long* out) { *out = *c; }
+
+template <typename T>
+struct Plan {
+    size_t cub_bytes = 0, total = 0;
+    int rows, words_per_row;
+    Plan(int64_t n) {
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const T*)nullptr, (T*)nullptr,
+                                                  (const int*)nullptr, (int*)nullptr, (int)n);
+        rows = (int)(n < NB ? n : NB);
+        words_per_row = (int)tf_align_up((size_t)(rows + 63) / 64, 4);
+        size_t a = 0;
+        auto add = [&](size_t b) { a = tf_align_up(a, 256) + b; };
+        add(sizeof(int) * n); add(sizeof(int) * n);                 // iota, order
+        add(sizeof(T) * n);                                          // sorted keys
+        add(cub_bytes);
+        add(sizeof(Box<T>) * n); add(sizeof(T) * n);                 // sorted boxes, areas
+        add(sizeof(Box<T>) * n); add(sizeof(T) * n);                 // kept boxes, areas
+        add((size_t)rows);                                           // dead flags
+        add((size_t)rows * words_per_row * 8);                       // bit matrix
+        add(256);                                                    // counter
+        total = a + 256;
+    }
+};
+
+template <typename T>
+int run_nms(const void* boxes, const void* scores, int64_t n, double thr, long long* keep, long long* num_keep,
+            void* ws, size_t ws_bytes, cudaStream_t st) {
+    Plan<T> plan(n);
+    if (ws_bytes < plan.total) { tf_set_error("tf_nms: workspace %zu < required %zu", ws_bytes, plan.total); return TF_ERR_WORKSPACE; }
+    TfArena ar(ws, ws_bytes);
+    int* iota = ar.take<int>(n);
+    int* order = ar.take<int>(n);
+    T* keys = ar.take<T>(n);
+    void* cub_tmp = ar.take<char>(plan.cub_bytes);
+    Box<T>* sb = ar.take<Box<T>>(n);
+    T* area = ar.take<T>(n);
+    Box<T>* kept = ar.take<Box<T>>(n);
+    T* kept_area = ar.take<T>(n);
+    unsigned char* dead = ar.take<unsigned char>(plan.rows);
+    unsigned long long* mask = ar.take<unsigned long long>((size_t)plan.rows * plan.words_per_row);
+    int* counter = ar.take<int>(64);
+    const bool prefilter = thr >= 0.0;
+    const int ni = (int)n;
+    TF_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    iota_kernel<<<(ni + 255) / 256, 256, 0, st>>>(iota, ni);
+    size_t cb = plan.cub_bytes;
+    TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, cb, (const T*)scores, keys, (const int*)iota, order,
+                                                            ni, 0, (int)sizeof(T) * 8, st));
+    gather_sorted_kernel<T><<<(ni + 255) / 256, 256, 0, st>>>((const T*)boxes, order, ni, sb, area);
+    for (int start = 0; start < ni; start += NB) {
+        const int nb = min(NB, ni - start);
+        if (start == 0) {
+            TF_CHECK_CUDA(cudaMemsetAsync(dead, 0, nb, st));
+        } else {
+            suppress_by_kept_kernel<T><<<(nb + 255) / 256, 256, 0, st>>>(sb, area, start, nb, kept, kept_area, counter,
+                                                                        dead, thr, prefilter);
+        }
+        dim3 grid((nb + COLS_PER_CTA - 1) / COLS_PER_CTA, (nb + 63) / 64);
+        mask_kernel<T><<<grid, 64, 0, st>>>(sb, area, start, nb, dead, mask, plan.words_per_row, thr, prefilter);
+        scan_kernel<T><<<1, 1024, 0, st>>>(sb, area, order, start, nb, dead, mask, plan.words_per_row, keep, kept,
+                                           kept_area, counter);
+    }
+    count_to_i64_kernel<<<1, 1, 0, st>>>(counter, num_keep);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+}  // namespace
+
+TF_API int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes) {
+    TF_REQUIRE(bytes && n >= 0 && n < (1ll << 31) && (elem_bytes == 8 || elem_bytes == 4), "tf_nms_workspace_bytes: bad args");
+    if (n == 0) { *bytes = 256; return TF_OK; }
+    *bytes = elem_bytes == 8 ? Plan<double>(n).total : Plan<float>(n).total;
+    return TF_OK;
+}
+
+TF_API int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold,
+                  int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
+    TF_REQUIRE(n >= 0 && n < (1ll << 31) && (elem_bytes == 8 || elem_bytes == 4), "tf_nms: bad args");
+    TF_REQUIRE(num_keep, "tf_nms: num_keep is null");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { TF_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st)); return TF_OK; }
+    TF_REQUIRE(boxes && scores && keep && workspace, "tf_nms: null pointer");
+    if (elem_bytes == 8)
+        return run_nms<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
+    return run_nms<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
+}

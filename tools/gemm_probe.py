@@ -1,0 +1,77 @@
+"""First-contact probe for the tcgen05 kernels: every configuration runs in its own subprocess with a
+timeout (a trapped kernel poisons its CUDA context), results go to gpurun_out/gemm_probe.jsonl."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tiny-faces-pytorch_b200"))
+sys.path.insert(0, ROOT)
+
+CASES = [
+    ("fprop", 1, 8, 16, 32, 64, 1), ("fprop", 1, 8, 16, 32, 128, 1), ("fprop", 1, 8, 16, 32, 256, 1),
+    ("fprop", 2, 17, 23, 64, 128, 1), ("fprop", 1, 30, 40, 256, 256, 1), ("fprop", 1, 8, 16, 32, 64, 3),
+    ("fprop", 2, 15, 20, 256, 256, 3),
+    ("wgrad", 1, 8, 16, 32, 64, 1), ("wgrad", 1, 8, 16, 128, 128, 1), ("wgrad", 2, 17, 23, 256, 256, 1),
+    ("wgrad", 1, 8, 16, 32, 64, 3), ("wgrad", 2, 15, 20, 256, 256, 3),
+]
+
+
+def run_case(kind, B, H, W, Cin, Cout, k):
+    import torch
+    from tinyfaces_b200 import ops
+    d = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(1)
+
+    def tf32(t):
+        i = t.contiguous().view(torch.int32)
+        return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    x = tf32(torch.randn(B, Cin, H, W, generator=gen))
+    res = dict(kind=kind, shape=[B, H, W, Cin, Cout, k])
+    if kind == "fprop":
+        w = tf32(torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5)
+        ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=k // 2).float()
+        y = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(d),
+                            w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous().to(d), k)
+        torch.cuda.synchronize()
+        got = y.cpu().permute(0, 3, 1, 2)
+    else:
+        dy = tf32(torch.randn(B, Cout, H, W, generator=gen))
+        w = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+        torch.nn.functional.conv2d(x.double(), w, padding=k // 2).backward(dy.double())
+        ref = w.grad.float()
+        dw = ops.conv2d_wgrad_nhwc(x.permute(0, 2, 3, 1).contiguous().to(d), dy.permute(0, 2, 3, 1).contiguous().to(d), k)
+        torch.cuda.synchronize()
+        got = dw.cpu().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    diff = (got - ref).abs()
+    res["rel_err"] = diff.max().item() / ref.abs().max().item()
+    res["frac_bad"] = (diff > 1e-3 * ref.abs().max()).float().mean().item()
+    res["got_absmax"] = got.abs().max().item()
+    res["ref_absmax"] = ref.abs().max().item()
+    res["flag"] = ops.gemm_error_flag()
+    # a few samples to diagnose layout mistakes
+    res["got0"] = got.flatten()[:6].tolist()
+    res["ref0"] = ref.flatten()[:6].tolist()
+    return res
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        args = json.loads(sys.argv[1])
+        print("RESULT " + json.dumps(run_case(*args)))
+        sys.exit(0)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "gemm_probe.jsonl"), "w") as f:
+        for c in CASES:
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), json.dumps(c)], capture_output=True,
+                                   text=True, timeout=180)
+                line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+                rec = json.loads(line[0][7:]) if line else dict(case=c, rc=r.returncode, err=r.stderr[-1500:])
+            except subprocess.TimeoutExpired:
+                rec = dict(case=c, timeout=True)
+            f.write(json.dumps(rec) + "\n")
+            f.flush()
+            print(json.dumps(rec)[:400])
