@@ -43,7 +43,10 @@ struct GemmParams {
     int spatial;                  // 0: A/D are 2-D [pixels, C]; 1: 4-D (C, W, H, B) with spatial tiles
     int tiles_x, tiles_y, tw, th; // spatial tiling of one image (tw * th == 128)
     int taps, kblocks, nseg;      // K loop = nseg x taps x kblocks blocks of 32 channels
-    const float* bias;            // optional per-output-channel bias
+    const float* scale;           // optional per-output-channel epilogue: v = v * scale[n] + shift[n]
+    const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
+    int relu, round_out;
+    int accumulate;               // 1: D += result (TMA reduce-add) instead of D = result
     int* err_flag;
 };
 
@@ -186,9 +189,17 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chunk * 32, r);
                 tmem_ld_wait();
                 if (chunk == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
-                if (p.bias) {
+                if (p.scale || p.shift || p.relu || p.round_out) {
+                    const int nb = n0 + chunk * 32;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + n0 + chunk * 32 + j));
+                    for (int j = 0; j < 32; ++j) {
+                        float v = __uint_as_float(r[j]);
+                        if (p.scale) v *= __ldg(p.scale + nb + j);
+                        if (p.shift) v += __ldg(p.shift + nb + j);
+                        if (p.relu) v = fmaxf(v, 0.f);
+                        if (p.round_out) v = tf_round_tf32(v);
+                        r[j] = __float_as_uint(v);
+                    }
                 }
                 uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
                 if (store_thread) tma_store_wait_read<1>();      // the store that last used this buffer has drained
@@ -197,8 +208,13 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 fence_proxy_async();
                 named_bar_sync_epi();
                 if (store_thread) {
-                    if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0, y0, img);
-                    else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                    if (p.accumulate) {
+                        if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0, y0, img);
+                        else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                    } else {
+                        if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0, y0, img);
+                        else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                    }
                     tma_store_commit();
                 }
                 ebuf ^= 1;
@@ -211,12 +227,13 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
-struct WgradMaps { CUtensorMap a, b, d; };     // a: dY (Cout, pixels), b: X (Cin, pixels), d: dW [Cout, taps*Cin]
+struct WgradMaps { CUtensorMap a[MAX_SEG], b[MAX_SEG], d; };   // a: dY (Cout, pixels), b: X (Cin, pixels), d: dW [Cout, taps*Cin]
 struct WgradParams {
-    int m_tiles, n_tiles, taps, splits;
+    int m_tiles, n_tiles, taps, splits, nseg;
     int spatial, tiles_x, tiles_y, tw, th;     // pixel blocks of 32: flat or (tw x th) patches of one image
     int num_pblocks;                            // total pixel blocks
     int cin;                                    // column offset of a tap in dW = tap * cin
+    int plain_store;                            // debug: overwrite instead of reduce-add (needs splits == 1)
     int* err_flag;
 };
 
@@ -235,7 +252,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
-        prefetch_tmap(&maps.a); prefetch_tmap(&maps.b); prefetch_tmap(&maps.d);
+        for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&maps.a[s]); prefetch_tmap(&maps.b[s]); }
+        prefetch_tmap(&maps.d);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&tfull[0], 1);
         fence_barrier_init();
@@ -259,7 +277,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         if (warp == 0) {
             if (lane == 0) {
                 int stage = 0; uint32_t phase = 0;
-                for (int pb = pb0; pb < pb1; ++pb) {
+                for (int pb = pb0; pb < pb1; ++pb)
+                for (int seg = 0; seg < p.nseg; ++seg) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 11);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
@@ -268,14 +287,14 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                         const int img = pb / tiles_per_img, r = pb % tiles_per_img;
                         const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
 #pragma unroll
-                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_4d(sa + i * 4096, &maps.a, &full[stage], m0 + i * 32, x0, y0, img);
+                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_4d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, x0, y0, img);
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &maps.b, &full[stage], n0 + j * 32, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &maps.b[seg], &full[stage], n0 + j * 32, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(sa + i * 4096, &maps.a, &full[stage], m0 + i * 32, pb * 32);
+                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, pb * 32);
 #pragma unroll
-                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &maps.b, &full[stage], n0 + j * 32, pb * 32);
+                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &maps.b[seg], &full[stage], n0 + j * 32, pb * 32);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -284,16 +303,19 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             if (lane == 0) {
                 constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN, MAJOR_MN, MAJOR_MN);
                 int stage = 0; uint32_t phase = 0;
-                for (int pb = pb0; pb < pb1; ++pb) {
+                for (int pb = pb0; pb < pb1; ++pb)
+                for (int seg = 0; seg < p.nseg; ++seg) {
                     mbar_wait(&full[stage], phase, p.err_flag, 13);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {       // 32 pixels = 4 MMAs of K = 8
-                        const uint64_t ad = make_smem_desc(sa + j * 1024, 4096, 1024);
-                        const uint64_t bd = make_smem_desc(sb + j * 1024, 4096, 1024);
-                        mma_tf32(tmem_base, ad, bd, idesc, (pb != pb0) || j != 0);
+                        // MN-major tf32: 32 channels (128 B) x 32 pixel rows per TMA box, SWIZZLE_128B_BASE32B atoms of
+                        // 4 rows: LBO = next 32-channel box (4096 B), SBO = next 4-row group (512 B), K step = 8 rows
+                        const uint64_t ad = make_smem_desc(sa + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                        const uint64_t bd = make_smem_desc(sb + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                        mma_tf32(tmem_base, ad, bd, idesc, (pb != pb0) || seg != 0 || j != 0);
                     }
                     tc_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -319,7 +341,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 fence_proxy_async();
                 named_bar_sync_epi();
                 if (store_thread) {
-                    tma_reduce_add_2d(&maps.d, buf, tap * p.cin + n0 + chunk * 32, m0);
+                    if (p.plain_store) tma_store_2d(&maps.d, buf, tap * p.cin + n0 + chunk * 32, m0);
+                    else               tma_reduce_add_2d(&maps.d, buf, tap * p.cin + n0 + chunk * 32, m0);
                     tma_store_commit();
                 }
                 ebuf ^= 1;
@@ -352,7 +375,7 @@ EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor [rows, cols] (cols contiguous, row pitch = pitch_elems), box (box_cols<=32, box_rows)
 int encode_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t pitch_elems, uint32_t box_cols,
-              uint32_t box_rows) {
+              uint32_t box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
     cuuint64_t dims[2] = {cols, rows};
@@ -360,7 +383,7 @@ int encode_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uin
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(2d cols=%llu rows=%llu pitch=%llu box=%u,%u) failed: %d",
                                           (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_elems, box_cols, box_rows, (int)r); return TF_ERR_CUDA; }
@@ -368,7 +391,7 @@ int encode_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uin
 }
 // 4-D NHWC fp32 tensor viewed as (C, W, H, B), box (bc<=32, bw, bh, 1)
 int encode_4d(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t bc, uint32_t bw,
-              uint32_t bh) {
+              uint32_t bh, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
     cuuint64_t dims[4] = {C, W, H, B};
@@ -376,7 +399,7 @@ int encode_4d(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t 
     cuuint32_t box[4] = {bc, bw, bh, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(4d C=%llu W=%llu H=%llu B=%llu box=%u,%u,%u) failed: %d",
                                           (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, bc, bw, bh, (int)r); return TF_ERR_CUDA; }
@@ -434,7 +457,112 @@ int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
     return TF_OK;
 }
 
+int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
 }  // namespace
+
+TF_API int tf_debug_set(int key, int value) {
+    TF_REQUIRE(key >= 0 && key < 8, "tf_debug_set: bad key");
+    g_debug[key] = value;
+    return TF_OK;
+}
+
+#include "tf_conv_gemm.h"
+namespace tfg {
+
+int conv_fprop(const ConvArgs& a, cudaStream_t st) {
+    TF_REQUIRE(a.x && a.w && a.y, "conv_fprop: null pointer");
+    TF_REQUIRE((a.x_lo == nullptr) == (a.w_lo == nullptr), "conv_fprop: x_lo and w_lo must be given together");
+    TF_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.Cin > 0 && a.Cin % 32 == 0 && a.Cout >= 64 && a.Cout % 64 == 0,
+               "conv_fprop: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", a.B, a.H, a.W, a.Cin, a.Cout);
+    TF_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_fprop: ksize must be 1 or 3");
+    int rc = ensure_device_state();
+    if (rc) return rc;
+    const int B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout;
+    const int BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
+    const int taps = a.ksize * a.ksize;
+    GemmMaps maps;
+    GemmParams p = {};
+    p.taps = taps; p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
+    p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
+    p.accumulate = a.accumulate || g_debug[1];
+    p.err_flag = g_err_flag;
+    p.num_n_tiles = Cout / BN;
+    const float* as[3] = {a.x, a.x_lo, a.x};
+    const float* bs[3] = {a.w, a.w, a.w_lo};
+    const long long M = (long long)B * H * W;
+    if (a.ksize == 1) {
+        p.spatial = 0;
+        p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+        p.tiles_x = p.tiles_y = 1; p.tw = 128; p.th = 1;
+        for (int s = 0; s < p.nseg; ++s)
+            if ((rc = encode_2d(&maps.a[s], as[s], Cin, M, Cin, 32, BLOCK_M))) return rc;
+        if ((rc = encode_2d(&maps.d, a.y, Cout, M, Cout, 32, BLOCK_M))) return rc;
+    } else {
+        p.spatial = 1;
+        pick_tile(W, H, BLOCK_M, &p.tw, &p.th);
+        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
+        p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+        for (int s = 0; s < p.nseg; ++s)
+            if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th))) return rc;
+        if ((rc = encode_4d(&maps.d, a.y, Cout, W, H, B, 32, p.tw, p.th))) return rc;
+    }
+    for (int s = 0; s < p.nseg; ++s)
+        if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
+    if (BN == 256) return launch_gemm<256>(maps, p, st);
+    if (BN == 128) return launch_gemm<128>(maps, p, st);
+    return launch_gemm<64>(maps, p, st);
+}
+
+int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
+    TF_REQUIRE(a.x && a.dy && a.dw, "conv_wgrad: null pointer");
+    TF_REQUIRE((a.x_lo == nullptr) == (a.dy_lo == nullptr), "conv_wgrad: x_lo and dy_lo must be given together");
+    TF_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.Cin > 0 && a.Cin % 32 == 0 && a.Cout > 0 && a.Cout % 32 == 0,
+               "conv_wgrad: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", a.B, a.H, a.W, a.Cin, a.Cout);
+    TF_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_wgrad: ksize must be 1 or 3");
+    int rc = ensure_device_state();
+    if (rc) return rc;
+    const int B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout;
+    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+    WgradMaps maps;
+    WgradParams p = {};
+    p.taps = a.ksize * a.ksize; p.cin = Cin; p.err_flag = g_err_flag;
+    p.nseg = a.x_lo ? 3 : 1;
+    p.m_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = (Cin + BN - 1) / BN;
+    const float* as[3] = {a.dy, a.dy_lo, a.dy};
+    const float* bs[3] = {a.x, a.x, a.x_lo};
+    const long long M = (long long)B * H * W;
+    if (a.ksize == 1) {
+        p.spatial = 0; p.tiles_x = p.tiles_y = 1; p.tw = 32; p.th = 1;
+        p.num_pblocks = (int)((M + 31) / 32);
+        for (int s = 0; s < p.nseg; ++s) {
+            if ((rc = encode_2d(&maps.a[s], as[s], Cout, M, Cout, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+            if ((rc = encode_2d(&maps.b[s], bs[s], Cin, M, Cin, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+        }
+    } else {
+        p.spatial = 1;
+        pick_tile(W, H, 32, &p.tw, &p.th);
+        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
+        p.num_pblocks = B * p.tiles_x * p.tiles_y;
+        for (int s = 0; s < p.nseg; ++s) {
+            if ((rc = encode_4d(&maps.a[s], as[s], Cout, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+            if ((rc = encode_4d(&maps.b[s], bs[s], Cin, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+        }
+    }
+    if ((rc = encode_2d(&maps.d, a.dw, (uint64_t)p.taps * Cin, Cout, (uint64_t)p.taps * Cin, 32, BLOCK_M))) return rc;
+    const int units = p.m_tiles * p.n_tiles * p.taps;
+    int splits = (2 * g_num_sms + units - 1) / units;
+    if (splits > p.num_pblocks) splits = p.num_pblocks;
+    if (splits < 1) splits = 1;
+    if (g_debug[0]) { splits = 1; p.plain_store = 1; }
+    p.splits = splits;
+    if (BN == 256) return launch_wgrad<256>(maps, p, st);
+    if (BN == 128) return launch_wgrad<128>(maps, p, st);
+    return launch_wgrad<64>(maps, p, st);
+}
+
+}  // namespace tfg
 
 // y[B,H,W,Cout] = conv(x[B,H,W,Cin], w) with stride 1 and "same" zero padding, NHWC fp32.
 //   w_packed : [Cout][ksize*ksize][Cin]  (tap-major K), Cout and Cin multiples of 32 (Cout multiple of 64)
@@ -443,86 +571,18 @@ int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
 //   row-major GEMM  y[M,Cout] = x[M,Cin] * w[Cout,Cin]^T  (ksize 1, B=1, H=1, W=M).
 TF_API int tf_conv2d_nhwc(const float* x, const float* x_lo, int B, int H, int W, int Cin, const float* w_packed,
                           const float* w_lo, int Cout, int ksize, const float* bias, float* y, void* stream) {
-    TF_REQUIRE(x && w_packed && y, "tf_conv2d_nhwc: null pointer");
-    TF_REQUIRE((x_lo == nullptr) == (w_lo == nullptr), "tf_conv2d_nhwc: x_lo and w_lo must be given together");
-    TF_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 32 == 0 && Cout >= 64 && Cout % 64 == 0,
-               "tf_conv2d_nhwc: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
-    TF_REQUIRE(ksize == 1 || ksize == 3, "tf_conv2d_nhwc: ksize must be 1 or 3");
-    int rc = ensure_device_state();
-    if (rc) return rc;
-    const int BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
-    const int taps = ksize * ksize;
-    GemmMaps maps;
-    GemmParams p = {};
-    p.taps = taps; p.kblocks = Cin / 32; p.nseg = x_lo ? 3 : 1;
-    p.bias = bias; p.err_flag = g_err_flag;
-    p.num_n_tiles = Cout / BN;
-    const float* as[3] = {x, x_lo, x};
-    const float* bs[3] = {w_packed, w_packed, w_lo};
-    const long long M = (long long)B * H * W;
-    if (ksize == 1) {
-        p.spatial = 0;
-        p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
-        p.tiles_x = p.tiles_y = 1; p.tw = 128; p.th = 1;
-        for (int s = 0; s < p.nseg; ++s)
-            if ((rc = encode_2d(&maps.a[s], as[s], Cin, M, Cin, 32, BLOCK_M))) return rc;
-        if ((rc = encode_2d(&maps.d, y, Cout, M, Cout, 32, BLOCK_M))) return rc;
-    } else {
-        p.spatial = 1;
-        pick_tile(W, H, BLOCK_M, &p.tw, &p.th);
-        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
-        p.num_m_tiles = B * p.tiles_x * p.tiles_y;
-        for (int s = 0; s < p.nseg; ++s)
-            if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th))) return rc;
-        if ((rc = encode_4d(&maps.d, y, Cout, W, H, B, 32, p.tw, p.th))) return rc;
-    }
-    for (int s = 0; s < p.nseg; ++s)
-        if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (BN == 256) return launch_gemm<256>(maps, p, st);
-    if (BN == 128) return launch_gemm<128>(maps, p, st);
-    return launch_gemm<64>(maps, p, st);
+    tfg::ConvArgs a = {};
+    a.x = x; a.x_lo = x_lo; a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+    a.w = w_packed; a.w_lo = w_lo; a.Cout = Cout; a.ksize = ksize; a.shift = bias; a.y = y;
+    return tfg::conv_fprop(a, (cudaStream_t)stream);
 }
 
 // dw_packed[Cout][ksize*ksize][Cin] += sum_pixels dy[pixel, co] * x[pixel (+) tap, ci]   (caller zeroes dw_packed)
 TF_API int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
                                 float* dw_packed, void* stream) {
-    TF_REQUIRE(x && dy && dw_packed, "tf_conv2d_wgrad_nhwc: null pointer");
-    TF_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cin % 32 == 0 && Cout > 0 && Cout % 32 == 0,
-               "tf_conv2d_wgrad_nhwc: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", B, H, W, Cin, Cout);
-    TF_REQUIRE(ksize == 1 || ksize == 3, "tf_conv2d_wgrad_nhwc: ksize must be 1 or 3");
-    int rc = ensure_device_state();
-    if (rc) return rc;
-    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
-    WgradMaps maps;
-    WgradParams p = {};
-    p.taps = ksize * ksize; p.cin = Cin; p.err_flag = g_err_flag;
-    p.m_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
-    p.n_tiles = (Cin + BN - 1) / BN;
-    const long long M = (long long)B * H * W;
-    if (ksize == 1) {
-        p.spatial = 0; p.tiles_x = p.tiles_y = 1; p.tw = 32; p.th = 1;
-        p.num_pblocks = (int)((M + 31) / 32);
-        if ((rc = encode_2d(&maps.a, dy, Cout, M, Cout, 32, 32))) return rc;
-        if ((rc = encode_2d(&maps.b, x, Cin, M, Cin, 32, 32))) return rc;
-    } else {
-        p.spatial = 1;
-        pick_tile(W, H, 32, &p.tw, &p.th);
-        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
-        p.num_pblocks = B * p.tiles_x * p.tiles_y;
-        if ((rc = encode_4d(&maps.a, dy, Cout, W, H, B, 32, p.tw, p.th))) return rc;
-        if ((rc = encode_4d(&maps.b, x, Cin, W, H, B, 32, p.tw, p.th))) return rc;
-    }
-    if ((rc = encode_2d(&maps.d, dw_packed, (uint64_t)p.taps * Cin, Cout, (uint64_t)p.taps * Cin, 32, BLOCK_M))) return rc;
-    const int units = p.m_tiles * p.n_tiles * p.taps;
-    int splits = (2 * g_num_sms + units - 1) / units;
-    if (splits > p.num_pblocks) splits = p.num_pblocks;
-    if (splits < 1) splits = 1;
-    p.splits = splits;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (BN == 256) return launch_wgrad<256>(maps, p, st);
-    if (BN == 128) return launch_wgrad<128>(maps, p, st);
-    return launch_wgrad<64>(maps, p, st);
+    tfg::WgradArgs a = {};
+    a.x = x; a.dy = dy; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.dw = dw_packed;
+    return tfg::conv_wgrad(a, (cudaStream_t)stream);
 }
 
 // Reads (and clears) the device-side pipeline error flag set by a timed-out mbarrier wait.

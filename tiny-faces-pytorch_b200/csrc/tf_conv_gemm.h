@@ -1,0 +1,24 @@
+// Internal C++ interface of the tcgen05 convolution GEMMs (tf_conv_gemm.cu), used by tf_model.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tfg {
+struct ConvArgs {
+    const float* x; const float* x_lo;     // NHWC input (+ low-order split part in 3xTF32 mode)
+    int B, H, W, Cin;
+    const float* w; const float* w_lo;     // packed [Cout][k*k][Cin]
+    int Cout, ksize;                       // stride 1, "same" padding
+    const float* scale; const float* shift;// optional per-channel epilogue (shift alone = bias)
+    int relu, round_out, accumulate;
+    float* y;                              // NHWC output
+};
+int conv_fprop(const ConvArgs& a, cudaStream_t st);
+
+struct WgradArgs {
+    const float* x; const float* x_lo;
+    const float* dy; const float* dy_lo;
+    int B, H, W, Cin, Cout, ksize;
+    float* dw;                             // packed [Cout][k*k][Cin], accumulated into
+};
+int conv_wgrad(const WgradArgs& a, cudaStream_t st);
+}  // namespace tfg

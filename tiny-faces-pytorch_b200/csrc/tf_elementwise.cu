@@ -1,0 +1,547 @@
+// HBM-bound NHWC fp32 kernels around the convolution GEMMs: BatchNorm statistics / apply / backward,
+// ReLU, residual add, max-pool, stem im2col, stride-2 subsample / zero-insert, weight (un)packing and the
+// head combine (bilinear 2x upsample + crop + add + NCHW transpose).  They replace the elementwise part
+// of /root/reference/tinyfaces/models/model.py:89-128 (torchvision Bottleneck.forward, resnet.py:143-163)
+// and its autograd backward.  All tensors are [pixels, C] with C % 4 == 0; accesses are float4.
+#include "tf_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+inline int ew_blocks(long long n, int per_thread = 1) {
+    long long b = (n + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
+    return (int)std::min<long long>(std::max<long long>(b, 1), 148LL * 32);
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// write v either rounded to tf32 (fast mode), or split into (hi, lo) (parity mode), or unchanged
+__device__ __forceinline__ void store_act(float* out, float* out_lo, long long i, float4 v, int mode) {
+    if (mode == 1) {
+        v.x = tf_round_tf32(v.x); v.y = tf_round_tf32(v.y); v.z = tf_round_tf32(v.z); v.w = tf_round_tf32(v.w);
+        st4(out + i, v);
+    } else if (mode == 2) {
+        float4 h = make_float4(hi_part(v.x), hi_part(v.y), hi_part(v.z), hi_part(v.w));
+        st4(out + i, h);
+        st4(out_lo + i, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+    } else {
+        st4(out + i, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel column reductions over [M, C]: partial[blk][k][C], k = 0..1
+//   mode 0: (sum y, sum y^2)                                  -- BN forward statistics
+//   mode 1: (sum g, sum g*xhat), g = dout (* [act > 0])       -- BN backward
+//   mode 2: (sum y, 0)                                        -- bias gradient
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                               const float* __restrict__ act,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, long long M, int C,
+                                                               float* __restrict__ partial) {
+    const int groups = C / 4;                       // float4 channel groups (<= 256)
+    const int lanes = EW_THREADS / groups;          // row lanes per block
+    const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+    float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
+    float4 mu = s0, rs = s0;
+    if (MODE == 1) { mu = ld4(mean + g * 4); rs = ld4(rstd + g * 4); }
+    if (rl < lanes) {
+        for (long long r = (long long)blockIdx.x * lanes + rl; r < M; r += (long long)gridDim.x * lanes) {
+            const long long i = r * C + g * 4;
+            float4 v = ld4(a + i);
+            if (MODE == 0) {
+                s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+                s1.x += v.x * v.x; s1.y += v.y * v.y; s1.z += v.z * v.z; s1.w += v.w * v.w;
+            } else if (MODE == 1) {
+                if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) v.x = 0.f; if (!(o.y > 0.f)) v.y = 0.f; if (!(o.z > 0.f)) v.z = 0.f; if (!(o.w > 0.f)) v.w = 0.f; }
+                float4 y = ld4(b + i);
+                s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+                s1.x += v.x * (y.x - mu.x) * rs.x; s1.y += v.y * (y.y - mu.y) * rs.y;
+                s1.z += v.z * (y.z - mu.z) * rs.z; s1.w += v.w * (y.w - mu.w) * rs.w;
+            } else {
+                s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+            }
+        }
+    }
+    __shared__ float4 sm0[EW_THREADS], sm1[EW_THREADS];
+    sm0[threadIdx.x] = s0; sm1[threadIdx.x] = s1;
+    __syncthreads();
+    if (rl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+            float4 t0 = sm0[l * groups + g], t1 = sm1[l * groups + g];
+            s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+            s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+        }
+        float* p = partial + (size_t)blockIdx.x * 2 * C;
+        st4(p + g * 4, s0);
+        st4(p + C + g * 4, s1);
+    }
+}
+
+// BN forward finalize (training): batch mean / biased var -> scale, shift, saved mean / rstd, running stats
+__global__ void bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                         float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
+                                         float* __restrict__ scale, float* __restrict__ shift,
+                                         float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0, q = 0;
+    for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+    const double mean = s / (double)M;
+    double var = q / (double)M - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = rstd;
+    if (run_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
+    }
+}
+// eval: scale / shift from the running statistics
+__global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                        const float* __restrict__ run_mean, const float* __restrict__ run_var, float eps,
+                                        float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] / sqrtf(run_var[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - run_mean[c] * sc;
+}
+// BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+                                       const float* __restrict__ gamma, const float* __restrict__ rstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef /* [3][C]: gamma*rstd, mean(g), mean(g*xhat) */) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0, q = 0;
+    for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+    if (dgamma) dgamma[c] = (float)q;
+    if (dbeta) dbeta[c] = (float)s;
+    coef[c] = gamma[c] * rstd[c];
+    coef[C + c] = (float)(s / (double)M);
+    coef[2 * C + c] = (float)(q / (double)M);
+}
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
+                                       float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    double s = 0;
+    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 2 * C + c];
+    out[c] = (float)s;
+}
+
+// out = act( y*scale + shift (+ res | + res*rscale + rshift) )
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const float* __restrict__ res,
+                                                              const float* __restrict__ rscale,
+                                                              const float* __restrict__ rshift, int relu, long long n4,
+                                                              int C, float* __restrict__ out, float* __restrict__ out_lo,
+                                                              int mode) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t * 4;
+        const int c = (int)(i % C);
+        float4 v = ld4(y + i);
+        const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+        v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+        if (res) {
+            float4 r = ld4(res + i);
+            if (rscale) {
+                const float4 a = ld4(rscale + c), b = ld4(rshift + c);
+                r.x = r.x * a.x + b.x; r.y = r.y * a.y + b.y; r.z = r.z * a.z + b.z; r.w = r.w * a.w + b.w;
+            }
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        store_act(out, out_lo, i, v, mode);
+    }
+}
+
+// dy = coef0 * (g - coef1 - xhat*coef2),  g = dout (* [act > 0]);  optionally gmask_out = g (identity branch)
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ dout,
+                                                                  const float* __restrict__ act,
+                                                                  const float* __restrict__ y,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  const float* __restrict__ coef, long long n4, int C,
+                                                                  float* __restrict__ dy, float* __restrict__ dy_lo,
+                                                                  float* __restrict__ gmask_out, int mode) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t * 4;
+        const int c = (int)(i % C);
+        float4 g = ld4(dout + i);
+        if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
+        if (gmask_out) st4(gmask_out + i, g);
+        const float4 v = ld4(y + i), mu = ld4(mean + c), rs = ld4(rstd + c);
+        const float4 c0 = ld4(coef + c), c1 = ld4(coef + C + c), c2 = ld4(coef + 2 * C + c);
+        float4 r;
+        r.x = c0.x * (g.x - c1.x - (v.x - mu.x) * rs.x * c2.x);
+        r.y = c0.y * (g.y - c1.y - (v.y - mu.y) * rs.y * c2.y);
+        r.z = c0.z * (g.z - c1.z - (v.z - mu.z) * rs.z * c2.z);
+        r.w = c0.w * (g.w - c1.w - (v.w - mu.w) * rs.w * c2.w);
+        store_act(dy, dy_lo, i, r, mode);
+    }
+}
+
+// out = a (* [act > 0]) (+ b)
+__global__ void __launch_bounds__(EW_THREADS) masked_add_kernel(const float* __restrict__ a, const float* __restrict__ act,
+                                                                const float* __restrict__ b, long long n4,
+                                                                float* __restrict__ out) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t * 4;
+        float4 g = ld4(a + i);
+        if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
+        if (b) { float4 v = ld4(b + i); g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w; }
+        st4(out + i, g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stem
+// im2col for conv1 (7x7, stride 2, pad 3) straight from the caller's NCHW image:
+//   col[(b,oy,ox)][k], k = c*49 + kh*7 + kw (== OIHW flattening of conv1.weight), zero-padded to K_pad
+__global__ void __launch_bounds__(EW_THREADS) stem_im2col_kernel(const float* __restrict__ x, int B, int H, int W, int Ho,
+                                                                 int Wo, int K_pad, float* __restrict__ col,
+                                                                 float* __restrict__ col_lo, int mode) {
+    const long long total = (long long)B * Ho * Wo * K_pad;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % K_pad);
+        const long long pix = t / K_pad;
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        float v = 0.f;
+        if (k < 147) {
+            const int c = k / 49, kh = (k % 49) / 7, kw = k % 7;
+            const int iy = oy * 2 + kh - 3, ix = ox * 2 + kw - 3;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)b * 3 + c) * H + iy) * W + ix];
+        }
+        if (mode == 1) col[t] = tf_round_tf32(v);
+        else if (mode == 2) { const float h = hi_part(v); col[t] = h; col_lo[t] = v - h; }
+        else col[t] = v;
+    }
+}
+
+// max-pool 3x3 stride 2 pad 1, NHWC
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                                 int Ho, int Wo, float* __restrict__ out,
+                                                                 float* __restrict__ out_lo, int mode) {
+    const long long total = (long long)B * Ho * Wo * (C / 4);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % (C / 4));
+        const long long pix = t / (C / 4);
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int kh = 0; kh < 3; ++kh) {
+            const int iy = oy * 2 + kh - 1;
+            if (iy < 0 || iy >= H) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ix = ox * 2 + kw - 1;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = ld4(x + (((long long)b * H + iy) * W + ix) * C + cg * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        store_act(out, out_lo, pix * C + cg * 4, m, mode);
+    }
+}
+// gather formulation of the backward: input pixel (iy, ix) receives dout of every window whose FIRST maximum
+// (scan order kh, kw ascending -- the rule of ATen's CPU max_pool2d) is this pixel.
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout,
+                                                                 int B, int H, int W, int C, int Ho, int Wo,
+                                                                 float* __restrict__ dx) {
+    const long long total = (long long)B * H * W * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % C);
+        const long long pix = t / C;
+        const int ix = (int)(pix % W), iy = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+        float acc = 0.f;
+        const int oy_lo = max(0, (iy) / 2), oy_hi = min(Ho - 1, (iy + 1) / 2);
+        const int ox_lo = max(0, (ix) / 2), ox_hi = min(Wo - 1, (ix + 1) / 2);
+        for (int oy = oy_lo; oy <= oy_hi; ++oy)
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                float best = -INFINITY; int by = -1, bx = -1;
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int yy = oy * 2 + kh - 1;
+                    if (yy < 0 || yy >= H) continue;
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const int xx = ox * 2 + kw - 1;
+                        if (xx < 0 || xx >= W) continue;
+                        const float v = x[(((long long)b * H + yy) * W + xx) * C + c];
+                        if (v > best || by < 0) { best = v; by = yy; bx = xx; }
+                    }
+                }
+                if (by == iy && bx == ix) acc += dout[(((long long)b * Ho + oy) * Wo + ox) * C + c];
+            }
+        dx[t] = acc;
+    }
+}
+
+// out[b,oy,ox,:] = x[b,2oy,2ox,:]
+__global__ void __launch_bounds__(EW_THREADS) subsample2_kernel(const float* __restrict__ x, const float* __restrict__ x_lo,
+                                                                int B, int H, int W, int C, int Ho, int Wo,
+                                                                float* __restrict__ out, float* __restrict__ out_lo) {
+    const long long total = (long long)B * Ho * Wo * (C / 4);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % (C / 4));
+        const long long pix = t / (C / 4);
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        const long long src = (((long long)b * H + oy * 2) * W + ox * 2) * C + cg * 4;
+        st4(out + pix * C + cg * 4, ld4(x + src));
+        if (x_lo) st4(out_lo + pix * C + cg * 4, ld4(x_lo + src));
+    }
+}
+// out[b,y,x,:] = (y,x both even) ? xs[b,y/2,x/2,:] : 0     (adjoint of subsample2)
+__global__ void __launch_bounds__(EW_THREADS) zero_insert2_kernel(const float* __restrict__ xs, const float* __restrict__ xs_lo,
+                                                                  int B, int H, int W, int C, int Ho, int Wo,
+                                                                  float* __restrict__ out, float* __restrict__ out_lo) {
+    const long long total = (long long)B * H * W * (C / 4);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % (C / 4));
+        const long long pix = t / (C / 4);
+        const int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+        float4 v = make_float4(0, 0, 0, 0), l = v;
+        if (!(x & 1) && !(y & 1)) {
+            const long long src = (((long long)b * Ho + y / 2) * Wo + x / 2) * C + cg * 4;
+            v = ld4(xs + src);
+            if (xs_lo) l = ld4(xs_lo + src);
+        }
+        st4(out + pix * C + cg * 4, v);
+        if (out_lo) st4(out_lo + pix * C + cg * 4, l);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+// dst[o][t][i] (o < O_pad, i < I_pad) from an OIHW source:
+//   transpose == 0:  src[o][i][t]                 (fprop:  [Cout][taps][Cin])
+//   transpose == 1:  src[i][o][taps-1-t]          (dgrad:  [Cin][flipped taps][Cout])
+__global__ void pack_weight_kernel(const float* __restrict__ w, int O_src, int I_src, int taps, int transpose, int O_pad,
+                                   int I_pad, float* __restrict__ dst, float* __restrict__ dst_lo, int mode) {
+    const long long total = (long long)O_pad * taps * I_pad;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % I_pad), tp = (int)((t / I_pad) % taps), o = (int)(t / ((long long)I_pad * taps));
+        float v = 0.f;
+        if (!transpose) { if (o < O_src && i < I_src) v = w[((long long)o * I_src + i) * taps + tp]; }
+        else            { if (i < O_src && o < I_src) v = w[((long long)i * I_src + o) * taps + (taps - 1 - tp)]; }
+        if (mode == 1) dst[t] = tf_round_tf32(v);
+        else if (mode == 2) { const float h = hi_part(v); dst[t] = h; dst_lo[t] = v - h; }
+        else dst[t] = v;
+    }
+}
+// OIHW gradient from the packed [O_pad][taps][I_pad] wgrad output
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int O, int I, int taps, int I_pad,
+                                    float* __restrict__ dw) {
+    const long long total = (long long)O * I * taps;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int tp = (int)(t % taps), i = (int)((t / taps) % I), o = (int)(t / ((long long)taps * I));
+        dw[t] = dwp[((long long)o * taps + tp) * I_pad + i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ heads
+// model.py:104-126: out[b,c,y,x] = s3[b,y,x,c] + sum_{i,j} s4[b,i,j,c] * up[c][y+1-2i][x+1-2j]   (NCHW result)
+__global__ void __launch_bounds__(EW_THREADS) head_combine_fwd_kernel(const float* __restrict__ s3, const float* __restrict__ s4,
+                                                                      const float* __restrict__ up /*[Cn][16]*/, int B,
+                                                                      int H3, int W3, int H4, int W4, int Cn, int Cp,
+                                                                      float* __restrict__ out) {
+    const long long total = (long long)B * Cn * H3 * W3;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(t % W3), y = (int)((t / W3) % H3), c = (int)((t / ((long long)W3 * H3)) % Cn);
+        const int b = (int)(t / ((long long)W3 * H3 * Cn));
+        float v = s3[(((long long)b * H3 + y) * W3 + x) * Cp + c];
+        const int i0 = (y + 1) >> 1, j0 = (x + 1) >> 1;
+#pragma unroll
+        for (int di = 0; di < 2; ++di) {
+            const int i = i0 - di, ky = y + 1 - 2 * i;
+            if (i < 0 || i >= H4) continue;
+#pragma unroll
+            for (int dj = 0; dj < 2; ++dj) {
+                const int j = j0 - dj, kx = x + 1 - 2 * j;
+                if (j < 0 || j >= W4) continue;
+                v += s4[(((long long)b * H4 + i) * W4 + j) * Cp + c] * up[c * 16 + ky * 4 + kx];
+            }
+        }
+        out[t] = v;
+    }
+}
+// adjoint: ds3[b,y,x,c] = dout[b,c,y,x] (padded channels = 0); ds4[b,i,j,c] = sum_{y,x} dout[b,c,y,x] * up[c][y+1-2i][x+1-2j]
+__global__ void __launch_bounds__(EW_THREADS) head_combine_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ up,
+                                                                      int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
+                                                                      float* __restrict__ ds3, float* __restrict__ ds4) {
+    const long long n3 = (long long)B * H3 * W3 * Cp, n4 = (long long)B * H4 * W4 * Cp;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n3 + n4; t += (long long)gridDim.x * blockDim.x) {
+        if (t < n3) {
+            const int c = (int)(t % Cp);
+            const long long pix = t / Cp;
+            const int x = (int)(pix % W3), y = (int)((pix / W3) % H3), b = (int)(pix / ((long long)W3 * H3));
+            ds3[t] = c < Cn ? dout[(((long long)b * Cn + c) * H3 + y) * W3 + x] : 0.f;
+        } else {
+            const long long u = t - n3;
+            const int c = (int)(u % Cp);
+            const long long pix = u / Cp;
+            const int j = (int)(pix % W4), i = (int)((pix / W4) % H4), b = (int)(pix / ((long long)W4 * H4));
+            float v = 0.f;
+            if (c < Cn) {
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int y = 2 * i - 1 + ky;
+                    if (y < 0 || y >= H3) continue;
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const int x = 2 * j - 1 + kx;
+                        if (x < 0 || x >= W3) continue;
+                        v += dout[(((long long)b * Cn + c) * H3 + y) * W3 + x] * up[c * 16 + ky * 4 + kx];
+                    }
+                }
+            }
+            ds4[u] = v;
+        }
+    }
+}
+// up[c][k] = w[c][c][k]  (the ConvTranspose2d weight must be diagonal, model.py:45-65); offdiag = max |off-diagonal|
+__global__ void extract_upsample_diag_kernel(const float* __restrict__ w, int Cn, float* __restrict__ up,
+                                             float* __restrict__ offdiag_max) {
+    const long long total = (long long)Cn * Cn * 16;
+    float m = 0.f;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % 16), co = (int)((t / 16) % Cn), ci = (int)(t / (16LL * Cn));
+        if (ci == co) up[ci * 16 + k] = w[t];
+        else m = fmaxf(m, fabsf(w[t]));
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16)); m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(offdiag_max), __float_as_int(m));
+}
+
+}  // namespace
+
+// ================================================================================================ host API
+// (internal C++ interface used by tf_model.cu; the unit-testable subset is also exported through the C-ABI)
+#include "tf_elementwise.h"
+
+namespace tfe {
+
+static int reduce_blocks(long long M, int C) {
+    const int lanes = EW_THREADS / (C / 4);
+    long long b = (M + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
+    return (int)std::min<long long>(std::max<long long>(b, 1), COLREDUCE_MAX_BLOCKS);
+}
+
+int bn_stats_train(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                   float* run_mean, float* run_var, float* scale, float* shift, float* save_mean, float* save_rstd,
+                   float* partial, cudaStream_t st) {
+    TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_stats_train: C=%d unsupported", C);
+    const int nb = reduce_blocks(M, C);
+    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
+                                                              run_var, scale, shift, save_mean, save_rstd);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
+                        float eps, float* scale, float* shift, cudaStream_t st) {
+    bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, run_mean, run_var, eps, scale, shift);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
+             const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, cudaStream_t st) {
+    const long long n4 = M * C / 4;
+    bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int bn_backward(const float* dout, const float* act, const float* y, const float* save_mean, const float* save_rstd,
+                const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
+                float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st) {
+    TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_backward: C=%d unsupported", C);
+    const int nb = reduce_blocks(M, C);
+    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, save_mean, save_rstd, M, C, partial);
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
+    const long long n4 = M * C / 4;
+    bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
+                                                                gmask_out, mode);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st) {
+    TF_REQUIRE(C % 4 == 0 && C <= 1024, "column_sum: C=%d unsupported", C);
+    const int nb = reduce_blocks(M, C);
+    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    colsum_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(partial, nb, C, Cout, out);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int masked_add(const float* a, const float* act, const float* b, long long n, float* out, cudaStream_t st) {
+    masked_add_kernel<<<ew_blocks(n / 4, 2), EW_THREADS, 0, st>>>(a, act, b, n / 4, out);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,
+                cudaStream_t st) {
+    stem_im2col_kernel<<<ew_blocks((long long)B * Ho * Wo * K_pad, 4), EW_THREADS, 0, st>>>(x_nchw, B, H, W, Ho, Wo, K_pad, col, col_lo, mode);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode, cudaStream_t st) {
+    maxpool_fwd_kernel<<<ew_blocks((long long)B * Ho * Wo * C / 4), EW_THREADS, 0, st>>>(x, B, H, W, C, Ho, Wo, out, out_lo, mode);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int maxpool_bwd(const float* x, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st) {
+    maxpool_bwd_kernel<<<ew_blocks((long long)B * H * W * C, 2), EW_THREADS, 0, st>>>(x, dout, B, H, W, C, Ho, Wo, dx);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int subsample2(const float* x, const float* x_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    subsample2_kernel<<<ew_blocks((long long)B * Ho * Wo * C / 4), EW_THREADS, 0, st>>>(x, x_lo, B, H, W, C, Ho, Wo, out, out_lo);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st) {
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    zero_insert2_kernel<<<ew_blocks((long long)B * H * W * C / 4), EW_THREADS, 0, st>>>(xs, xs_lo, B, H, W, C, Ho, Wo, out, out_lo);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, int O_pad, int I_pad, float* dst,
+                float* dst_lo, int mode, cudaStream_t st) {
+    pack_weight_kernel<<<ew_blocks((long long)O_pad * taps * I_pad), EW_THREADS, 0, st>>>(w, O_src, I_src, taps, transpose, O_pad, I_pad, dst, dst_lo, mode);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int unpack_wgrad(const float* dwp, int O, int I, int taps, int I_pad, float* dw, cudaStream_t st) {
+    unpack_wgrad_kernel<<<ew_blocks((long long)O * I * taps), EW_THREADS, 0, st>>>(dwp, O, I, taps, I_pad, dw);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, int H3, int W3, int H4, int W4, int Cn,
+                     int Cp, float* out_nchw, cudaStream_t st) {
+    head_combine_fwd_kernel<<<ew_blocks((long long)B * Cn * H3 * W3), EW_THREADS, 0, st>>>(s3, s4, up, B, H3, W3, H4, W4, Cn, Cp, out_nchw);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int head_combine_bwd(const float* dout_nchw, const float* up, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
+                     float* ds3, float* ds4, cudaStream_t st) {
+    const long long n = (long long)B * (H3 * W3 + H4 * W4) * Cp;
+    head_combine_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, st>>>(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int extract_upsample_diag(const float* w, int Cn, float* up, float* offdiag_max, cudaStream_t st) {
+    TF_CHECK_CUDA(cudaMemsetAsync(offdiag_max, 0, sizeof(float), st));
+    extract_upsample_diag_kernel<<<ew_blocks((long long)Cn * Cn * 16), EW_THREADS, 0, st>>>(w, Cn, up, offdiag_max);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+}  // namespace tfe

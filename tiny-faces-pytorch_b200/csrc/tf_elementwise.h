@@ -1,0 +1,35 @@
+// Internal C++ interface of the elementwise layer (tf_elementwise.cu), used by tf_model.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tfe {
+constexpr int COLREDUCE_MAX_BLOCKS = 592;     // partial buffers hold COLREDUCE_MAX_BLOCKS * 2 * C floats
+// `mode` of every activation producer: 0 = store as is, 1 = round to TF32 (fast mode operands),
+// 2 = store the (hi, lo) TF32 split into (out, out_lo) (3xTF32 parity mode)
+int bn_stats_train(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                   float* run_mean, float* run_var, float* scale, float* shift, float* save_mean, float* save_rstd,
+                   float* partial, cudaStream_t st);
+int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
+                        float eps, float* scale, float* shift, cudaStream_t st);
+int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
+             const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, cudaStream_t st);
+int bn_backward(const float* dout, const float* act, const float* y, const float* save_mean, const float* save_rstd,
+                const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
+                float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st);
+int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st);
+int masked_add(const float* a, const float* act, const float* b, long long n, float* out, cudaStream_t st);
+int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,
+                cudaStream_t st);
+int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode, cudaStream_t st);
+int maxpool_bwd(const float* x, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st);
+int subsample2(const float* x, const float* x_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
+int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
+int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, int O_pad, int I_pad, float* dst,
+                float* dst_lo, int mode, cudaStream_t st);
+int unpack_wgrad(const float* dwp, int O, int I, int taps, int I_pad, float* dw, cudaStream_t st);
+int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, int H3, int W3, int H4, int W4, int Cn,
+                     int Cp, float* out_nchw, cudaStream_t st);
+int head_combine_bwd(const float* dout_nchw, const float* up, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
+                     float* ds3, float* ds4, cudaStream_t st);
+int extract_upsample_diag(const float* w, int Cn, float* up, float* offdiag_max, cudaStream_t st);
+}  // namespace tfe

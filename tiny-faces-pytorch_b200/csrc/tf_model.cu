@@ -1,0 +1,570 @@
+// DetectionModel forward / backward executor: the whole ResNet-101 res2-res4 trunk + heads of
+// /root/reference/tinyfaces/models/model.py:89-128 (and the backward autograd derives for it,
+// /root/reference/tinyfaces/trainer.py:86) as one stream-ordered sequence of this library's kernels.
+//
+// Data layout: activations NHWC fp32 in a caller-provided workspace (bump-allocated; every tensor needed by the
+// backward stays resident -- ~25 GB at batch-8 960x1280, far below the 180 GB of HBM3e); weights are re-packed
+// from the caller's OIHW parameters into [Cout][tap][Cin] each call.  The caller's tensors (image, parameters,
+// output, gradients) keep the reference's NCHW / OIHW layouts.
+//
+// Precision modes: 1 = "fast": GEMM operands rounded to TF32 by their producers, one tensor-core product;
+//                  2 = "parity": operands kept as exact (hi, lo) TF32 splits, three products (3xTF32).
+// Stride-2 convolutions: 1x1/s2 = subsample then GEMM; 3x3/s2 = stride-1 conv then subsample (forward) and
+// zero-insert then stride-1 dgrad/wgrad (backward).
+#include "tf_common.cuh"
+#include "tf_conv_gemm.h"
+#include "tf_elementwise.h"
+#include <algorithm>
+#include <string>
+#include <vector>
+
+namespace {
+
+#define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+struct ConvP { int w = -1; int cin = 0, cout = 0, k = 1, stride = 1; };
+struct BnP { int gamma = -1, beta = -1, rm = -1, rv = -1, C = 0; };
+struct BlockP { ConvP c1, c2, c3, cd; BnP b1, b2, b3, bd; bool has_ds = false; int stride = 1; };
+
+struct Arena {
+    char* base = nullptr; size_t cap = 0, off = 0, peak = 0; bool dry = true;
+    float* f(size_t n) {
+        off = tf_align_up(off, 1024);
+        float* p = reinterpret_cast<float*>(base + off);
+        off += n * sizeof(float);
+        if (off > peak) peak = off;
+        return p;
+    }
+};
+
+// one conv + BN unit as the backward needs it
+struct Unit {
+    ConvP c; BnP bn;
+    const float* x = nullptr; const float* x_lo = nullptr;      // GEMM input (after subsampling for 1x1/s2)
+    int B = 0, H = 0, W = 0;                                    // spatial size the GEMM ran at
+    int Ho = 0, Wo = 0;                                         // output size (after subsampling for 3x3/s2)
+    float* y = nullptr;                                         // raw conv output at (Ho, Wo)
+    float *mean = nullptr, *rstd = nullptr, *scale = nullptr, *shift = nullptr;
+    float* a = nullptr; float* a_lo = nullptr;                  // post BN(+ReLU) activation (null for bn3 / ds)
+    float* wp = nullptr; float* wp_lo = nullptr;                // packed fprop weights
+};
+struct BlockS { Unit u1, u2, u3, ud; const float* x = nullptr; const float* x_lo = nullptr; int B = 0, H = 0, W = 0, Ho = 0, Wo = 0;
+                float* out = nullptr; float* out_lo = nullptr; bool has_ds = false; };
+
+struct Model {
+    int T = 25, Cn = 125, Cp = 128;
+    std::vector<std::string> names;
+    ConvP stem; BnP stem_bn; std::vector<BlockP> blocks;
+    int s3_w = -1, s3_b = -1, s4_w = -1, s4_b = -1, up_w = -1;
+    // ---- state of the last forward (training) ----
+    int B = 0, H = 0, W = 0, mode = 1, training = 0;
+    Arena ar;
+    const void* const* params = nullptr;
+    Unit stem_u; float* col = nullptr; float* col_lo = nullptr; int H2 = 0, W2 = 0, Hp = 0, Wp = 0;
+    float* pool = nullptr; float* pool_lo = nullptr;
+    std::vector<BlockS> bs;
+    int H3 = 0, W3 = 0, H4 = 0, W4 = 0;
+    const float* res3 = nullptr; const float* res3_lo = nullptr; const float* res4 = nullptr; const float* res4_lo = nullptr;
+    float *w3p = nullptr, *w3p_lo = nullptr, *w4p = nullptr, *w4p_lo = nullptr, *b3p = nullptr, *b4p = nullptr, *up = nullptr, *offdiag = nullptr;
+    float* partial = nullptr; float* coef = nullptr; float* dwtmp = nullptr; size_t fwd_mark = 0;
+    float eps = 1e-5f, momentum = 0.1f;
+
+    int add(const std::string& n) { names.push_back(n); return (int)names.size() - 1; }
+    ConvP conv(const std::string& p, int cin, int cout, int k, int stride) { ConvP c; c.w = add(p + ".weight"); c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; return c; }
+    BnP bnp(const std::string& p, int C) { BnP b; b.gamma = add(p + ".weight"); b.beta = add(p + ".bias"); b.rm = add(p + ".running_mean"); b.rv = add(p + ".running_var"); b.C = C; return b; }
+
+    explicit Model(int templates) : T(templates), Cn(5 * templates) {
+        Cp = (int)tf_align_up((size_t)Cn, 64);
+        stem = conv("model.conv1", 3, 64, 7, 2);
+        stem_bn = bnp("model.bn1", 64);
+        const int nblocks[3] = {3, 4, 23}, planes[3] = {64, 128, 256}, strides[3] = {1, 2, 2};
+        int inpl = 64;
+        for (int l = 0; l < 3; ++l)
+            for (int i = 0; i < nblocks[l]; ++i) {
+                const std::string p = "model.layer" + std::to_string(l + 1) + "." + std::to_string(i);
+                BlockP b;
+                b.stride = i == 0 ? strides[l] : 1;
+                b.c1 = conv(p + ".conv1", inpl, planes[l], 1, 1); b.b1 = bnp(p + ".bn1", planes[l]);
+                b.c2 = conv(p + ".conv2", planes[l], planes[l], 3, b.stride); b.b2 = bnp(p + ".bn2", planes[l]);
+                b.c3 = conv(p + ".conv3", planes[l], planes[l] * 4, 1, 1); b.b3 = bnp(p + ".bn3", planes[l] * 4);
+                if (i == 0) { b.has_ds = true; b.cd = conv(p + ".downsample.0", inpl, planes[l] * 4, 1, b.stride); b.bd = bnp(p + ".downsample.1", planes[l] * 4); }
+                inpl = planes[l] * 4;
+                blocks.push_back(b);
+            }
+        s3_w = add("score_res3.weight"); s3_b = add("score_res3.bias");
+        s4_w = add("score_res4.weight"); s4_b = add("score_res4.bias");
+        up_w = add("score4_upsample.weight");
+    }
+    const float* P(int i) const { return reinterpret_cast<const float*>(params[i]); }
+    float* PW(int i) const { return reinterpret_cast<float*>(const_cast<void*>(params[i])); }
+
+    // ------------------------------------------------------------------------------------------ forward pieces
+    int pack(const ConvP& c, int O_pad, int I_pad, int transpose, float** wp, float** wp_lo, cudaStream_t st) {
+        const int taps = c.k * c.k;
+        const size_t n = (size_t)O_pad * taps * I_pad;
+        *wp = ar.f(n);
+        *wp_lo = mode == 2 ? ar.f(n) : nullptr;
+        if (!ar.dry) RC(tfe::pack_weight(P(c.w), c.cout, c.cin, taps, transpose, O_pad, I_pad, *wp, *wp_lo, mode, st));
+        return TF_OK;
+    }
+    // conv (+ stride handling) producing the raw output u.y at (Ho, Wo); fused != 0: eval epilogue scale/shift(/relu)
+    int run_conv(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, int fused, int relu, float* fused_out,
+                 cudaStream_t st) {
+        const ConvP& c = u.c;
+        u.B = B_;
+        const int Ho = c.stride == 2 ? (H_ + 1) / 2 : H_, Wo = c.stride == 2 ? (W_ + 1) / 2 : W_;
+        u.Ho = Ho; u.Wo = Wo;
+        RC(pack(c, c.cout, c.cin, 0, &u.wp, &u.wp_lo, st));
+        tfg::ConvArgs a = {};
+        a.B = B_; a.Cin = c.cin; a.Cout = c.cout; a.ksize = c.k; a.w = u.wp; a.w_lo = u.wp_lo;
+        if (fused) { a.scale = u.scale; a.shift = u.shift; a.relu = relu; a.round_out = 1; }
+        if (c.k == 1 && c.stride == 2) {
+            float* xs = ar.f((size_t)B_ * Ho * Wo * c.cin);
+            float* xs_lo = x_lo ? ar.f((size_t)B_ * Ho * Wo * c.cin) : nullptr;
+            if (!ar.dry) RC(tfe::subsample2(x, x_lo, B_, H_, W_, c.cin, xs, xs_lo, st));
+            u.x = xs; u.x_lo = xs_lo; u.H = Ho; u.W = Wo;
+        } else {
+            u.x = x; u.x_lo = x_lo; u.H = H_; u.W = W_;
+        }
+        a.x = u.x; a.x_lo = u.x_lo; a.H = u.H; a.W = u.W;
+        float* dst = fused_out ? fused_out : ar.f((size_t)B_ * Ho * Wo * c.cout);
+        if (c.k == 3 && c.stride == 2) {
+            float* yf = ar.f((size_t)B_ * H_ * W_ * c.cout);
+            a.y = yf;
+            if (!ar.dry) { RC(tfg::conv_fprop(a, st)); RC(tfe::subsample2(yf, nullptr, B_, H_, W_, c.cout, dst, nullptr, st)); }
+        } else {
+            a.y = dst;
+            if (!ar.dry) RC(tfg::conv_fprop(a, st));
+        }
+        u.y = dst;
+        return TF_OK;
+    }
+    int alloc_bn(Unit& u) {
+        const int C = u.bn.C;
+        u.scale = ar.f(C); u.shift = ar.f(C); u.mean = ar.f(C); u.rstd = ar.f(C);
+        return TF_OK;
+    }
+    int bn_prepare_eval(Unit& u, cudaStream_t st) {
+        RC(alloc_bn(u));
+        if (!ar.dry) RC(tfe::bn_scale_shift_eval(u.bn.C, P(u.bn.gamma), P(u.bn.beta), P(u.bn.rm), P(u.bn.rv), eps, u.scale, u.shift, st));
+        return TF_OK;
+    }
+    int bn_stats(Unit& u, cudaStream_t st) {
+        RC(alloc_bn(u));
+        const long long M = (long long)u.B * u.Ho * u.Wo;
+        if (!ar.dry) RC(tfe::bn_stats_train(u.y, M, u.bn.C, P(u.bn.gamma), P(u.bn.beta), eps, momentum, PW(u.bn.rm), PW(u.bn.rv),
+                                            u.scale, u.shift, u.mean, u.rstd, partial, st));
+        return TF_OK;
+    }
+    // conv + BN + ReLU -> activation (u.a)
+    int conv_bn_relu(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, cudaStream_t st) {
+        const int Ho = u.c.stride == 2 ? (H_ + 1) / 2 : H_, Wo = u.c.stride == 2 ? (W_ + 1) / 2 : W_;
+        const long long M = (long long)B_ * Ho * Wo;
+        if (!training && mode == 1) {           // eval fast path: BN + ReLU + TF32 rounding in the GEMM epilogue
+            RC(bn_prepare_eval(u, st));
+            u.a = ar.f((size_t)M * u.c.cout); u.a_lo = nullptr;
+            RC(run_conv(u, x, x_lo, B_, H_, W_, 1, 1, u.a, st));
+            return TF_OK;
+        }
+        if (!training) RC(bn_prepare_eval(u, st));
+        RC(run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st));
+        if (training) RC(bn_stats(u, st));
+        u.a = ar.f((size_t)M * u.c.cout);
+        u.a_lo = mode == 2 ? ar.f((size_t)M * u.c.cout) : nullptr;
+        if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M, u.c.cout, u.a, u.a_lo, mode, st));
+        return TF_OK;
+    }
+    int block_forward(const BlockP& bp, BlockS& s, const float* x, const float* x_lo, int B_, int H_, int W_, float* out_pre,
+                      float* out_lo_pre, cudaStream_t st) {
+        s.has_ds = bp.has_ds;
+        s.x = x; s.x_lo = x_lo; s.B = B_; s.H = H_; s.W = W_;
+        s.u1.c = bp.c1; s.u1.bn = bp.b1; s.u2.c = bp.c2; s.u2.bn = bp.b2; s.u3.c = bp.c3; s.u3.bn = bp.b3; s.ud.c = bp.cd; s.ud.bn = bp.bd;
+        RC(conv_bn_relu(s.u1, x, x_lo, B_, H_, W_, st));
+        RC(conv_bn_relu(s.u2, s.u1.a, s.u1.a_lo, B_, H_, W_, st));
+        const int Ho = s.u2.Ho, Wo = s.u2.Wo;
+        s.Ho = Ho; s.Wo = Wo;
+        const long long Mo = (long long)B_ * Ho * Wo;
+        const int C4 = bp.c3.cout;
+        if (!training) RC(bn_prepare_eval(s.u3, st));
+        RC(run_conv(s.u3, s.u2.a, s.u2.a_lo, B_, Ho, Wo, 0, 0, nullptr, st));
+        if (training) RC(bn_stats(s.u3, st));
+        const float* res = x; const float* rscale = nullptr; const float* rshift = nullptr;
+        if (bp.has_ds) {
+            if (!training && mode == 1) {
+                RC(bn_prepare_eval(s.ud, st));
+                RC(run_conv(s.ud, x, x_lo, B_, H_, W_, 1, 0, nullptr, st));        // BN folded into the epilogue
+            } else {
+                if (!training) RC(bn_prepare_eval(s.ud, st));
+                RC(run_conv(s.ud, x, x_lo, B_, H_, W_, 0, 0, nullptr, st));
+                if (training) RC(bn_stats(s.ud, st));
+                rscale = s.ud.scale; rshift = s.ud.shift;
+            }
+            res = s.ud.y;
+        }
+        s.out = out_pre ? out_pre : ar.f((size_t)Mo * C4);
+        s.out_lo = mode == 2 ? (out_lo_pre ? out_lo_pre : ar.f((size_t)Mo * C4)) : nullptr;
+        if (!bp.has_ds && mode == 2) {
+            // parity mode: the identity is x_hi + x_lo -- fold the lo part in first
+            float* xsum = ar.f((size_t)Mo * C4);
+            if (!ar.dry) RC(tfe::masked_add(x, nullptr, x_lo, Mo * C4, xsum, st));
+            res = xsum;
+        }
+        if (!ar.dry) RC(tfe::bn_apply(s.u3.y, s.u3.scale, s.u3.shift, res, rscale, rshift, 1, Mo, C4, s.out, s.out_lo, mode, st));
+        return TF_OK;
+    }
+
+    int forward(const float* x_nchw, float* out_nchw, cudaStream_t st) {
+        H2 = (H - 1) / 2 + 1; W2 = (W - 1) / 2 + 1;
+        Hp = (H2 - 1) / 2 + 1; Wp = (W2 - 1) / 2 + 1;
+        partial = ar.f((size_t)tfe::COLREDUCE_MAX_BLOCKS * 2 * 1024);
+        coef = ar.f(3 * 1024);
+        dwtmp = ar.f((size_t)1024 * 1024 + 4096);
+        offdiag = ar.f(64);
+        // ---- stem: im2col + GEMM (K = 147 padded to 160), BN, ReLU, max-pool
+        const long long M2 = (long long)B * H2 * W2;
+        col = ar.f((size_t)M2 * 160);
+        col_lo = mode == 2 ? ar.f((size_t)M2 * 160) : nullptr;
+        if (!ar.dry) RC(tfe::stem_im2col(x_nchw, B, H, W, H2, W2, 160, col, col_lo, mode, st));
+        Unit& u = stem_u;
+        u = Unit();
+        u.c = stem; u.bn = stem_bn; u.B = B; u.H = H2; u.W = W2; u.Ho = H2; u.Wo = W2; u.x = col; u.x_lo = col_lo;
+        {   // packed stem weight [64][1][160]: rows are the OIHW-flattened filters, zero padded
+            ConvP c = stem; c.cin = 147; c.k = 1;
+            RC(pack(c, 64, 160, 0, &u.wp, &u.wp_lo, st));
+        }
+        tfg::ConvArgs a = {};
+        a.x = col; a.x_lo = col_lo; a.B = 1; a.H = 1; a.W = (int)M2; a.Cin = 160; a.w = u.wp; a.w_lo = u.wp_lo; a.Cout = 64; a.ksize = 1;
+        TF_REQUIRE(M2 < (1ll << 31), "forward: stem pixel count overflows");
+        float* a0; float* a0_lo = nullptr;
+        if (!training && mode == 1) {
+            RC(bn_prepare_eval(u, st));
+            a.scale = u.scale; a.shift = u.shift; a.relu = 1; a.round_out = 0;
+            a0 = ar.f((size_t)M2 * 64);
+            a.y = a0; u.y = a0;
+            if (!ar.dry) RC(tfg::conv_fprop(a, st));
+        } else {
+            if (!training) RC(bn_prepare_eval(u, st));
+            u.y = ar.f((size_t)M2 * 64);
+            a.y = u.y;
+            if (!ar.dry) RC(tfg::conv_fprop(a, st));
+            if (training) RC(bn_stats(u, st));
+            a0 = ar.f((size_t)M2 * 64);
+            if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M2, 64, a0, nullptr, 0, st));
+        }
+        u.a = a0; u.a_lo = a0_lo;
+        const long long Mp = (long long)B * Hp * Wp;
+        pool = ar.f((size_t)Mp * 64);
+        pool_lo = mode == 2 ? ar.f((size_t)Mp * 64) : nullptr;
+        if (!ar.dry) RC(tfe::maxpool_fwd(a0, B, H2, W2, 64, Hp, Wp, pool, pool_lo, mode, st));
+        // ---- heads' buffers (model.py:104-126) are allocated first so that they survive the per-block resets
+        auto half = [](int v) { return (v - 1) / 2 + 1; };
+        H3 = half(Hp); W3 = half(Wp); H4 = half(H3); W4 = half(W3);
+        const long long M3 = (long long)B * H3 * W3, M4 = (long long)B * H4 * W4;
+        ConvP h3; h3.w = s3_w; h3.cin = 512; h3.cout = Cn; h3.k = 1;
+        ConvP h4; h4.w = s4_w; h4.cin = 1024; h4.cout = Cn; h4.k = 1;
+        RC(pack(h3, Cp, 512, 0, &w3p, &w3p_lo, st));
+        RC(pack(h4, Cp, 1024, 0, &w4p, &w4p_lo, st));
+        b3p = ar.f(Cp); b4p = ar.f(Cp); up = ar.f((size_t)Cn * 16);
+        float* s3 = ar.f((size_t)M3 * Cp); float* s4 = ar.f((size_t)M4 * Cp);
+        if (!ar.dry) {
+            TF_CHECK_CUDA(cudaMemsetAsync(b3p, 0, Cp * 4, st)); TF_CHECK_CUDA(cudaMemsetAsync(b4p, 0, Cp * 4, st));
+            TF_CHECK_CUDA(cudaMemcpyAsync(b3p, P(s3_b), Cn * 4, cudaMemcpyDeviceToDevice, st));
+            TF_CHECK_CUDA(cudaMemcpyAsync(b4p, P(s4_b), Cn * 4, cudaMemcpyDeviceToDevice, st));
+            RC(tfe::extract_upsample_diag(P(up_w), Cn, up, offdiag, st));
+        }
+        // ---- residual stages.  Training keeps every tensor for the backward; inference ping-pongs the block
+        //      outputs and reuses one scratch region per block (bounded memory for the 5000x5000 pyramid level).
+        bs.assign(blocks.size(), BlockS());
+        float* pp[2] = {nullptr, nullptr}; float* pp_lo[2] = {nullptr, nullptr};
+        if (!training) {
+            size_t mx = 0; int th = Hp, tw_ = Wp;
+            for (const BlockP& bp : blocks) {
+                if (bp.stride == 2) { th = half(th); tw_ = half(tw_); }
+                mx = std::max(mx, (size_t)B * th * tw_ * bp.c3.cout);
+            }
+            for (int k = 0; k < 2; ++k) { pp[k] = ar.f(mx); pp_lo[k] = mode == 2 ? ar.f(mx) : nullptr; }
+        }
+        const size_t scratch_mark = ar.off;
+        const float* cur = pool; const float* cur_lo = pool_lo;
+        int ch = Hp, cw = Wp;
+        for (size_t i = 0; i < blocks.size(); ++i) {
+            if (!training) ar.off = scratch_mark;
+            RC(block_forward(blocks[i], bs[i], cur, cur_lo, B, ch, cw, pp[i & 1], pp_lo[i & 1], st));
+            cur = bs[i].out; cur_lo = bs[i].out_lo; ch = bs[i].Ho; cw = bs[i].Wo;
+            if (i == 6) {
+                res3 = cur; res3_lo = cur_lo;
+                TF_REQUIRE(ch == H3 && cw == W3, "forward: res3 shape mismatch");
+                if (!ar.dry) {
+                    tfg::ConvArgs h = {};
+                    h.x = res3; h.x_lo = res3_lo; h.B = B; h.H = H3; h.W = W3; h.Cin = 512; h.w = w3p; h.w_lo = w3p_lo; h.Cout = Cp; h.ksize = 1; h.shift = b3p; h.y = s3;
+                    RC(tfg::conv_fprop(h, st));
+                }
+            }
+        }
+        res4 = cur; res4_lo = cur_lo;
+        TF_REQUIRE(ch == H4 && cw == W4, "forward: res4 shape mismatch");
+        if (!ar.dry) {
+            tfg::ConvArgs h = {};
+            h.x = res4; h.x_lo = res4_lo; h.B = B; h.H = H4; h.W = W4; h.Cin = 1024; h.w = w4p; h.w_lo = w4p_lo; h.Cout = Cp; h.ksize = 1; h.shift = b4p; h.y = s4;
+            RC(tfg::conv_fprop(h, st));
+            RC(tfe::head_combine_fwd(s3, s4, up, B, H3, W3, H4, W4, Cn, Cp, out_nchw, st));
+        }
+        fwd_mark = ar.off;
+        return TF_OK;
+    }
+
+    // ------------------------------------------------------------------------------------------ backward pieces
+    float* G(void* const* grads, int idx) const { return (grads && idx >= 0) ? reinterpret_cast<float*>(grads[idx]) : nullptr; }
+
+    // BN backward of unit u: dout (masked by act > 0 when act != null) -> dy (+lo); dgamma/dbeta into the caller's grads
+    int unit_bn_bwd(const Unit& u, const float* dout, const float* act, float* gmask_out, float** dy, float** dy_lo,
+                    void* const* grads, cudaStream_t st) {
+        const long long M = (long long)u.B * u.Ho * u.Wo;
+        const int C = u.bn.C;
+        *dy = ar.f((size_t)M * C);
+        *dy_lo = mode == 2 ? ar.f((size_t)M * C) : nullptr;
+        if (!ar.dry) RC(tfe::bn_backward(dout, act, u.y, u.mean, u.rstd, P(u.bn.gamma), M, C, G(grads, u.bn.gamma), G(grads, u.bn.beta),
+                                         *dy, *dy_lo, gmask_out, mode, partial, coef, st));
+        return TF_OK;
+    }
+    // conv backward of unit u given dy at (Ho, Wo): weight gradient (always) and input gradient into dx
+    // (dx_accumulate: add into dx instead of overwriting); dx == null skips the dgrad.
+    int unit_conv_bwd(const Unit& u, const float* dy, const float* dy_lo, float* dx, int dx_accumulate, int dxH, int dxW,
+                      void* const* grads, cudaStream_t st) {
+        const ConvP& c = u.c;
+        const int taps = c.k * c.k;
+        const float* dyg = dy; const float* dyg_lo = dy_lo;         // dy at the resolution the GEMM ran at
+        if (c.k == 3 && c.stride == 2) {
+            float* z = ar.f((size_t)u.B * u.H * u.W * c.cout);
+            float* z_lo = dy_lo ? ar.f((size_t)u.B * u.H * u.W * c.cout) : nullptr;
+            if (!ar.dry) RC(tfe::zero_insert2(dy, dy_lo, u.B, u.H, u.W, c.cout, z, z_lo, st));
+            dyg = z; dyg_lo = z_lo;
+        }
+        // ---- wgrad
+        float* gw = G(grads, c.w);
+        if (gw && !ar.dry) {
+            TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)c.cout * taps * c.cin * 4, st));
+            tfg::WgradArgs w = {};
+            w.x = u.x; w.x_lo = u.x_lo; w.dy = dyg; w.dy_lo = dyg_lo; w.B = u.B; w.H = u.H; w.W = u.W; w.Cin = c.cin; w.Cout = c.cout;
+            w.ksize = c.k; w.dw = dwtmp;
+            if (w.x_lo == nullptr || w.dy_lo == nullptr) { w.x_lo = nullptr; w.dy_lo = nullptr; }
+            RC(tfg::conv_wgrad(w, st));
+            RC(tfe::unpack_wgrad(dwtmp, c.cout, c.cin, taps, c.cin, gw, st));
+        }
+        // ---- dgrad: dx = conv(dy, w^T flipped)
+        if (dx) {
+            float *wt, *wt_lo;
+            ConvP ct = c;
+            RC(pack(ct, c.cin, c.cout, 1, &wt, &wt_lo, st));        // [Cin][taps][Cout]
+            tfg::ConvArgs a = {};
+            a.x = dyg; a.x_lo = dyg_lo; a.B = u.B; a.H = u.H; a.W = u.W; a.Cin = c.cout; a.w = wt; a.w_lo = wt_lo; a.Cout = c.cin; a.ksize = c.k;
+            if (a.x_lo == nullptr) a.w_lo = nullptr;
+            if (c.k == 1 && c.stride == 2) {
+                // gradient w.r.t. the subsampled input, then scatter to the even positions of dx
+                float* dxs = ar.f((size_t)u.B * u.H * u.W * c.cin);
+                a.y = dxs;
+                if (!ar.dry) {
+                    RC(tfg::conv_fprop(a, st));
+                    TF_REQUIRE(!dx_accumulate, "unit_conv_bwd: accumulate into a strided dgrad is not supported");
+                    RC(tfe::zero_insert2(dxs, nullptr, u.B, dxH, dxW, c.cin, dx, nullptr, st));
+                }
+            } else {
+                a.y = dx; a.accumulate = dx_accumulate;
+                if (!ar.dry) RC(tfg::conv_fprop(a, st));
+            }
+        }
+        return TF_OK;
+    }
+    int block_backward(const BlockS& s, const float* dout, float* dx, void* const* grads, cudaStream_t st) {
+        const long long Mo = (long long)s.B * s.Ho * s.Wo;
+        const int C4 = s.u3.c.cout;
+        float *dy3, *dy3_lo;
+        const bool has_ds = s.has_ds;
+        // G = dout * [out > 0]: with an identity shortcut dx simply starts as G, otherwise G feeds the downsample BN
+        float* g = has_ds ? ar.f((size_t)Mo * C4) : dx;
+        RC(unit_bn_bwd(s.u3, dout, s.out, g, &dy3, &dy3_lo, grads, st));
+        const long long M2o = (long long)s.B * s.u2.Ho * s.u2.Wo;
+        float* da2 = ar.f((size_t)M2o * s.u2.c.cout);
+        RC(unit_conv_bwd(s.u3, dy3, dy3_lo, da2, 0, s.Ho, s.Wo, grads, st));
+        float *dy2, *dy2_lo;
+        RC(unit_bn_bwd(s.u2, da2, s.u2.a, nullptr, &dy2, &dy2_lo, grads, st));
+        const long long M1 = (long long)s.B * s.H * s.W;
+        float* da1 = ar.f((size_t)M1 * s.u1.c.cout);
+        RC(unit_conv_bwd(s.u2, dy2, dy2_lo, da1, 0, s.H, s.W, grads, st));
+        float *dy1, *dy1_lo;
+        RC(unit_bn_bwd(s.u1, da1, s.u1.a, nullptr, &dy1, &dy1_lo, grads, st));
+        if (has_ds) {
+            float *dyd, *dyd_lo;
+            RC(unit_bn_bwd(s.ud, g, nullptr, nullptr, &dyd, &dyd_lo, grads, st));
+            RC(unit_conv_bwd(s.ud, dyd, dyd_lo, dx, 0, s.H, s.W, grads, st));          // dx = downsample path
+        }
+        RC(unit_conv_bwd(s.u1, dy1, dy1_lo, dx, 1, s.H, s.W, grads, st));              // dx += main path
+        return TF_OK;
+    }
+
+    int backward(const float* dout_nchw, void* const* grads, cudaStream_t st) {
+        TF_REQUIRE(training, "tf_model_backward: the last forward was not a training forward");
+        ar.off = fwd_mark;
+        const long long M3 = (long long)B * H3 * W3, M4 = (long long)B * H4 * W4;
+        float* ds3 = ar.f((size_t)M3 * Cp); float* ds4 = ar.f((size_t)M4 * Cp);
+        if (!ar.dry) {
+            RC(tfe::head_combine_bwd(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4, st));
+            if (G(grads, s3_b)) RC(tfe::column_sum(ds3, M3, Cp, Cn, G(grads, s3_b), partial, st));
+            if (G(grads, s4_b)) RC(tfe::column_sum(ds4, M4, Cp, Cn, G(grads, s4_b), partial, st));
+        }
+        // head weight gradients and input gradients (as 1x1 "units" with padded Cout)
+        Unit h3; h3.c.w = s3_w; h3.c.cin = 512; h3.c.cout = Cp; h3.c.k = 1; h3.x = res3; h3.x_lo = nullptr; h3.B = B; h3.H = H3; h3.W = W3; h3.Ho = H3; h3.Wo = W3;
+        Unit h4 = h3; h4.c.w = s4_w; h4.c.cin = 1024; h4.x = res4; h4.H = H4; h4.W = W4; h4.Ho = H4; h4.Wo = W4;
+        float* dres4 = ar.f((size_t)M4 * 1024);
+        // input gradients ping-pong between two buffers; one scratch region is reused by every block (single stream)
+        size_t mx = 0;
+        for (const BlockS& s : bs) mx = std::max(mx, (size_t)s.B * s.H * s.W * s.u1.c.cin);
+        float* dxbuf[2] = {ar.f(mx), ar.f(mx)};
+        const size_t scratch_mark = ar.off;
+        RC(head_bwd(h4, ds4, dres4, 0, grads, st));
+        // ---- layer3 .. layer1
+        const float* dcur = dres4;
+        for (int i = (int)blocks.size() - 1; i >= 0; --i) {
+            const BlockS& s = bs[i];
+            ar.off = scratch_mark;
+            float* dx = dxbuf[i & 1];
+            RC(block_backward(s, dcur, dx, grads, st));
+            if (i == 7) RC(head_bwd(h3, ds3, dx, 1, grads, st));   // res3 also feeds score_res3: dx(block 7 input) += head dgrad
+            dcur = dx;
+        }
+        ar.off = scratch_mark;
+        // ---- stem
+        const long long M2 = (long long)B * H2 * W2;
+        float* da0 = ar.f((size_t)M2 * 64);
+        if (!ar.dry) RC(tfe::maxpool_bwd(stem_u.a, dcur, B, H2, W2, 64, Hp, Wp, da0, st));
+        float *dy0, *dy0_lo;
+        RC(unit_bn_bwd(stem_u, da0, stem_u.a, nullptr, &dy0, &dy0_lo, grads, st));
+        float* gw = G(grads, stem.w);
+        if (gw && !ar.dry) {
+            TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)64 * 160 * 4, st));
+            tfg::WgradArgs w = {};
+            w.x = col; w.x_lo = col_lo; w.dy = dy0; w.dy_lo = dy0_lo; w.B = 1; w.H = 1; w.W = (int)M2; w.Cin = 160; w.Cout = 64; w.ksize = 1; w.dw = dwtmp;
+            if (!w.x_lo || !w.dy_lo) { w.x_lo = nullptr; w.dy_lo = nullptr; }
+            RC(tfg::conv_wgrad(w, st));
+            RC(tfe::unpack_wgrad(dwtmp, 64, 147, 1, 160, gw, st));
+        }
+        return TF_OK;
+    }
+    // head (score_res3 / score_res4) backward: weight gradient [Cn, Cin] and dres (+)= ds * W
+    int head_bwd(const Unit& h, const float* ds, float* dres, int accumulate, void* const* grads, cudaStream_t st) {
+        const ConvP& c = h.c;
+        float* gw = G(grads, c.w);
+        if (gw && !ar.dry) {
+            TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)Cp * c.cin * 4, st));
+            tfg::WgradArgs w = {};
+            w.x = h.x; w.dy = ds; w.B = h.B; w.H = h.H; w.W = h.W; w.Cin = c.cin; w.Cout = Cp; w.ksize = 1; w.dw = dwtmp;
+            RC(tfg::conv_wgrad(w, st));
+            RC(tfe::unpack_wgrad(dwtmp, Cn, c.cin, 1, c.cin, gw, st));
+        }
+        float *wt, *wt_lo;
+        ConvP ct = c; ct.cout = Cn;
+        RC(pack(ct, c.cin, Cp, 1, &wt, &wt_lo, st));                 // [Cin][1][Cp], columns >= Cn are zero
+        tfg::ConvArgs a = {};
+        a.x = ds; a.B = h.B; a.H = h.H; a.W = h.W; a.Cin = Cp; a.w = wt; a.Cout = c.cin; a.ksize = 1; a.y = dres; a.accumulate = accumulate;
+        if (!ar.dry) RC(tfg::conv_fprop(a, st));
+        return TF_OK;
+    }
+};
+
+}  // namespace
+
+TF_API int tf_model_create(int num_templates, void** handle) {
+    TF_REQUIRE(handle && num_templates > 0 && num_templates <= 32, "tf_model_create: bad args");
+    *handle = new Model(num_templates);
+    return TF_OK;
+}
+TF_API int tf_model_destroy(void* handle) { delete reinterpret_cast<Model*>(handle); return TF_OK; }
+TF_API int tf_model_num_params(void* handle) { return handle ? (int)reinterpret_cast<Model*>(handle)->names.size() : -1; }
+TF_API const char* tf_model_param_name(void* handle, int i) {
+    Model* m = reinterpret_cast<Model*>(handle);
+    return (m && i >= 0 && i < (int)m->names.size()) ? m->names[i].c_str() : nullptr;
+}
+TF_API int tf_model_output_shape(void* handle, int H, int W, int* H3, int* W3) {
+    TF_REQUIRE(handle && H3 && W3 && H > 0 && W > 0, "tf_model_output_shape: bad args");
+    auto half = [](int v) { return (v - 1) / 2 + 1; };
+    *H3 = half(half(half(H))); *W3 = half(half(half(W)));
+    return TF_OK;
+}
+// Workspace needed by forward (+ backward when training) for this shape / mode (dry run of the same code path).
+TF_API int tf_model_workspace_bytes(void* handle, int B, int H, int W, int training, int mode, size_t* bytes) {
+    TF_REQUIRE(handle && bytes && B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_workspace_bytes: bad args");
+    Model* m = reinterpret_cast<Model*>(handle);
+    m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode;
+    m->ar = Arena(); m->ar.dry = true; m->ar.base = nullptr;
+    RC(m->forward(nullptr, nullptr, nullptr));
+    if (training) RC(m->backward(nullptr, nullptr, nullptr));
+    *bytes = m->ar.peak + 4096;
+    return TF_OK;
+}
+// x: [B,3,H,W] fp32 NCHW (device).  params: num_params device pointers in tf_model_param_name order.
+// out: [B,5T,H3,W3] fp32 NCHW (device).  training != 0: batch-statistics BN, running stats updated in place,
+// everything the backward needs stays in the workspace until the next forward.
+TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, const void* const* params, int training,
+                            int mode, float bn_momentum, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+    TF_REQUIRE(handle && x && params && out && workspace, "tf_model_forward: null pointer");
+    TF_REQUIRE(B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_forward: bad shape/mode");
+    Model* m = reinterpret_cast<Model*>(handle);
+    size_t need;
+    RC(tf_model_workspace_bytes(handle, B, H, W, training, mode, &need));
+    if (workspace_bytes < need) { tf_set_error("tf_model_forward: workspace %zu < required %zu", workspace_bytes, need); return TF_ERR_WORKSPACE; }
+    m->params = params; m->momentum = bn_momentum;
+    m->ar = Arena(); m->ar.dry = false; m->ar.base = reinterpret_cast<char*>(workspace); m->ar.cap = workspace_bytes;
+    return m->forward(x, out, (cudaStream_t)stream);
+}
+// dout: [B,5T,H3,W3] NCHW.  grads: num_params device pointers (null = not wanted); conv / head weights in OIHW,
+// BN gamma/beta, head biases.  Must follow a training forward on the same workspace.
+TF_API int tf_model_backward(void* handle, const float* dout, void* const* grads, void* stream) {
+    TF_REQUIRE(handle && dout && grads, "tf_model_backward: null pointer");
+    Model* m = reinterpret_cast<Model*>(handle);
+    TF_REQUIRE(!m->ar.dry && m->ar.base, "tf_model_backward: no forward state");
+    return m->backward(dout, grads, (cudaStream_t)stream);
+}
+// Debug / test hook: locate an internal NHWC activation of the last forward ("stem", "pool", "block<i>.out",
+// "block<i>.u<1|2|3|d>.<y|a>") and copy it (device to device) into dst (capacity in floats).
+TF_API int tf_model_get_tensor(void* handle, const char* name, float* dst, int64_t capacity, int* shape4, void* stream) {
+    TF_REQUIRE(handle && name && shape4, "tf_model_get_tensor: bad args");
+    Model* m = reinterpret_cast<Model*>(handle);
+    TF_REQUIRE(!m->ar.dry && m->ar.base, "tf_model_get_tensor: no forward state");
+    const std::string n(name);
+    const float* src = nullptr; int B = m->B, H = 0, W = 0, C = 0;
+    if (n == "stem") { src = m->stem_u.a; H = m->H2; W = m->W2; C = 64; }
+    else if (n == "stem.y") { src = m->stem_u.y; H = m->H2; W = m->W2; C = 64; }
+    else if (n == "col") { src = m->col; H = m->H2; W = m->W2; C = 160; }
+    else if (n == "pool") { src = m->pool; H = m->Hp; W = m->Wp; C = 64; }
+    else if (n.rfind("block", 0) == 0) {
+        const size_t dot = n.find('.');
+        TF_REQUIRE(dot != std::string::npos, "tf_model_get_tensor: bad name %s", name);
+        const int i = atoi(n.substr(5, dot - 5).c_str());
+        TF_REQUIRE(i >= 0 && i < (int)m->bs.size(), "tf_model_get_tensor: bad block index in %s", name);
+        const BlockS& s = m->bs[i];
+        const std::string rest = n.substr(dot + 1);
+        if (rest == "out") { src = s.out; H = s.Ho; W = s.Wo; C = s.u3.c.cout; }
+        else {
+            const Unit* u = rest[1] == '1' ? &s.u1 : rest[1] == '2' ? &s.u2 : rest[1] == '3' ? &s.u3 : &s.ud;
+            H = u->Ho; W = u->Wo; C = u->c.cout;
+            src = rest.back() == 'y' ? u->y : u->a;
+        }
+    }
+    TF_REQUIRE(src, "tf_model_get_tensor: unknown or empty tensor %s", name);
+    shape4[0] = B; shape4[1] = H; shape4[2] = W; shape4[3] = C;
+    const int64_t cnt = (int64_t)B * H * W * C;
+    if (dst) {
+        TF_REQUIRE(capacity >= cnt, "tf_model_get_tensor: capacity too small");
+        TF_CHECK_CUDA(cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    return TF_OK;
+}
+// max |off-diagonal| of score4_upsample.weight seen by the last forward (host value; synchronises the stream)
+TF_API int tf_model_upsample_offdiag(void* handle, float* value, void* stream) {
+    TF_REQUIRE(handle && value, "tf_model_upsample_offdiag: bad args");
+    Model* m = reinterpret_cast<Model*>(handle);
+    TF_REQUIRE(m->offdiag && !m->ar.dry, "tf_model_upsample_offdiag: no forward state");
+    TF_CHECK_CUDA(cudaMemcpyAsync(value, m->offdiag, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TF_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return TF_OK;
+}

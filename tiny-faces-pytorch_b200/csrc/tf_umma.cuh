@@ -75,6 +75,10 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -136,13 +140,17 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, uint32_t a_
 //   K-major : rows of 128 B, 8-row atoms; SBO = byte distance between 8-row groups (1024), LBO unused (1)
 //   MN-major: 128 B of MN-contiguous elements per K row, 8 K-rows per atom;
 //             LBO = byte distance between 128 B column groups along MN, SBO = distance between 8-row K groups
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major fp32/tf32 operands: only SWIZZLE_128B_BASE32B (layout_type 1, TMA swizzle 128B_ATOM_32B) exists:
+//             32 B chunks swizzled within 128 B rows, 4 K-rows per atom (512 B): SBO = distance between 4-row groups
+enum : uint32_t { LAYOUT_SW128 = 2, LAYOUT_SW128_BASE32B = 1 };
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = LAYOUT_SW128) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 

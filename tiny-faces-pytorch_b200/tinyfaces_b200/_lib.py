@@ -16,6 +16,7 @@ c_u32, c_u64, c_vp, c_sz = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_void_p, ct
 
 _SIGS = {
     "tf_version": (c_i32, []),
+    "tf_debug_set": (c_i32, [c_i32, c_i32]),
     "tf_gemm_error_flag": (c_i32, [ctypes.POINTER(c_i32)]),
     "tf_nms_workspace_bytes": (c_i32, [c_i64, c_i32, ctypes.POINTER(c_sz)]),
     "tf_nms": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp, c_vp, c_sz, c_vp]),
@@ -27,6 +28,17 @@ _SIGS = {
     "tf_detloss_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "tf_detloss_sample_workspace_bytes": (c_i32, [c_i32, ctypes.POINTER(c_sz)]),
     "tf_detloss_sample_device": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i32, c_u64, c_vp, c_sz, c_vp]),
+    "tf_model_create": (c_i32, [c_i32, ctypes.POINTER(c_vp)]),
+    "tf_model_destroy": (c_i32, [c_vp]),
+    "tf_model_num_params": (c_i32, [c_vp]),
+    "tf_model_param_name": (ctypes.c_char_p, [c_vp, c_i32]),
+    "tf_model_output_shape": (c_i32, [c_vp, c_i32, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
+    "tf_model_workspace_bytes": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_sz)]),
+    "tf_model_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(c_vp), c_i32, c_i32, c_f32, c_vp, c_vp,
+                                 c_sz, c_vp]),
+    "tf_model_backward": (c_i32, [c_vp, c_vp, ctypes.POINTER(c_vp), c_vp]),
+    "tf_model_get_tensor": (c_i32, [c_vp, ctypes.c_char_p, c_vp, c_i64, ctypes.POINTER(c_i32), c_vp]),
+    "tf_model_upsample_offdiag": (c_i32, [c_vp, ctypes.POINTER(c_f32), c_vp]),
     "tf_conv2d_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "tf_conv2d_wgrad_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
 }

@@ -1,0 +1,184 @@
+"""DetectionModel -- drop-in for /root/reference/tinyfaces/models/model.py:7-128.
+
+Same constructor, same parameter / buffer names (``state_dict`` is key-compatible, including the unused
+``model.fc`` the reference keeps), same ``learnable_parameters`` groups, same ``forward(x) -> [B, 5T, H/8, W/8]``
+NCHW fp32 contract, and it participates in autograd.  The arithmetic, however, never touches torch.nn: the
+whole trunk + heads forward and backward run inside libtinyfaces_b200.so (tcgen05 implicit-GEMM convolutions,
+fused BN / ReLU / residual kernels) through ``tf_model_forward`` / ``tf_model_backward``.  There is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+from torchvision.models import ResNet101_Weights, resnet101
+
+from .. import _lib
+from .._lib import check, lib, stream_ptr
+
+PRECISION = {"fast": 1, "parity": 2}
+
+
+class _Executor:
+    """Owns the C-side model handle, the workspace and the parameter pointer table."""
+
+    def __init__(self, num_templates):
+        h = ctypes.c_void_p()
+        check(lib().tf_model_create(num_templates, ctypes.byref(h)), "tf_model_create")
+        self.handle = h
+        n = lib().tf_model_num_params(h)
+        self.names = [lib().tf_model_param_name(h, i).decode() for i in range(n)]
+        self.workspace = None
+
+    def __del__(self):
+        try:
+            lib().tf_model_destroy(self.handle)
+        except Exception:
+            pass
+
+    def ensure_workspace(self, device, B, H, W, training, mode):
+        sz = ctypes.c_size_t()
+        check(lib().tf_model_workspace_bytes(self.handle, B, H, W, int(training), mode, ctypes.byref(sz)),
+              "tf_model_workspace_bytes")
+        if self.workspace is None or self.workspace.numel() < sz.value or self.workspace.device != device:
+            self.workspace = None
+            self.workspace = torch.empty(sz.value + 4096, dtype=torch.uint8, device=device)
+        return self.workspace
+
+
+class _TrunkFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, *tensors):
+        ex = module._executor
+        _lib.require_cuda(x, "x")
+        if x.dtype != torch.float32:
+            raise RuntimeError("DetectionModel expects float32 input")
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        mode = PRECISION[module.precision]
+        training = bool(module.training)
+        ws = ex.ensure_workspace(x.device, B, H, W, training, mode)
+        table = module._tensor_table()
+        for t in table:
+            if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("DetectionModel parameters must be contiguous float32 tensors on the input's device")
+        ptrs = (ctypes.c_void_p * len(table))(*[t.data_ptr() for t in table])
+        h3, w3 = ctypes.c_int(), ctypes.c_int()
+        check(lib().tf_model_output_shape(ex.handle, H, W, ctypes.byref(h3), ctypes.byref(w3)), "tf_model_output_shape")
+        out = torch.empty((B, 5 * module.num_templates, h3.value, w3.value), dtype=torch.float32, device=x.device)
+        check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, 0.1, out.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
+        if training:
+            for m in module.modules():
+                if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
+                    m.num_batches_tracked += 1
+        ctx.module = module
+        ctx.table = table
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module = ctx.module
+        ex = module._executor
+        grad_out = grad_out.contiguous()
+        named = dict(module.named_parameters())
+        grads = {}
+        ptrs = (ctypes.c_void_p * len(ex.names))()
+        for i, name in enumerate(ex.names):
+            p = named.get(name)
+            if p is not None and p.requires_grad and name != "score4_upsample.weight":
+                g = torch.empty_like(p)
+                grads[name] = g
+                ptrs[i] = g.data_ptr()
+            else:
+                ptrs[i] = None
+        check(lib().tf_model_backward(ex.handle, grad_out.data_ptr(), ptrs, stream_ptr(grad_out.device)),
+              "tf_model_backward")
+        out = [None, None]
+        for name in module._autograd_names:
+            out.append(grads.get(name))
+        return tuple(out)
+
+
+class DetectionModel(nn.Module):
+    """Hybrid-resolution Tiny Faces detector (model.py:7-40), Blackwell-native execution."""
+
+    def __init__(self, base_model=resnet101, pretrained_weights=ResNet101_Weights.IMAGENET1K_V1, num_templates=1,
+                 num_objects=1):
+        super().__init__()
+        if num_objects != 1:
+            raise RuntimeError("tinyfaces_b200 supports num_objects == 1 (the reference's only use, main.py:52)")
+        output = (num_objects + 4) * num_templates            # model.py:19
+        self.num_templates = num_templates
+        self.model = base_model(weights=pretrained_weights)   # parameter container only -- never called
+        del self.model.layer4                                 # model.py:23
+        self.score_res3 = nn.Conv2d(512, output, kernel_size=1, padding=0)
+        self.score_res4 = nn.Conv2d(1024, output, kernel_size=1, padding=0)
+        self.score4_upsample = nn.ConvTranspose2d(output, output, kernel_size=4, stride=2, padding=1, bias=False)
+        self._init_bilinear()
+        self.precision = "fast"
+        self._executor_obj = None
+        self._checked_upsample = False
+
+    @property
+    def _executor(self):
+        if self._executor_obj is None:
+            object.__setattr__(self, "_executor_obj", _Executor(self.num_templates))
+        return self._executor_obj
+
+    def _init_bilinear(self):
+        """model.py:45-65: diagonal bilinear 2x kernel with 1-D taps [.25, .75, .75, .25]."""
+        k = self.score4_upsample.kernel_size[0]
+        factor = np.floor((k + 1) / 2)
+        center = factor if k % 2 == 1 else factor + 0.5
+        taps = 1.0 - np.abs(np.arange(1, k + 1) - center) / factor
+        w = torch.zeros_like(self.score4_upsample.weight)
+        ch = torch.arange(w.shape[0])
+        w[ch, ch] = torch.tensor(np.outer(taps, taps), dtype=w.dtype)
+        self.score4_upsample.weight = nn.Parameter(w)
+
+    def learnable_parameters(self, lr):
+        """model.py:67-87 -- the four optimizer groups."""
+        return [{'params': self.model.parameters(), 'lr': lr},
+                {'params': self.score_res3.parameters(), 'lr': 0.1 * lr},
+                {'params': self.score_res4.parameters(), 'lr': 1 * lr},
+                {'params': self.score4_upsample.parameters(), 'lr': 0}]
+
+    def _tensor_table(self):
+        named = dict(self.named_parameters())
+        named.update(dict(self.named_buffers()))
+        return [named[n].data for n in self._executor.names]
+
+    @property
+    def _autograd_names(self):
+        names = getattr(self, "_ag_names", None)
+        if names is None:
+            params = dict(self.named_parameters())
+            names = [n for n in self._executor.names if n in params]
+            object.__setattr__(self, "_ag_names", names)
+        return names
+
+    def debug_tensor(self, name):
+        """Test hook: NHWC copy of an internal activation of the last forward (see tf_model_get_tensor)."""
+        shape = (ctypes.c_int * 4)()
+        ex = self._executor
+        dev = ex.workspace.device
+        check(lib().tf_model_get_tensor(ex.handle, name.encode(), None, 0, shape, stream_ptr(dev)), "tf_model_get_tensor")
+        t = torch.empty(tuple(shape), dtype=torch.float32, device=dev)
+        check(lib().tf_model_get_tensor(ex.handle, name.encode(), t.data_ptr(), t.numel(), shape, stream_ptr(dev)),
+              "tf_model_get_tensor")
+        return t
+
+    def forward(self, x):
+        params = dict(self.named_parameters())
+        tensors = [params[n] for n in self._autograd_names]
+        out = _TrunkFunction.apply(x, self, *tensors)
+        if not self._checked_upsample:
+            v = ctypes.c_float()
+            check(lib().tf_model_upsample_offdiag(self._executor.handle, ctypes.byref(v), stream_ptr(x.device)),
+                  "tf_model_upsample_offdiag")
+            if v.value != 0.0:
+                raise RuntimeError("score4_upsample.weight is not diagonal (max off-diagonal %g): only the reference's "
+                                   "frozen bilinear kernel (model.py:45-65) is supported" % v.value)
+            self._checked_upsample = True
+        return out

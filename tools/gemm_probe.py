@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tiny-faces-pytorch_b200"))
 sys.path.insert(0, ROOT)
 
-CASES = [
+CASES_OLD = [
     ("fprop", 1, 8, 16, 32, 64, 1), ("fprop", 1, 8, 16, 32, 128, 1), ("fprop", 1, 8, 16, 32, 256, 1),
     ("fprop", 2, 17, 23, 64, 128, 1), ("fprop", 1, 30, 40, 256, 256, 1), ("fprop", 1, 8, 16, 32, 64, 3),
     ("fprop", 2, 15, 20, 256, 256, 3),
@@ -18,9 +18,23 @@ CASES = [
 ]
 
 
+CASES = [
+    ("wgrad", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 128, 128, 1),
+    ("wgrad+plain", 2, 17, 23, 256, 256, 1), ("wgrad+plain", 2, 15, 20, 256, 256, 3),
+    ("fprop+acc", 1, 8, 16, 32, 64, 1), ("fprop+acc", 2, 15, 20, 256, 256, 3), ("wgrad", 2, 15, 20, 256, 256, 3),
+]
+
+
 def run_case(kind, B, H, W, Cin, Cout, k):
     import torch
-    from tinyfaces_b200 import ops
+    from tinyfaces_b200 import ops, _lib
+    if kind.endswith("+plain"):
+        _lib.lib().tf_debug_set(0, 1)
+        kind = "wgrad"
+    acc = kind.endswith("+acc")
+    if acc:
+        _lib.lib().tf_debug_set(1, 1)
+        kind = "fprop"
     d = torch.device("cuda:0")
     gen = torch.Generator().manual_seed(1)
 
@@ -33,10 +47,13 @@ def run_case(kind, B, H, W, Cin, Cout, k):
     if kind == "fprop":
         w = tf32(torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5)
         ref = torch.nn.functional.conv2d(x.double(), w.double(), padding=k // 2).float()
+        y0 = torch.ones((B, H, W, Cout), dtype=torch.float32, device=d) if acc else None
         y = ops.conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(d),
-                            w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous().to(d), k)
+                            w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous().to(d), k, out=y0)
         torch.cuda.synchronize()
         got = y.cpu().permute(0, 3, 1, 2)
+        if acc:
+            ref = ref + 1
     else:
         dy = tf32(torch.randn(B, Cout, H, W, generator=gen))
         w = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
@@ -51,6 +68,9 @@ def run_case(kind, B, H, W, Cin, Cout, k):
     res["got_absmax"] = got.abs().max().item()
     res["ref_absmax"] = ref.abs().max().item()
     res["flag"] = ops.gemm_error_flag()
+    res["nonzero_frac"] = (got != 0).float().mean().item()
+    g, r = got.flatten().double(), ref.flatten().double()
+    res["corr"] = float((g * r).sum() / ((g.norm() * r.norm()) + 1e-30))
     # a few samples to diagnose layout mistakes
     res["got0"] = got.flatten()[:6].tolist()
     res["ref0"] = ref.flatten()[:6].tolist()
