@@ -1,0 +1,85 @@
+/* tinyfaces_b200 -- C ABI of the Blackwell-native hot path of varunagrawal/tiny-faces-pytorch.
+ *
+ * One shared library (libtinyfaces_b200.so), plain pointers and sizes, no torch types.  The reference has no
+ * FFI of its own (it is pure Python over torch / torchvision); each entry point below names the reference
+ * interface it stands in for.  Conventions:
+ *   - every pointer is a DEVICE pointer unless the comment says HOST;
+ *   - the caller owns all memory: outputs and scratch are passed in; `*_workspace_bytes` reports scratch size;
+ *   - variable-size outputs use a caller capacity + a device-side count;
+ *   - `stream` is a cudaStream_t; all work is enqueued on it (thread-safe for distinct streams);
+ *   - return 0 on success, negative on error (tf_last_error_string() has the text);
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef TINYFACES_B200_H
+#define TINYFACES_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* tf_last_error_string(void);
+int tf_version(void);
+int tf_debug_set(int key, int value);            /* test hooks only */
+int tf_gemm_error_flag(int* value_host);         /* HOST out: non-zero if a tcgen05 pipeline wait timed out */
+
+/* ---- greedy NMS: replaces torchvision.ops.nms as called at tinyfaces/evaluation.py:84 (float64 CPU tensors).
+ * boxes [n,4] (x1,y1,x2,y2), scores [n]; elem_bytes 8 (float64) or 4 (float32).  keep [n] int64 receives the
+ * kept ORIGINAL indices in descending-score order; num_keep is a device int64.  Bit-identical to the CPU op:
+ * stable descending sort, area (x2-x1)*(y2-y1), suppress iff inter/(a_i+a_j-inter) > thr. */
+int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes_host);
+int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int64_t* keep,
+           int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- threshold + ordered compaction + anchor decode: replaces get_bboxes + regression_refinement
+ * (tinyfaces/models/utils.py:4-100) and the sigmoid / D2H / transpose of tinyfaces/evaluation.py:61-71.
+ * cls/reg/prob are float32 maps addressed by (b,y,x,channel) element strides, so both the NCHW model output and
+ * the reference's NHWC numpy arrays are accepted; prob == NULL fuses the sigmoid.  templates_host: HOST [T,5]
+ * float64.  invalid_x_mask reproduces the shipped utils.py:44 quirk (bit x: heat-map column x is zeroed);
+ * invalid_t_mask masks templates instead.  Candidates are emitted in C order over (b,y,x,c) (utils.py:46-47). */
+int tf_decode_workspace_bytes(int64_t B, int64_t H, int64_t W, size_t* bytes_host);
+int tf_decode(const float* cls, const float* reg, const float* prob, const int64_t* cls_strides_host,
+              const int64_t* reg_strides_host, int B, int H, int W, int T, const double* templates_host,
+              float prob_thresh, uint32_t invalid_x_mask, uint32_t invalid_t_mask, const int64_t* rf_stride_host,
+              const int64_t* rf_offset_host, double scale, double* boxes, double* scores, int64_t* src_index,
+              int64_t capacity, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- detection loss: replaces DetectionCriterion.forward (tinyfaces/models/loss.py:59-93) and, for the device
+ * sampler, balance_sampling (tinyfaces/models/utils.py:103-163).  NCHW: output [B,5T,H,W], class_map [B,T,H,W],
+ * regression_map [B,4T,H,W]; HW = H*W. */
+int tf_detloss_ohem(const float* output, float* class_map /* in place */, int B, int T, int64_t HW, float thresh,
+                    void* stream);
+int tf_detloss_fwd_bwd(const float* output, const float* labels, const float* regression_map, int B, int T, int64_t HW,
+                       float reg_weight, float* grad_output, double* sums /* [2], accumulated */, void* stream);
+int tf_detloss_sample_workspace_bytes(int B, size_t* bytes_host);
+int tf_detloss_sample_device(float* labels /* [B,L] in place */, int B, int64_t L, int max_pos, int max_neg,
+                             uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- tcgen05 implicit-GEMM convolutions (NHWC fp32 storage, TF32 tensor-core math, fp32 accumulate): the
+ * building block behind every nn.Conv2d of tinyfaces/models/model.py:90-106 and its autograd backward.
+ * w_packed: [Cout][k*k][Cin]; stride 1, "same" padding; x_lo/w_lo: optional low halves for the 3xTF32 mode. */
+int tf_conv2d_nhwc(const float* x, const float* x_lo, int B, int H, int W, int Cin, const float* w_packed,
+                   const float* w_lo, int Cout, int ksize, const float* bias, float* y, void* stream);
+int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
+                         float* dw_packed /* accumulated */, void* stream);
+
+/* ---- whole-model executor: replaces DetectionModel.forward (tinyfaces/models/model.py:89-128) and the backward
+ * autograd derives from it (tinyfaces/trainer.py:86).  params / grads: HOST arrays of tf_model_num_params()
+ * device pointers in tf_model_param_name() order (reference state_dict names; OIHW weights, BN vectors).
+ * mode: 1 = fast (1xTF32), 2 = parity (3xTF32).  x [B,3,H,W] and out [B,5T,H/8,W/8] are NCHW fp32. */
+int tf_model_create(int num_templates, void** handle_host);
+int tf_model_destroy(void* handle);
+int tf_model_num_params(void* handle);
+const char* tf_model_param_name(void* handle, int index);
+int tf_model_output_shape(void* handle, int H, int W, int* H3_host, int* W3_host);
+int tf_model_workspace_bytes(void* handle, int B, int H, int W, int training, int mode, size_t* bytes_host);
+int tf_model_forward(void* handle, const float* x, int B, int H, int W, const void* const* params_host, int training,
+                     int mode, float bn_momentum, float* out, void* workspace, size_t workspace_bytes, void* stream);
+int tf_model_backward(void* handle, const float* dout, void* const* grads_host, void* stream);
+int tf_model_get_tensor(void* handle, const char* name, float* dst, int64_t capacity, int* shape4_host, void* stream);
+int tf_model_upsample_offdiag(void* handle, float* value_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,147 @@
+"""GPU parity of the reference-facing call surface (DetectionCriterion, get_bboxes, nms, get_detections, train)
+against the reference-generated goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_detection_criterion_matches_reference(case):
+    """Same np.random seed -> same sampled label set, loss and gradient as the reference's DetectionCriterion."""
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    g = np.load(os.path.join(G, "loss_case%d.npz" % case))
+    rw = float(g["reg_weight"]) if "reg_weight" in g.files else 1
+    crit = DetectionCriterion(25, reg_weight=rw)
+    out = torch.from_numpy(g["output"]).cuda().requires_grad_(True)
+    cm = torch.from_numpy(g["class_map"].copy()).cuda()
+    np.random.seed(int(g["np_seed"]))
+    loss = crit(out, cm, torch.from_numpy(g["regression_map"]).cuda())
+    loss.backward()
+    assert loss.dim() == 0
+    assert abs(float(loss) - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
+    assert abs(float(crit.masked_class_loss) - float(g["cls_sum"])) <= 1e-5 * abs(float(g["cls_sum"]))
+    assert abs(float(crit.masked_reg_loss) - float(g["reg_sum"])) <= 1e-5 * abs(float(g["reg_sum"]))
+    np.testing.assert_allclose(out.grad.cpu().numpy(), g["grad"], rtol=1e-5, atol=1e-6)
+    # in-place OHEM on the caller's tensor (the CUDA behaviour of loss.py:62): labels with loss < 0.03 are zeroed
+    from oracle import loss_oracle
+    ref_cm = g["class_map"].copy()
+    loss_oracle.hard_negative_mining(g["output"][:, :25], ref_cm)
+    assert np.array_equal(cm.cpu().numpy(), ref_cm)
+    if "class_avg" in g.files:
+        assert abs(crit.class_average.average - float(g["class_avg"])) <= 1e-5 * abs(float(g["class_avg"]))
+        assert abs(crit.reg_average.average - float(g["reg_avg"])) <= 1e-5 * abs(float(g["reg_avg"]))
+    # upstream gradient scaling goes through autograd
+    out2 = torch.from_numpy(g["output"]).cuda().requires_grad_(True)
+    np.random.seed(int(g["np_seed"]))
+    (3.0 * DetectionCriterion(25, reg_weight=rw)(out2, torch.from_numpy(g["class_map"].copy()).cuda(),
+                                                  torch.from_numpy(g["regression_map"]).cuda())).backward()
+    np.testing.assert_allclose(out2.grad.cpu().numpy(), 3.0 * g["grad"], rtol=1e-5, atol=1e-6)
+
+
+def test_detection_criterion_device_sampler_statistics():
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    g = np.load(os.path.join(G, "loss_case0.npz"))
+    crit = DetectionCriterion(25, sampler="device", seed=3)
+    out = torch.from_numpy(g["output"]).cuda().requires_grad_(True)
+    loss = crit(out, torch.from_numpy(g["class_map"].copy()).cuda(), torch.from_numpy(g["regression_map"]).cuda())
+    loss.backward()
+    active = (out.grad[:, :25] != 0).sum(dim=(1, 2, 3)).cpu().numpy()
+    assert np.all(active == 256)                      # 128 positives + 128 negatives per image survive
+    assert 0.3 * float(g["total"]) < float(loss) < 3 * float(g["total"])
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_get_bboxes_shim(case):
+    from oracle import synth
+    from tinyfaces_b200.models.utils import get_bboxes
+    from test_gpu_ops import _assert_boxes_close
+    g = np.load(os.path.join(G, "decode_case%d.npz" % case))
+    prob = g["prob_cls"].copy()
+    boxes, scores = get_bboxes(g["score_cls"], g["score_reg"], prob, synth.load_templates(), float(g["thresh"]),
+                               synth.RF, float(g["scale"]))
+    assert np.array_equal(prob, g["prob_after"])                  # same in-place side effect as utils.py:44
+    assert boxes.dtype == np.float64 and scores.dtype == np.float32 and scores.shape == g["scores"].shape
+    assert np.array_equal(scores, g["scores"])
+    _assert_boxes_close(boxes, g["boxes"])
+    with pytest.raises(IndexError):                                # heat map narrower than 25 columns
+        z = np.zeros((1, 4, 20, 25), np.float32)
+        get_bboxes(z, np.zeros((1, 4, 20, 100), np.float32), z.copy(), synth.load_templates(), 0.5, synth.RF, 1)
+
+
+def test_nms_shim_is_torchvision_compatible():
+    from tinyfaces_b200.evaluation import nms
+    g = np.load(os.path.join(G, "nms_case0.npz"))
+    b, s = torch.from_numpy(g["boxes"]), torch.from_numpy(g["scores"])
+    k = nms(b, s, float(g["thr"]))                                  # CPU in -> CPU out
+    assert k.dtype == torch.int64 and k.device.type == "cpu" and np.array_equal(k.numpy(), g["keep"])
+    k2 = nms(b.cuda(), s.cuda(), float(g["thr"]))
+    assert k2.is_cuda and np.array_equal(k2.cpu().numpy(), g["keep"])
+    with pytest.raises(RuntimeError):
+        nms(b, s.float(), 0.3)
+    assert nms(torch.zeros((0, 4), dtype=torch.float64), torch.zeros(0, dtype=torch.float64), 0.3).shape == (0,)
+
+
+def _match_fraction(a, b, tol):
+    """fraction of rows of b that have a row of a within tol (max-abs)"""
+    if len(b) == 0:
+        return 1.0
+    if len(a) == 0:
+        return 0.0
+    hit = 0
+    for row in b:
+        hit += bool((np.abs(a - row).max(axis=1) <= tol).any())
+    return hit / len(b)
+
+
+def test_get_detections_end_to_end_vs_reference():
+    """Pyramid inference + decode + global NMS vs the reference's get_detections on the same image and weights."""
+    from oracle import synth
+    from torchvision import transforms
+    from tinyfaces_b200.evaluation import get_detections
+    from tinyfaces_b200.models.model import DetectionModel
+    g = np.load(os.path.join(G, "detections_case0.npz"))
+    sd = synth.synthetic_state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1)
+    xc = torch.randn(2, 3, 96, 136, generator=torch.Generator().manual_seed(4))
+    sd = synth.calibrate_running_stats(sd, xc)
+    m = DetectionModel(pretrained_weights=None, num_templates=25)
+    m.load_state_dict(sd)
+    m.precision = "parity"
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+    with torch.no_grad():
+        dets = get_detections(m, torch.from_numpy(g["img"]), synth.load_templates(), synth.RF, tf,
+                              prob_thresh=float(g["thresh"]), nms_thresh=0.3, scales=tuple(g["scales"]),
+                              device=torch.device("cuda:0"))
+    ref = g["dets"]
+    assert dets.dtype == np.float64 and dets.shape[1] == 4
+    # logits agree to ~1e-4 relative, so a handful of near-threshold candidates / near-tie NMS decisions may differ
+    assert abs(len(dets) - len(ref)) <= max(3, 0.02 * len(ref)), (len(dets), len(ref))
+    assert _match_fraction(dets, ref, tol=0.05) > 0.97
+    assert _match_fraction(ref, dets, tol=0.05) > 0.97
+
+
+def test_train_loop_runs_and_updates():
+    """trainer.train on a 2-batch synthetic loader: loss finite, parameters move, BN buffers update."""
+    from oracle import synth
+    from tinyfaces_b200 import synthetic
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    from tinyfaces_b200.models.model import DetectionModel
+    from tinyfaces_b200.trainer import train
+    sd = synth.synthetic_state_dict(seed=1, bn3_gamma=0.25)
+    m = DetectionModel(pretrained_weights=None, num_templates=25)
+    m.load_state_dict(sd)
+    crit = DetectionCriterion(25, sampler="device")
+    opt = torch.optim.SGD(m.learnable_parameters(1e-3), momentum=0.9, weight_decay=5e-4)
+    cm, rm = synthetic.targets(2, 13, 16, seed=0, p_neg=0.7, p_pos=0.1)
+    loader = [(synthetic.images(2, 100, 128, seed=i), cm.clone(), rm.clone()) for i in range(2)]
+    w0 = m.model.layer3[5].conv2.weight.detach().clone()
+    up0 = m.score4_upsample.weight.detach().clone()
+    train(m, crit, opt, loader, 0, torch.device("cuda:0"))
+    assert np.isfinite(crit.class_average.average) and np.isfinite(crit.reg_average.average)
+    assert not torch.equal(m.model.layer3[5].conv2.weight.detach().cpu(), w0)
+    assert torch.equal(m.score4_upsample.weight.detach().cpu(), up0)          # lr 0 group never moves
+    assert int(m.model.bn1.num_batches_tracked) == 2

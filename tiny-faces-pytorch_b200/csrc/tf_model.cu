@@ -531,11 +531,11 @@ TF_API int tf_model_get_tensor(void* handle, const char* name, float* dst, int64
     Model* m = reinterpret_cast<Model*>(handle);
     TF_REQUIRE(!m->ar.dry && m->ar.base, "tf_model_get_tensor: no forward state");
     const std::string n(name);
-    const float* src = nullptr; int B = m->B, H = 0, W = 0, C = 0;
+    const float* src = nullptr; const float* src_lo = nullptr; int B = m->B, H = 0, W = 0, C = 0;
     if (n == "stem") { src = m->stem_u.a; H = m->H2; W = m->W2; C = 64; }
     else if (n == "stem.y") { src = m->stem_u.y; H = m->H2; W = m->W2; C = 64; }
     else if (n == "col") { src = m->col; H = m->H2; W = m->W2; C = 160; }
-    else if (n == "pool") { src = m->pool; H = m->Hp; W = m->Wp; C = 64; }
+    else if (n == "pool") { src = m->pool; src_lo = m->pool_lo; H = m->Hp; W = m->Wp; C = 64; }
     else if (n.rfind("block", 0) == 0) {
         const size_t dot = n.find('.');
         TF_REQUIRE(dot != std::string::npos, "tf_model_get_tensor: bad name %s", name);
@@ -543,11 +543,12 @@ TF_API int tf_model_get_tensor(void* handle, const char* name, float* dst, int64
         TF_REQUIRE(i >= 0 && i < (int)m->bs.size(), "tf_model_get_tensor: bad block index in %s", name);
         const BlockS& s = m->bs[i];
         const std::string rest = n.substr(dot + 1);
-        if (rest == "out") { src = s.out; H = s.Ho; W = s.Wo; C = s.u3.c.cout; }
+        if (rest == "out") { src = s.out; src_lo = s.out_lo; H = s.Ho; W = s.Wo; C = s.u3.c.cout; }
         else {
             const Unit* u = rest[1] == '1' ? &s.u1 : rest[1] == '2' ? &s.u2 : rest[1] == '3' ? &s.u3 : &s.ud;
             H = u->Ho; W = u->Wo; C = u->c.cout;
             src = rest.back() == 'y' ? u->y : u->a;
+            if (rest.back() != 'y') src_lo = u->a_lo;
         }
     }
     TF_REQUIRE(src, "tf_model_get_tensor: unknown or empty tensor %s", name);
@@ -555,7 +556,8 @@ TF_API int tf_model_get_tensor(void* handle, const char* name, float* dst, int64
     const int64_t cnt = (int64_t)B * H * W * C;
     if (dst) {
         TF_REQUIRE(capacity >= cnt, "tf_model_get_tensor: capacity too small");
-        TF_CHECK_CUDA(cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        if (src_lo) RC(tfe::masked_add(src, nullptr, src_lo, cnt, dst, (cudaStream_t)stream));     // parity mode: hi + lo
+        else TF_CHECK_CUDA(cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }
     return TF_OK;
 }

@@ -1,0 +1,151 @@
+"""get_detections / nms -- drop-ins for /root/reference/tinyfaces/evaluation.py:20-87 and the
+``torchvision.ops.nms`` call it makes (evaluation.py:84).
+
+Per pyramid level only the resized image goes up and nothing comes down: forward, sigmoid + threshold +
+order-preserving compaction + anchor decode (``tf_decode``) and the final global NMS (``tf_nms``) stay on the GPU;
+the K kept boxes are the only device->host copy.  (The reference copies 150 floats per heat-map pixel per level
+to the host, evaluation.py:64-68, and runs NMS single-threaded on the CPU.)
+"""
+import numpy as np
+import torch
+from torchvision import transforms
+
+from . import ops
+from .models.utils import _bitmask, invalid_template_ids
+
+
+def nms(boxes, scores, iou_threshold):
+    """torchvision.ops.nms(boxes[N,4], scores[N], iou_threshold) -> int64[K] (descending score), bit-identical
+    keep indices.  CPU inputs are moved to the current CUDA device and the result is returned on the input's
+    device, like the op it replaces."""
+    if boxes.dtype != scores.dtype:
+        raise RuntimeError("nms: boxes and scores should have the same dtype")
+    src = boxes.device
+    dev = src if boxes.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    keep, count = ops.nms_device(boxes.to(dev), scores.to(dev), iou_threshold)
+    return keep[: int(count.item())].to(src)
+
+
+def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True):
+    """Device-side replacement of evaluation.py:61-71 for one pyramid level.
+    output: [B,5T,H,W] CUDA tensor.  Returns (boxes f64 [N,4], scores f64 [N]) on the device."""
+    B, C, H, W = output.shape
+    T = templates.shape[0]
+    if bug_compat and W < 25:
+        raise IndexError("index 24 is out of bounds for axis 2 with size %d" % W)   # the reference's failure mode
+    inv = _bitmask(invalid_template_ids(templates, scale))
+    hw = H * W
+    strides = (C * hw, W, 1, hw)                       # (b, y, x, c) element strides of an NCHW tensor
+    out = output.contiguous()
+    boxes, scores, _, count = ops.decode_device(out, out[:, T:], None, strides, strides, B, H, W, T, templates,
+                                                prob_thresh, inv if bug_compat else 0, 0 if bug_compat else inv, rf, scale)
+    n = int(count.item())
+    return boxes[:n], scores[:n]
+
+
+def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3, scales=(-2, -1, 0, 1),
+                   device=None, return_scores=False):
+    """evaluation.py:20-87.  img: CHW float tensor in [0,1]; scales are exponents of 2; returns ndarray [K,4] float64."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    model = model.to(device)
+    model.eval()
+    templates = np.asarray(templates, dtype=np.float64)
+    image = transforms.functional.to_pil_image(img)                 # evaluation.py:40
+    min_side = np.min(image.size)
+    all_boxes, all_scores = [], []
+    for scale in [2 ** x for x in scales]:                          # evaluation.py:37,44
+        scaled = transforms.functional.resize(image, int(min_side * scale))
+        x = img_transforms(scaled).unsqueeze(0).float().to(device, non_blocking=True)
+        with torch.no_grad():
+            output = model(x)
+        b, s = decode_level(output, templates, prob_thresh, rf, scale)
+        all_boxes.append(b)
+        all_scores.append(s)
+    boxes = torch.cat(all_boxes) if all_boxes else torch.zeros((0, 4), dtype=torch.float64, device=device)
+    scores = torch.cat(all_scores) if all_scores else torch.zeros(0, dtype=torch.float64, device=device)
+    keep, count = ops.nms_device(boxes, scores, nms_thresh)         # evaluation.py:84
+    keep = keep[: int(count.item())]
+    dets = boxes[keep].cpu().numpy()                                # evaluation.py:85-87
+    if return_scores:
+        return dets, scores[keep].cpu().numpy()
+    return dets
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU
+def gather_level_candidates(per_level, num_levels, group=None, dst=0):
+    """Scale-sharded inference exchange step.  ``per_level``: {level_index: (boxes [n,4] f64, scores [n] f64)} for
+    the pyramid levels this rank evaluated.  Every rank contributes its levels; rank ``dst`` receives all
+    candidates concatenated in level order (the reference's ``scales`` order, evaluation.py:78) -- which is what
+    makes the global NMS keep indices identical to the single-GPU run.  Returns (boxes, scores) on ``dst`` and
+    (None, None) elsewhere.  Variable sizes are exchanged first, payloads are padded to the maximum."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    any_t = next(iter(per_level.values()))[0] if per_level else None
+    dev = any_t.device if any_t is not None else torch.device("cpu")
+    counts = torch.zeros(num_levels, dtype=torch.int64, device=dev)
+    for lv, (b, _s) in per_level.items():
+        counts[lv] = b.shape[0]
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    total = torch.stack(all_counts).sum(0)                       # per-level totals (each level lives on one rank)
+    mine = sorted(per_level)
+    payload = torch.cat([torch.cat([per_level[lv][0], per_level[lv][1][:, None]], dim=1) for lv in mine]) \
+        if mine else torch.zeros((0, 5), dtype=torch.float64, device=dev)
+    sizes = [int(c.sum().item()) for c in all_counts]
+    cap = max(max(sizes), 1)
+    padded = torch.zeros((cap, 5), dtype=torch.float64, device=dev)
+    padded[: payload.shape[0]] = payload
+    gathered = [torch.zeros_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None, None
+    chunks = [None] * num_levels
+    for r in range(world):
+        off = 0
+        for lv in range(num_levels):
+            n = int(all_counts[r][lv].item())
+            if n:
+                chunks[lv] = gathered[r][off:off + n]
+                off += n
+    cat = torch.cat([c for c in chunks if c is not None]) if any(c is not None for c in chunks) \
+        else torch.zeros((0, 5), dtype=torch.float64, device=dev)
+    assert cat.shape[0] == int(total.sum().item())
+    return cat[:, :4].contiguous(), cat[:, 4].contiguous()
+
+
+def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3,
+                           scales=(-2, -1, 0, 1), device=None, group=None):
+    """get_detections with one pyramid level per rank (round-robin when there are more levels than ranks), a
+    candidate gather to rank 0 and the global NMS there.  Rank 0 returns ndarray [K,4]; other ranks return None."""
+    import torch.distributed as dist
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    model = model.to(device)
+    model.eval()
+    templates = np.asarray(templates, dtype=np.float64)
+    image = transforms.functional.to_pil_image(img)
+    min_side = np.min(image.size)
+    levels = [2 ** x for x in scales]
+    # largest levels first onto distinct ranks (cost ~ 4^exponent): simple longest-processing-time packing
+    order = sorted(range(len(levels)), key=lambda i: -levels[i])
+    load = [0.0] * world
+    owner = {}
+    for i in order:
+        r = min(range(world), key=lambda k: load[k])
+        owner[i] = r
+        load[r] += levels[i] ** 2
+    per_level = {}
+    for i, scale in enumerate(levels):
+        if owner[i] != rank:
+            continue
+        scaled = transforms.functional.resize(image, int(min_side * scale))
+        x = img_transforms(scaled).unsqueeze(0).float().to(device, non_blocking=True)
+        with torch.no_grad():
+            output = model(x)
+        per_level[i] = decode_level(output, templates, prob_thresh, rf, scale)
+    boxes, scores = gather_level_candidates(per_level, len(levels), group=group, dst=0)
+    if rank != 0:
+        return None
+    keep, count = ops.nms_device(boxes, scores, nms_thresh)
+    return boxes[keep[: int(count.item())]].cpu().numpy()

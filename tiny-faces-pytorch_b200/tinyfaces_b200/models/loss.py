@@ -1,0 +1,115 @@
+"""DetectionCriterion -- drop-in for /root/reference/tinyfaces/models/loss.py:24-97.
+
+OHEM, the masked SoftMargin + SmoothL1 sums and their gradient run in the library's kernels
+(``tf_detloss_ohem``, ``tf_detloss_fwd_bwd``: one fused forward+backward pass); balance sampling is either the
+reference's host-side numpy procedure (``sampler='numpy'``: identical ``np.random`` consumption, identical label
+maps) or the device sampler (``sampler='device'``: statistically equivalent, no host round trip).
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from .utils import balance_sampling
+
+
+class AvgMeter:
+    """loss.py:7-21 with the accumulation kept on the device: reading ``average`` is the only sync point."""
+
+    def __init__(self):
+        self.reset()
+
+    def update(self, loss, size):
+        n = self.num_averaged
+        m = n + size
+        loss = loss.detach() if isinstance(loss, torch.Tensor) else loss
+        self._average = ((n * self._average) + loss) / m
+        self.num_averaged = m
+
+    @property
+    def average(self):
+        a = self._average
+        return float(a) if isinstance(a, torch.Tensor) else a
+
+    def reset(self):
+        self._average = 0
+        self.num_averaged = 0
+
+
+class _LossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, output, labels, regression_map, reg_weight):
+        sums, grad = ops.detloss_fwd_bwd(output, labels, regression_map, reg_weight)
+        ctx.save_for_backward(grad)
+        sums32 = sums.to(torch.float32)
+        total = sums32[0] + reg_weight * sums32[1]
+        ctx.mark_non_differentiable(sums32)
+        return total, sums32
+
+    @staticmethod
+    def backward(ctx, g_total, _g_sums):
+        (grad,) = ctx.saved_tensors
+        return grad * g_total, None, None, None
+
+
+class DetectionCriterion(nn.Module):
+    """The loss for the Tiny Faces detector (loss.py:24-97)."""
+
+    def __init__(self, n_templates=25, reg_weight=1, pos_fraction=0.5, sampler="numpy", sample_size=256, seed=0):
+        super().__init__()
+        if sampler not in ("numpy", "device"):
+            raise ValueError("sampler must be 'numpy' (reference RNG protocol) or 'device'")
+        self.n_templates = n_templates
+        self.reg_weight = reg_weight
+        self.pos_fraction = pos_fraction
+        self.sampler = sampler
+        self.sample_size = sample_size
+        self._seed = seed
+        self._step = 0
+        self.class_average = AvgMeter()
+        self.reg_average = AvgMeter()
+        self.masked_class_loss = None       # 0-dim tensors: the masked SUMS (the reference's per-element maps are
+        self.masked_reg_loss = None         # only ever consumed through .sum(), loss.py:87-91)
+        self.total_loss = None
+
+    def hard_negative_mining(self, output, class_map):
+        """loss.py:59-63, in place on class_map.  Takes the full [B,5T,H,W] output (the kernel reads its
+        classification channels in place instead of slicing a copy)."""
+        ops.detloss_ohem_(output.detach().contiguous(), class_map)
+        return class_map
+
+    def balance_sample(self, class_map):
+        """loss.py:47-57: per-image balance sampling; returns a NEW label tensor (the CUDA behaviour of the
+        reference, where .cpu().numpy() is a copy)."""
+        if self.sampler == "numpy":
+            lab = class_map.cpu().numpy()
+            for i in range(lab.shape[0]):
+                balance_sampling(lab[i], pos_fraction=self.pos_fraction, sample_size=self.sample_size)
+            return torch.from_numpy(lab).to(class_map.device)
+        lab = class_map.clone()
+        max_pos = int(self.sample_size * self.pos_fraction)
+        max_neg = int(max_pos * (1 - self.pos_fraction) / self.pos_fraction)
+        self._step += 1
+        ops.detloss_sample_device_(lab, max_pos, max_neg, seed=(self._seed << 32) + self._step)
+        return lab
+
+    def forward(self, output, class_map, regression_map):
+        if not output.is_cuda:
+            raise RuntimeError("DetectionCriterion: output must be a CUDA tensor (no CPU fallback)")
+        out_c = output.contiguous()
+        cm = class_map if (class_map.is_contiguous() and class_map.dtype == torch.float32) else class_map.float().contiguous()
+        ops.detloss_ohem_(out_c.detach(), cm)                       # loss.py:70 (in place)
+        if cm is not class_map:
+            class_map.copy_(cm)
+        labels = self.balance_sample(cm)                            # loss.py:72
+        total, sums = _LossFunction.apply(out_c, labels, regression_map.float().contiguous(), float(self.reg_weight))
+        self.masked_class_loss = sums[0]
+        self.masked_reg_loss = sums[1]
+        self.total_loss = total
+        self.class_average.update(sums[0], output.size(0))          # loss.py:90-91
+        self.reg_average.update(sums[1], output.size(0))
+        return total
+
+    def reset(self):
+        self.class_average.reset()
+        self.reg_average.reset()
