@@ -67,11 +67,31 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_reference_step_rate(steps, warmup, sample_hw=(960, 1280), batch=1):
-    """The reference's CPU path (oracle port: same torch CPU ops, same loss incl. the numpy sampler), fp32,
-    all host threads.  Returns (images/s, cores, sample description)."""
-    from oracle import loss_oracle, model_oracle, synth
+def _best_thread_count():
+    """torch CPU convs stop scaling (and then regress) well before 128 threads: pick the fastest count on a tiny conv."""
+    import torch.nn.functional as F
     cores = os.cpu_count() or 1
+    x = torch.randn(1, 256, 60, 80)            # the dominant layer3 3x3 at the sampled size
+    w = torch.randn(256, 256, 3, 3)
+    best, best_t = 1, 1e30
+    for n in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
+        torch.set_num_threads(n)
+        F.conv2d(x, w, padding=1)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            F.conv2d(x, w, padding=1)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = n, t
+    return best
+
+
+def cpu_reference_step_rate(steps, warmup, sample_hw=(480, 640), batch=1):
+    """The reference's CPU path (oracle port: same torch CPU ops, same loss incl. the numpy sampler), fp32, on the
+    host threads that run it fastest.  The sample is B=1 at 480x640 (a quarter of the 960x1280 image: per-image conv
+    cost is proportional to area), scaled to 960x1280-image units.  Returns (images/s, threads, sample description)."""
+    from oracle import loss_oracle, model_oracle, synth
+    cores = _best_thread_count()
     torch.set_num_threads(cores)
     H, W = sample_hw
     sd = synth.synthetic_state_dict(seed=0)
@@ -99,7 +119,9 @@ def cpu_reference_step_rate(steps, warmup, sample_hw=(960, 1280), batch=1):
         if it >= warmup:
             times.append(dt)
     t = float(np.mean(times))
-    return batch / t, cores, "%d timed step(s) of B=%d %dx%d on %d host threads (mean %.2f s/step)" % (steps, batch, H, W, cores, t)
+    area = (H * W) / float(H_IMG * W_IMG)
+    return batch * area / t, cores, ("%d timed step(s) of B=%d %dx%d on %d of %d host threads (mean %.2f s/step), scaled by "
+                                     "area to %dx%d images" % (steps, batch, H, W, cores, os.cpu_count() or 1, t, H_IMG, W_IMG))
 
 
 def run_reference(args):
@@ -126,10 +148,13 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nms-n", type=int, default=100000)
+    ap.add_argument("--breakdown", default="", help="write a per-kernel time table of one step to this file")
+    ap.add_argument("--profile-mode", action="store_true", help="only the timed steps (for runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    args.warmup = max(args.warmup, 3)
+    if not args.profile_mode:
+        args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
     from tinyfaces_b200 import ops, synthetic
@@ -189,6 +214,10 @@ def main():
     sampler.start()
     ms_total = timed(step_resident, args.steps, args.warmup)
     sampler.stop_flag = True
+    if args.profile_mode:
+        if rank == 0:
+            print(json.dumps(dict(profile_mode=True, ms_per_step=ms_total / args.steps)))
+        return
     ms_e2e = timed(step_e2e, args.steps, 1)
     imgs = B * world * args.steps
     value = imgs / (ms_total / 1000.0)
@@ -224,6 +253,17 @@ def main():
             tot = sum(e.device_time for e in ev) or 1.0
             gemm = sum(e.device_time for e in ev if "conv_gemm_kernel" in e.name or "conv_wgrad_kernel" in e.name)
             line["gemm_share_of_step"] = gemm / tot
+            if args.breakdown:
+                agg = {}
+                for e in ev:
+                    a = agg.setdefault(e.name[:110], [0, 0.0])
+                    a[0] += 1
+                    a[1] += e.device_time
+                with open(args.breakdown, "w") as f:
+                    f.write("# one training step, batch-8 960x1280, torch.profiler (CUPTI) device times\n")
+                    f.write("%-112s %6s %10s %6s\n" % ("kernel", "calls", "total_us", "share"))
+                    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                        f.write("%-112s %6d %10.1f %5.1f%%\n" % (k, n, t, 100.0 * t / tot))
         except Exception as ex:      # noqa: BLE001
             line["gpu_launches"] = None
             line["profiler_error"] = str(ex)[:200]

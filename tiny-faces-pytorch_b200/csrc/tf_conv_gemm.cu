@@ -47,6 +47,8 @@ struct GemmParams {
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
     int relu, round_out;
     int accumulate;               // 1: D += result (TMA reduce-add) instead of D = result
+    float* stats_partial;         // optional BN statistics: [grid/num_n_tiles*4][2][Cout] per-channel (sum, sum^2) partials
+    int cout;                     //   of the raw accumulators (needs gridDim.x % num_n_tiles == 0: fixed n-tile per CTA)
     int* err_flag;
 };
 
@@ -169,6 +171,9 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int row = q * 32 + lane;
         const bool store_thread = threadIdx.x == 64;
         int it = 0, ebuf = 0;
+        float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
@@ -183,7 +188,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int chunk = 0; chunk < BN / 32; ++chunk) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chunk * 32, r);
@@ -217,7 +222,27 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                     }
                     tma_store_commit();
                 }
+                if (p.stats_partial) {
+                    // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged tile
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int rw = q * 32 + rr;
+                        const float v = *reinterpret_cast<const float*>(buf + rw * 128 + (((lane >> 2) ^ (rw & 7)) << 4) + ((lane & 3) << 2));
+                        s0 += v; s1 += v * v;
+                    }
+                    st_sum[chunk] += s0; st_sq[chunk] += s1;
+                }
                 ebuf ^= 1;
+            }
+        }
+        if (p.stats_partial) {
+            const int n0 = (blockIdx.x % p.num_n_tiles) * BN;
+            float* dst = p.stats_partial + (size_t)((blockIdx.x / p.num_n_tiles) * 4 + q) * 2 * p.cout;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                dst[n0 + c * 32 + lane] = st_sum[c];
+                dst[p.cout + n0 + c * 32 + lane] = st_sq[c];
             }
         }
         if (store_thread) tma_store_wait_all<0>();
@@ -438,7 +463,8 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st) {
         attr_set = true;
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    grid = grid / p.num_n_tiles * p.num_n_tiles;          // every CTA keeps one n-tile (see stats_partial)
     conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -486,6 +512,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     p.taps = taps; p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
+    p.stats_partial = a.stats_partial; p.cout = Cout;
     p.err_flag = g_err_flag;
     p.num_n_tiles = Cout / BN;
     const float* as[3] = {a.x, a.x_lo, a.x};
@@ -509,6 +536,11 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     }
     for (int s = 0; s < p.nseg; ++s)
         if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
+    if (a.stats_blocks) {
+        const int tiles = p.num_m_tiles * p.num_n_tiles;
+        const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / p.num_n_tiles * p.num_n_tiles;
+        *a.stats_blocks = grid / p.num_n_tiles * 4;
+    }
     if (BN == 256) return launch_gemm<256>(maps, p, st);
     if (BN == 128) return launch_gemm<128>(maps, p, st);
     return launch_gemm<64>(maps, p, st);

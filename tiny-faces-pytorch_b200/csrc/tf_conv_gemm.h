@@ -11,6 +11,8 @@ struct ConvArgs {
     const float* scale; const float* shift;// optional per-channel epilogue (shift alone = bias)
     int relu, round_out, accumulate;
     float* y;                              // NHWC output
+    float* stats_partial;                  // optional: per-channel (sum, sum^2) partials of the raw output,
+    int* stats_blocks;                     //   [*stats_blocks][2][Cout] (HOST out: number of partial rows written)
 };
 int conv_fprop(const ConvArgs& a, cudaStream_t st);
 

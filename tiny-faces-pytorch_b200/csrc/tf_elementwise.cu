@@ -446,6 +446,14 @@ int bn_stats_train(const float* y, long long M, int C, const float* gamma, const
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
+                      float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
+                      float* save_rstd, cudaStream_t st) {
+    bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
+                                                              run_var, scale, shift, save_mean, save_rstd);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
 int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
                         float eps, float* scale, float* shift, cudaStream_t st) {
     bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, run_mean, run_var, eps, scale, shift);

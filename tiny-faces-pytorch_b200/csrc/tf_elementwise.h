@@ -9,6 +9,9 @@ constexpr int COLREDUCE_MAX_BLOCKS = 592;     // partial buffers hold COLREDUCE_
 int bn_stats_train(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
                    float* run_mean, float* run_var, float* scale, float* shift, float* save_mean, float* save_rstd,
                    float* partial, cudaStream_t st);
+int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
+                      float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
+                      float* save_rstd, cudaStream_t st);
 int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
                         float eps, float* scale, float* shift, cudaStream_t st);
 int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,

@@ -59,7 +59,7 @@ struct Model {
     // ---- state of the last forward (training) ----
     int B = 0, H = 0, W = 0, mode = 1, training = 0;
     Arena ar;
-    const void* const* params = nullptr;
+    std::vector<const void*> params;     // copied from the caller's table at every forward (backward reuses it)
     Unit stem_u; float* col = nullptr; float* col_lo = nullptr; int H2 = 0, W2 = 0, Hp = 0, Wp = 0;
     float* pool = nullptr; float* pool_lo = nullptr;
     std::vector<BlockS> bs;
@@ -109,7 +109,7 @@ struct Model {
     }
     // conv (+ stride handling) producing the raw output u.y at (Ho, Wo); fused != 0: eval epilogue scale/shift(/relu)
     int run_conv(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, int fused, int relu, float* fused_out,
-                 cudaStream_t st) {
+                 cudaStream_t st, int* stats_blocks = nullptr) {
         const ConvP& c = u.c;
         u.B = B_;
         const int Ho = c.stride == 2 ? (H_ + 1) / 2 : H_, Wo = c.stride == 2 ? (W_ + 1) / 2 : W_;
@@ -134,9 +134,25 @@ struct Model {
             if (!ar.dry) { RC(tfg::conv_fprop(a, st)); RC(tfe::subsample2(yf, nullptr, B_, H_, W_, c.cout, dst, nullptr, st)); }
         } else {
             a.y = dst;
+            if (stats_blocks) { a.stats_partial = partial; a.stats_blocks = stats_blocks; }   // BN statistics in the epilogue
             if (!ar.dry) RC(tfg::conv_fprop(a, st));
         }
         u.y = dst;
+        return TF_OK;
+    }
+    // conv whose training-mode BN statistics come out of the GEMM epilogue (separate reduction only for 3x3/s2)
+    int conv_with_stats(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, cudaStream_t st) {
+        if (!training) return run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st);
+        if (u.c.k == 3 && u.c.stride == 2) {
+            RC(run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st));
+            return bn_stats(u, st);
+        }
+        int nblk = 0;
+        RC(run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st, &nblk));
+        RC(alloc_bn(u));
+        const long long M = (long long)u.B * u.Ho * u.Wo;
+        if (!ar.dry) RC(tfe::bn_finalize_train(partial, nblk, M, u.bn.C, P(u.bn.gamma), P(u.bn.beta), eps, momentum, PW(u.bn.rm),
+                                               PW(u.bn.rv), u.scale, u.shift, u.mean, u.rstd, st));
         return TF_OK;
     }
     int alloc_bn(Unit& u) {
@@ -167,8 +183,7 @@ struct Model {
             return TF_OK;
         }
         if (!training) RC(bn_prepare_eval(u, st));
-        RC(run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st));
-        if (training) RC(bn_stats(u, st));
+        RC(conv_with_stats(u, x, x_lo, B_, H_, W_, st));
         u.a = ar.f((size_t)M * u.c.cout);
         u.a_lo = mode == 2 ? ar.f((size_t)M * u.c.cout) : nullptr;
         if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M, u.c.cout, u.a, u.a_lo, mode, st));
@@ -186,8 +201,7 @@ struct Model {
         const long long Mo = (long long)B_ * Ho * Wo;
         const int C4 = bp.c3.cout;
         if (!training) RC(bn_prepare_eval(s.u3, st));
-        RC(run_conv(s.u3, s.u2.a, s.u2.a_lo, B_, Ho, Wo, 0, 0, nullptr, st));
-        if (training) RC(bn_stats(s.u3, st));
+        RC(conv_with_stats(s.u3, s.u2.a, s.u2.a_lo, B_, Ho, Wo, st));
         const float* res = x; const float* rscale = nullptr; const float* rshift = nullptr;
         if (bp.has_ds) {
             if (!training && mode == 1) {
@@ -195,8 +209,7 @@ struct Model {
                 RC(run_conv(s.ud, x, x_lo, B_, H_, W_, 1, 0, nullptr, st));        // BN folded into the epilogue
             } else {
                 if (!training) RC(bn_prepare_eval(s.ud, st));
-                RC(run_conv(s.ud, x, x_lo, B_, H_, W_, 0, 0, nullptr, st));
-                if (training) RC(bn_stats(s.ud, st));
+                RC(conv_with_stats(s.ud, x, x_lo, B_, H_, W_, st));
                 rscale = s.ud.scale; rshift = s.ud.shift;
             }
             res = s.ud.y;
@@ -246,8 +259,14 @@ struct Model {
             if (!training) RC(bn_prepare_eval(u, st));
             u.y = ar.f((size_t)M2 * 64);
             a.y = u.y;
+            int nblk = 0;
+            if (training) { a.stats_partial = partial; a.stats_blocks = &nblk; }
             if (!ar.dry) RC(tfg::conv_fprop(a, st));
-            if (training) RC(bn_stats(u, st));
+            if (training) {
+                RC(alloc_bn(u));
+                if (!ar.dry) RC(tfe::bn_finalize_train(partial, nblk, M2, 64, P(u.bn.gamma), P(u.bn.beta), eps, momentum, PW(u.bn.rm),
+                                                       PW(u.bn.rv), u.scale, u.shift, u.mean, u.rstd, st));
+            }
             a0 = ar.f((size_t)M2 * 64);
             if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M2, 64, a0, nullptr, 0, st));
         }
@@ -512,7 +531,7 @@ TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, c
     size_t need;
     RC(tf_model_workspace_bytes(handle, B, H, W, training, mode, &need));
     if (workspace_bytes < need) { tf_set_error("tf_model_forward: workspace %zu < required %zu", workspace_bytes, need); return TF_ERR_WORKSPACE; }
-    m->params = params; m->momentum = bn_momentum;
+    m->params.assign(params, params + m->names.size()); m->momentum = bn_momentum;
     m->ar = Arena(); m->ar.dry = false; m->ar.base = reinterpret_cast<char*>(workspace); m->ar.cap = workspace_bytes;
     return m->forward(x, out, (cudaStream_t)stream);
 }
