@@ -49,6 +49,7 @@ struct GemmParams {
     int accumulate;               // 1: D += result (TMA reduce-add) instead of D = result
     float* stats_partial;         // optional BN statistics: [grid/num_n_tiles*4][2][Cout] per-channel (sum, sum^2) partials
     int cout;                     //   of the raw accumulators (needs gridDim.x % num_n_tiles == 0: fixed n-tile per CTA)
+    int img_w, img_h;             // spatial mode: rows of a patch that fall outside the image are not statistics
     int* err_flag;
 };
 
@@ -224,11 +225,13 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 }
                 if (p.stats_partial) {
                     // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged tile
+                    // (a 3x3 tap can pull in-image data into an out-of-image output row, so those rows are masked)
                     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) {
                         const int rw = q * 32 + rr;
-                        const float v = *reinterpret_cast<const float*>(buf + rw * 128 + (((lane >> 2) ^ (rw & 7)) << 4) + ((lane & 3) << 2));
+                        float v = *reinterpret_cast<const float*>(buf + rw * 128 + (((lane >> 2) ^ (rw & 7)) << 4) + ((lane & 3) << 2));
+                        if (p.spatial && (x0 + rw % p.tw >= p.img_w || y0 + rw / p.tw >= p.img_h)) v = 0.f;
                         s0 += v; s1 += v * v;
                     }
                     st_sum[chunk] += s0; st_sq[chunk] += s1;
@@ -257,7 +260,7 @@ struct WgradParams {
     int m_tiles, n_tiles, taps, splits, nseg;
     int spatial, tiles_x, tiles_y, tw, th;     // pixel blocks of 32: flat or (tw x th) patches of one image
     int num_pblocks;                            // total pixel blocks
-    int cin;                                    // column offset of a tap in dW = tap * cin
+    int cin, cout;                              // dW is [cout][taps*cin]; column = tap * cin + ci
     int plain_store;                            // debug: overwrite instead of reduce-add (needs splits == 1)
     int* err_flag;
 };
@@ -289,11 +292,14 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int units = p.m_tiles * p.n_tiles * p.taps;
+    // GEMM view: D[Cout, taps*Cin] -- a column block of BN may span several taps (Cin < BN) or part of one
+    const int units = p.m_tiles * p.n_tiles;
     const int unit = blockIdx.x % units, split = blockIdx.x / units;
-    const int tap = unit % p.taps;
-    const int n0 = ((unit / p.taps) % p.n_tiles) * BN;
-    const int m0 = (unit / (p.taps * p.n_tiles)) * BLOCK_M;
+    const int n0 = (unit % p.n_tiles) * BN;
+    const int m0 = (unit / p.n_tiles) * BLOCK_M;
+    const int ncols = p.taps * p.cin;
+    const int a_boxes = min(BLOCK_M / 32, (p.cout - m0 + 31) / 32);     // boxes beyond Cout / taps*Cin are not loaded:
+    const int b_boxes = min(BN / 32, (ncols - n0 + 31) / 32);           // their accumulator rows / columns are never stored
     const int pb0 = (int)((long long)p.num_pblocks * split / p.splits);
     const int pb1 = (int)((long long)p.num_pblocks * (split + 1) / p.splits);
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -307,19 +313,18 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 11);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], (a_boxes + b_boxes) * 4096);
                     if (p.spatial) {
                         const int img = pb / tiles_per_img, r = pb % tiles_per_img;
                         const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
-#pragma unroll
-                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_4d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, x0, y0, img);
-#pragma unroll
-                        for (int j = 0; j < BN / 32; ++j) tma_load_4d(sb + j * 4096, &maps.b[seg], &full[stage], n0 + j * 32, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                        for (int i = 0; i < a_boxes; ++i) tma_load_4d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, x0, y0, img);
+                        for (int j = 0; j < b_boxes; ++j) {
+                            const int col = n0 + j * 32, tap = col / p.cin, ci = col - tap * p.cin;
+                            tma_load_4d(sb + j * 4096, &maps.b[seg], &full[stage], ci, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                        }
                     } else {
-#pragma unroll
-                        for (int i = 0; i < BLOCK_M / 32; ++i) tma_load_2d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, pb * 32);
-#pragma unroll
-                        for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, &maps.b[seg], &full[stage], n0 + j * 32, pb * 32);
+                        for (int i = 0; i < a_boxes; ++i) tma_load_2d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, pb * 32);
+                        for (int j = 0; j < b_boxes; ++j) tma_load_2d(sb + j * 4096, &maps.b[seg], &full[stage], n0 + j * 32, pb * 32);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -355,7 +360,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             tc_fence_after();
             int ebuf = 0;
 #pragma unroll 1
-            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+            for (int chunk = 0; chunk < b_boxes; ++chunk) {
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + chunk * 32, r);
                 tmem_ld_wait();
@@ -366,8 +371,8 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 fence_proxy_async();
                 named_bar_sync_epi();
                 if (store_thread) {
-                    if (p.plain_store) tma_store_2d(&maps.d, buf, tap * p.cin + n0 + chunk * 32, m0);
-                    else               tma_reduce_add_2d(&maps.d, buf, tap * p.cin + n0 + chunk * 32, m0);
+                    if (p.plain_store) tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                    else               tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0);
                     tma_store_commit();
                 }
                 ebuf ^= 1;
@@ -477,7 +482,7 @@ int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
         TF_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int grid = p.m_tiles * p.n_tiles * p.taps * p.splits;
+    const int grid = p.m_tiles * p.n_tiles * p.splits;
     conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -505,14 +510,27 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     int rc = ensure_device_state();
     if (rc) return rc;
     const int B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout;
-    const int BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : 64);
     const int taps = a.ksize * a.ksize;
     GemmMaps maps;
     GemmParams p = {};
+    const long long Mtot = (long long)B * H * W;
+    int m_tiles;
+    if (a.ksize == 1) m_tiles = (int)((Mtot + BLOCK_M - 1) / BLOCK_M);
+    else { int tw, th; pick_tile(W, H, BLOCK_M, &tw, &th); m_tiles = B * ((W + tw - 1) / tw) * ((H + th - 1) / th); }
+    // tile width: fewest (rounds over the SMs) x (time per tile ~ BN); narrower tiles pay more smem bandwidth per MMA
+    int BN = 64; double best = 1e30;
+    for (int cand = 256; cand >= 64; cand >>= 1) {
+        if (Cout % cand) continue;
+        const long long tiles = (long long)m_tiles * (Cout / cand);
+        const double rounds = (double)((tiles + g_num_sms - 1) / g_num_sms);
+        const double cost = rounds * cand * (cand == 256 ? 1.0 : (cand == 128 ? 1.06 : 1.5));
+        if (cost < best) { best = cost; BN = cand; }
+    }
+    if (g_debug[2]) BN = g_debug[2];
     p.taps = taps; p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
-    p.stats_partial = a.stats_partial; p.cout = Cout;
+    p.stats_partial = a.stats_partial; p.cout = Cout; p.img_w = W; p.img_h = H;
     p.err_flag = g_err_flag;
     p.num_n_tiles = Cout / BN;
     const float* as[3] = {a.x, a.x_lo, a.x};
@@ -555,13 +573,14 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
     int rc = ensure_device_state();
     if (rc) return rc;
     const int B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout;
-    const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+    const int ncols = a.ksize * a.ksize * Cin;
+    const int BN = ncols <= 64 ? 64 : (ncols <= 128 ? 128 : 256);
     WgradMaps maps;
     WgradParams p = {};
-    p.taps = a.ksize * a.ksize; p.cin = Cin; p.err_flag = g_err_flag;
+    p.taps = a.ksize * a.ksize; p.cin = Cin; p.cout = Cout; p.err_flag = g_err_flag;
     p.nseg = a.x_lo ? 3 : 1;
     p.m_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
-    p.n_tiles = (Cin + BN - 1) / BN;
+    p.n_tiles = (ncols + BN - 1) / BN;
     const float* as[3] = {a.dy, a.dy_lo, a.dy};
     const float* bs[3] = {a.x, a.x, a.x_lo};
     const long long M = (long long)B * H * W;
@@ -583,8 +602,8 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
         }
     }
     if ((rc = encode_2d(&maps.d, a.dw, (uint64_t)p.taps * Cin, Cout, (uint64_t)p.taps * Cin, 32, BLOCK_M))) return rc;
-    const int units = p.m_tiles * p.n_tiles * p.taps;
-    int splits = (2 * g_num_sms + units - 1) / units;
+    const int units = p.m_tiles * p.n_tiles;
+    int splits = g_num_sms / units;                       // one wave of CTAs
     if (splits > p.num_pblocks) splits = p.num_pblocks;
     if (splits < 1) splits = 1;
     if (g_debug[0]) { splits = 1; p.plain_store = 1; }

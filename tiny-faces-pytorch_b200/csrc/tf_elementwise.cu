@@ -83,16 +83,27 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
     }
 }
 
+// sum the per-block partials of 32 channels with 8 lanes per channel (fp64), result valid for threadIdx.y == 0
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
+    __shared__ double sh[2][8][32];
+    s = 0; q = 0;
+    if (c < C)
+        for (int b = threadIdx.y; b < nblk; b += 8) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+    sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0)
+        for (int l = 1; l < 8; ++l) { s += sh[0][l][threadIdx.x]; q += sh[1][l][threadIdx.x]; }
+}
 // BN forward finalize (training): batch mean / biased var -> scale, shift, saved mean / rstd, running stats
-__global__ void bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(256) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0, q = 0;
-    for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s, q;
+    reduce_partials(partial, nblk, C, c, s, q);
+    if (threadIdx.y != 0 || c >= C) return;
     const double mean = s / (double)M;
     double var = q / (double)M - mean * mean;
     if (var < 0) var = 0;
@@ -119,26 +130,26 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
     shift[c] = beta[c] - run_mean[c] * sc;
 }
 // BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef /* [3][C]: gamma*rstd, mean(g), mean(g*xhat) */) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0, q = 0;
-    for (int b = 0; b < nblk; ++b) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s, q;
+    reduce_partials(partial, nblk, C, c, s, q);
+    if (threadIdx.y != 0 || c >= C) return;
     if (dgamma) dgamma[c] = (float)q;
     if (dbeta) dbeta[c] = (float)s;
     coef[c] = gamma[c] * rstd[c];
     coef[C + c] = (float)(s / (double)M);
     coef[2 * C + c] = (float)(q / (double)M);
 }
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
                                        float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cout) return;
-    double s = 0;
-    for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * 2 * C + c];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s, q;
+    reduce_partials(partial, nblk, C, c, s, q);
+    if (threadIdx.y != 0 || c >= Cout) return;
     out[c] = (float)s;
 }
 
@@ -214,75 +225,83 @@ __global__ void __launch_bounds__(EW_THREADS) masked_add_kernel(const float* __r
 __global__ void __launch_bounds__(EW_THREADS) stem_im2col_kernel(const float* __restrict__ x, int B, int H, int W, int Ho,
                                                                  int Wo, int K_pad, float* __restrict__ col,
                                                                  float* __restrict__ col_lo, int mode) {
-    const long long total = (long long)B * Ho * Wo * K_pad;
+    const int kq = K_pad / 4;
+    const long long total = (long long)B * Ho * Wo * kq;
+    const long long plane = (long long)H * W;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int k = (int)(t % K_pad);
-        const long long pix = t / K_pad;
+        const int k0 = (int)(t % kq) * 4;
+        const long long pix = t / kq;
         const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-        float v = 0.f;
-        if (k < 147) {
-            const int c = k / 49, kh = (k % 49) / 7, kw = k % 7;
-            const int iy = oy * 2 + kh - 3, ix = ox * 2 + kw - 3;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = x[(((long long)b * 3 + c) * H + iy) * W + ix];
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            float val = 0.f;
+            if (k < 147) {
+                const int c = k / 49, r = k - c * 49, kh = r / 7, kw = r - kh * 7;
+                const int iy = oy * 2 + kh - 3, ix = ox * 2 + kw - 3;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(x + ((long long)b * 3 + c) * plane + (long long)iy * W + ix);
+            }
+            v[j] = val;
         }
-        if (mode == 1) col[t] = tf_round_tf32(v);
-        else if (mode == 2) { const float h = hi_part(v); col[t] = h; col_lo[t] = v - h; }
-        else col[t] = v;
+        store_act(col, col_lo, pix * K_pad + k0, make_float4(v[0], v[1], v[2], v[3]), mode);
     }
 }
 
 // max-pool 3x3 stride 2 pad 1, NHWC
 __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C,
                                                                  int Ho, int Wo, float* __restrict__ out,
-                                                                 float* __restrict__ out_lo, int mode) {
+                                                                 float* __restrict__ out_lo, int mode,
+                                                                 unsigned char* __restrict__ argmax) {
     const long long total = (long long)B * Ho * Wo * (C / 4);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int cg = (int)(t % (C / 4));
         const long long pix = t / (C / 4);
         const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int am[4] = {-1, -1, -1, -1};
         for (int kh = 0; kh < 3; ++kh) {
             const int iy = oy * 2 + kh - 1;
             if (iy < 0 || iy >= H) continue;
             for (int kw = 0; kw < 3; ++kw) {
                 const int ix = ox * 2 + kw - 1;
                 if (ix < 0 || ix >= W) continue;
-                const float4 v = ld4(x + (((long long)b * H + iy) * W + ix) * C + cg * 4);
-                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+                const float4 v4 = ld4(x + (((long long)b * H + iy) * W + ix) * C + cg * 4);
+                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)     // first maximum in (kh, kw) scan order wins (ATen's CPU max_pool2d rule)
+                    if (v[j] > m[j] || am[j] < 0) { m[j] = v[j]; am[j] = kh * 3 + kw; }
             }
         }
-        store_act(out, out_lo, pix * C + cg * 4, m, mode);
+        store_act(out, out_lo, pix * C + cg * 4, make_float4(m[0], m[1], m[2], m[3]), mode);
+        if (argmax) *reinterpret_cast<uchar4*>(argmax + pix * C + cg * 4) = make_uchar4(am[0], am[1], am[2], am[3]);
     }
 }
-// gather formulation of the backward: input pixel (iy, ix) receives dout of every window whose FIRST maximum
-// (scan order kh, kw ascending -- the rule of ATen's CPU max_pool2d) is this pixel.
-__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dout,
-                                                                 int B, int H, int W, int C, int Ho, int Wo,
-                                                                 float* __restrict__ dx) {
-    const long long total = (long long)B * H * W * C;
+// backward as a gather over the saved window argmax: input pixel (iy, ix) collects dout of the (at most 4)
+// windows whose arg-max it is.  float4 over channels.
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const unsigned char* __restrict__ argmax,
+                                                                 const float* __restrict__ dout, int B, int H, int W, int C,
+                                                                 int Ho, int Wo, float* __restrict__ dx) {
+    const long long total = (long long)B * H * W * (C / 4);
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(t % C);
-        const long long pix = t / C;
+        const int cg = (int)(t % (C / 4));
+        const long long pix = t / (C / 4);
         const int ix = (int)(pix % W), iy = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-        float acc = 0.f;
-        const int oy_lo = max(0, (iy) / 2), oy_hi = min(Ho - 1, (iy + 1) / 2);
-        const int ox_lo = max(0, (ix) / 2), ox_hi = min(Wo - 1, (ix + 1) / 2);
+        float4 acc = make_float4(0, 0, 0, 0);
+        const int oy_lo = iy / 2, oy_hi = min(Ho - 1, (iy + 1) / 2);
+        const int ox_lo = ix / 2, ox_hi = min(Wo - 1, (ix + 1) / 2);
         for (int oy = oy_lo; oy <= oy_hi; ++oy)
             for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                float best = -INFINITY; int by = -1, bx = -1;
-                for (int kh = 0; kh < 3; ++kh) {
-                    const int yy = oy * 2 + kh - 1;
-                    if (yy < 0 || yy >= H) continue;
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const int xx = ox * 2 + kw - 1;
-                        if (xx < 0 || xx >= W) continue;
-                        const float v = x[(((long long)b * H + yy) * W + xx) * C + c];
-                        if (v > best || by < 0) { best = v; by = yy; bx = xx; }
-                    }
-                }
-                if (by == iy && bx == ix) acc += dout[(((long long)b * Ho + oy) * Wo + ox) * C + c];
+                const int want = (iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1));
+                const long long o = (((long long)b * Ho + oy) * Wo + ox) * C + cg * 4;
+                const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + o);
+                const float4 g = ld4(dout + o);
+                if (am.x == want) acc.x += g.x;
+                if (am.y == want) acc.y += g.y;
+                if (am.z == want) acc.z += g.z;
+                if (am.w == want) acc.w += g.w;
             }
-        dx[t] = acc;
+        st4(dx + pix * C + cg * 4, acc);
     }
 }
 
@@ -441,7 +460,7 @@ int bn_stats_train(const float* y, long long M, int C, const float* gamma, const
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_stats_train: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
+    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -449,7 +468,7 @@ int bn_stats_train(const float* y, long long M, int C, const float* gamma, const
 int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st) {
-    bn_finalize_train_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
+    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -473,7 +492,7 @@ int bn_backward(const float* dout, const float* act, const float* y, const float
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_backward: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, save_mean, save_rstd, M, C, partial);
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
                                                                 gmask_out, mode);
@@ -484,7 +503,7 @@ int column_sum(const float* a, long long M, int C, int Cout, float* out, float* 
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "column_sum: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    colsum_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(partial, nb, C, Cout, out);
+    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -495,17 +514,18 @@ int masked_add(const float* a, const float* act, const float* b, long long n, fl
 }
 int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,
                 cudaStream_t st) {
-    stem_im2col_kernel<<<ew_blocks((long long)B * Ho * Wo * K_pad, 4), EW_THREADS, 0, st>>>(x_nchw, B, H, W, Ho, Wo, K_pad, col, col_lo, mode);
+    stem_im2col_kernel<<<ew_blocks((long long)B * Ho * Wo * K_pad / 4), EW_THREADS, 0, st>>>(x_nchw, B, H, W, Ho, Wo, K_pad, col, col_lo, mode);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
-int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode, cudaStream_t st) {
-    maxpool_fwd_kernel<<<ew_blocks((long long)B * Ho * Wo * C / 4), EW_THREADS, 0, st>>>(x, B, H, W, C, Ho, Wo, out, out_lo, mode);
+int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode,
+                unsigned char* argmax, cudaStream_t st) {
+    maxpool_fwd_kernel<<<ew_blocks((long long)B * Ho * Wo * C / 4), EW_THREADS, 0, st>>>(x, B, H, W, C, Ho, Wo, out, out_lo, mode, argmax);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
-int maxpool_bwd(const float* x, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st) {
-    maxpool_bwd_kernel<<<ew_blocks((long long)B * H * W * C, 2), EW_THREADS, 0, st>>>(x, dout, B, H, W, C, Ho, Wo, dx);
+int maxpool_bwd(const unsigned char* argmax, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st) {
+    maxpool_bwd_kernel<<<ew_blocks((long long)B * H * W * C / 4), EW_THREADS, 0, st>>>(argmax, dout, B, H, W, C, Ho, Wo, dx);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

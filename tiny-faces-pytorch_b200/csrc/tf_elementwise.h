@@ -23,8 +23,9 @@ int column_sum(const float* a, long long M, int C, int Cout, float* out, float* 
 int masked_add(const float* a, const float* act, const float* b, long long n, float* out, cudaStream_t st);
 int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,
                 cudaStream_t st);
-int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode, cudaStream_t st);
-int maxpool_bwd(const float* x, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st);
+int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode,
+                unsigned char* argmax /* optional [B,Ho,Wo,C] window index of the first maximum */, cudaStream_t st);
+int maxpool_bwd(const unsigned char* argmax, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st);
 int subsample2(const float* x, const float* x_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
 int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
 int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, int O_pad, int I_pad, float* dst,

@@ -61,7 +61,7 @@ struct Model {
     Arena ar;
     std::vector<const void*> params;     // copied from the caller's table at every forward (backward reuses it)
     Unit stem_u; float* col = nullptr; float* col_lo = nullptr; int H2 = 0, W2 = 0, Hp = 0, Wp = 0;
-    float* pool = nullptr; float* pool_lo = nullptr;
+    float* pool = nullptr; float* pool_lo = nullptr; unsigned char* pool_argmax = nullptr;
     std::vector<BlockS> bs;
     int H3 = 0, W3 = 0, H4 = 0, W4 = 0;
     const float* res3 = nullptr; const float* res3_lo = nullptr; const float* res4 = nullptr; const float* res4_lo = nullptr;
@@ -274,7 +274,8 @@ struct Model {
         const long long Mp = (long long)B * Hp * Wp;
         pool = ar.f((size_t)Mp * 64);
         pool_lo = mode == 2 ? ar.f((size_t)Mp * 64) : nullptr;
-        if (!ar.dry) RC(tfe::maxpool_fwd(a0, B, H2, W2, 64, Hp, Wp, pool, pool_lo, mode, st));
+        pool_argmax = training ? reinterpret_cast<unsigned char*>(ar.f((size_t)Mp * 64 / 4)) : nullptr;
+        if (!ar.dry) RC(tfe::maxpool_fwd(a0, B, H2, W2, 64, Hp, Wp, pool, pool_lo, mode, pool_argmax, st));
         // ---- heads' buffers (model.py:104-126) are allocated first so that they survive the per-block resets
         auto half = [](int v) { return (v - 1) / 2 + 1; };
         H3 = half(Hp); W3 = half(Wp); H4 = half(H3); W4 = half(W3);
@@ -455,7 +456,7 @@ struct Model {
         // ---- stem
         const long long M2 = (long long)B * H2 * W2;
         float* da0 = ar.f((size_t)M2 * 64);
-        if (!ar.dry) RC(tfe::maxpool_bwd(stem_u.a, dcur, B, H2, W2, 64, Hp, Wp, da0, st));
+        if (!ar.dry) RC(tfe::maxpool_bwd(pool_argmax, dcur, B, H2, W2, 64, Hp, Wp, da0, st));
         float *dy0, *dy0_lo;
         RC(unit_bn_bwd(stem_u, da0, stem_u.a, nullptr, &dy0, &dy0_lo, grads, st));
         float* gw = G(grads, stem.w);
