@@ -523,7 +523,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         if (Cout % cand) continue;
         const long long tiles = (long long)m_tiles * (Cout / cand);
         const double rounds = (double)((tiles + g_num_sms - 1) / g_num_sms);
-        const double cost = rounds * cand * (cand == 256 ? 1.0 : (cand == 128 ? 1.06 : 1.5));
+        const double cost = rounds * cand * (cand == 256 ? 1.0 : (cand == 128 ? 1.45 : 2.2));   // measured: N=128 tiles are smem-bandwidth bound
         if (cost < best) { best = cost; BN = cand; }
     }
     if (g_debug[2]) BN = g_debug[2];

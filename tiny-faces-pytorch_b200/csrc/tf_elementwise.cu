@@ -18,6 +18,18 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
+// ReLU masks are kept as 1 bit per element (element i -> bit i%32 of word i/32) so that the backward passes do not
+// have to re-read the activation tensor: 4 consecutive elements (one float4) = one nibble.
+__device__ __forceinline__ unsigned int mask_nibble(const unsigned int* __restrict__ mask, long long i) {
+    return (mask[i >> 5] >> (unsigned)(i & 31)) & 0xFu;
+}
+__device__ __forceinline__ void apply_mask(float4& g, unsigned int nib) {
+    if (!(nib & 1u)) g.x = 0.f;
+    if (!(nib & 2u)) g.y = 0.f;
+    if (!(nib & 4u)) g.z = 0.f;
+    if (!(nib & 8u)) g.w = 0.f;
+}
+
 // write v either rounded to tf32 (fast mode), or split into (hi, lo) (parity mode), or unchanged
 __device__ __forceinline__ void store_act(float* out, float* out_lo, long long i, float4 v, int mode) {
     if (mode == 1) {
@@ -41,6 +53,7 @@ __device__ __forceinline__ void store_act(float* out, float* out_lo, long long i
 template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                const float* __restrict__ act,
+                                                               const unsigned int* __restrict__ mask,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, long long M, int C,
                                                                float* __restrict__ partial) {
@@ -58,7 +71,8 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                 s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
                 s1.x += v.x * v.x; s1.y += v.y * v.y; s1.z += v.z * v.z; s1.w += v.w * v.w;
             } else if (MODE == 1) {
-                if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) v.x = 0.f; if (!(o.y > 0.f)) v.y = 0.f; if (!(o.z > 0.f)) v.z = 0.f; if (!(o.w > 0.f)) v.w = 0.f; }
+                if (mask) apply_mask(v, mask_nibble(mask, i));
+                else if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) v.x = 0.f; if (!(o.y > 0.f)) v.y = 0.f; if (!(o.z > 0.f)) v.z = 0.f; if (!(o.w > 0.f)) v.w = 0.f; }
                 float4 y = ld4(b + i);
                 s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
                 s1.x += v.x * (y.x - mu.x) * rs.x; s1.y += v.y * (y.y - mu.y) * rs.y;
@@ -153,36 +167,50 @@ __global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __res
     out[c] = (float)s;
 }
 
-// out = act( y*scale + shift (+ res | + res*rscale + rshift) )
+// out = act( y*scale + shift (+ res | + res*rscale + rshift) ); optional 1-bit ReLU mask of the result
 __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ res,
                                                               const float* __restrict__ rscale,
                                                               const float* __restrict__ rshift, int relu, long long n4,
                                                               int C, float* __restrict__ out, float* __restrict__ out_lo,
-                                                              int mode) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+                                                              int mode, unsigned int* __restrict__ mask_out) {
+    const long long n4_up = (n4 + 31) & ~31ll;          // whole warps iterate together (the mask needs shuffles)
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4_up; t += (long long)gridDim.x * blockDim.x) {
         const long long i = t * 4;
-        const int c = (int)(i % C);
-        float4 v = ld4(y + i);
-        const float4 sc = ld4(scale + c), sh = ld4(shift + c);
-        v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
-        if (res) {
-            float4 r = ld4(res + i);
-            if (rscale) {
-                const float4 a = ld4(rscale + c), b = ld4(rshift + c);
-                r.x = r.x * a.x + b.x; r.y = r.y * a.y + b.y; r.z = r.z * a.z + b.z; r.w = r.w * a.w + b.w;
+        const bool live = t < n4;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (live) {
+            const int c = (int)(i % C);
+            v = ld4(y + i);
+            const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+            v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
+            if (res) {
+                float4 r = ld4(res + i);
+                if (rscale) {
+                    const float4 a = ld4(rscale + c), b = ld4(rshift + c);
+                    r.x = r.x * a.x + b.x; r.y = r.y * a.y + b.y; r.z = r.z * a.z + b.z; r.w = r.w * a.w + b.w;
+                }
+                v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            store_act(out, out_lo, i, v, mode);
         }
-        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        store_act(out, out_lo, i, v, mode);
+        if (mask_out) {
+            unsigned int nib = (v.x > 0.f ? 1u : 0u) | (v.y > 0.f ? 2u : 0u) | (v.z > 0.f ? 4u : 0u) | (v.w > 0.f ? 8u : 0u);
+            unsigned int w = nib << ((threadIdx.x & 7) * 4);
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+            if ((threadIdx.x & 7) == 0 && live) mask_out[i >> 5] = w;
+        }
     }
 }
 
 // dy = coef0 * (g - coef1 - xhat*coef2),  g = dout (* [act > 0]);  optionally gmask_out = g (identity branch)
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ dout,
                                                                   const float* __restrict__ act,
+                                                                  const unsigned int* __restrict__ mask,
                                                                   const float* __restrict__ y,
                                                                   const float* __restrict__ mean,
                                                                   const float* __restrict__ rstd,
@@ -193,7 +221,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
         const long long i = t * 4;
         const int c = (int)(i % C);
         float4 g = ld4(dout + i);
-        if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
+        if (mask) apply_mask(g, mask_nibble(mask, i));
+        else if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
         if (gmask_out) st4(gmask_out + i, g);
         const float4 v = ld4(y + i), mu = ld4(mean + c), rs = ld4(rstd + c);
         const float4 c0 = ld4(coef + c), c1 = ld4(coef + C + c), c2 = ld4(coef + 2 * C + c);
@@ -459,7 +488,7 @@ int bn_stats_train(const float* y, long long M, int C, const float* gamma, const
                    float* partial, cudaStream_t st) {
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_stats_train: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
     bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
@@ -480,21 +509,22 @@ int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const floa
     return TF_OK;
 }
 int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
-             const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, cudaStream_t st) {
+             const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, unsigned int* mask_out,
+             cudaStream_t st) {
     const long long n4 = M * C / 4;
-    bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode);
+    bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
-int bn_backward(const float* dout, const float* act, const float* y, const float* save_mean, const float* save_rstd,
+int bn_backward(const float* dout, const float* act, const unsigned int* mask, const float* y, const float* save_mean, const float* save_rstd,
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
                 float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st) {
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_backward: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, save_mean, save_rstd, M, C, partial);
+    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, partial);
     bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
-    bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
+    bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
                                                                 gmask_out, mode);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -502,7 +532,7 @@ int bn_backward(const float* dout, const float* act, const float* y, const float
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st) {
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "column_sum: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
     colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;

@@ -15,8 +15,9 @@ int bn_finalize_train(const float* partial, int nblk, long long M, int C, const 
 int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
                         float eps, float* scale, float* shift, cudaStream_t st);
 int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
-             const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, cudaStream_t st);
-int bn_backward(const float* dout, const float* act, const float* y, const float* save_mean, const float* save_rstd,
+             const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode,
+             unsigned int* mask_out /* optional 1-bit ReLU mask, (M*C+31)/32 words */, cudaStream_t st);
+int bn_backward(const float* dout, const float* act, const unsigned int* mask /* either may gate dout */, const float* y, const float* save_mean, const float* save_rstd,
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
                 float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st);
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st);

@@ -46,10 +46,11 @@ struct Unit {
     float* y = nullptr;                                         // raw conv output at (Ho, Wo)
     float *mean = nullptr, *rstd = nullptr, *scale = nullptr, *shift = nullptr;
     float* a = nullptr; float* a_lo = nullptr;                  // post BN(+ReLU) activation (null for bn3 / ds)
+    unsigned int* amask = nullptr;                              // 1-bit ReLU mask of a (training)
     float* wp = nullptr; float* wp_lo = nullptr;                // packed fprop weights
 };
 struct BlockS { Unit u1, u2, u3, ud; const float* x = nullptr; const float* x_lo = nullptr; int B = 0, H = 0, W = 0, Ho = 0, Wo = 0;
-                float* out = nullptr; float* out_lo = nullptr; bool has_ds = false; };
+                float* out = nullptr; float* out_lo = nullptr; unsigned int* omask = nullptr; bool has_ds = false; };
 
 struct Model {
     int T = 25, Cn = 125, Cp = 128;
@@ -186,7 +187,8 @@ struct Model {
         RC(conv_with_stats(u, x, x_lo, B_, H_, W_, st));
         u.a = ar.f((size_t)M * u.c.cout);
         u.a_lo = mode == 2 ? ar.f((size_t)M * u.c.cout) : nullptr;
-        if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M, u.c.cout, u.a, u.a_lo, mode, st));
+        u.amask = training ? reinterpret_cast<unsigned int*>(ar.f((size_t)(M * u.c.cout + 31) / 32)) : nullptr;
+        if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M, u.c.cout, u.a, u.a_lo, mode, u.amask, st));
         return TF_OK;
     }
     int block_forward(const BlockP& bp, BlockS& s, const float* x, const float* x_lo, int B_, int H_, int W_, float* out_pre,
@@ -222,7 +224,8 @@ struct Model {
             if (!ar.dry) RC(tfe::masked_add(x, nullptr, x_lo, Mo * C4, xsum, st));
             res = xsum;
         }
-        if (!ar.dry) RC(tfe::bn_apply(s.u3.y, s.u3.scale, s.u3.shift, res, rscale, rshift, 1, Mo, C4, s.out, s.out_lo, mode, st));
+        s.omask = training ? reinterpret_cast<unsigned int*>(ar.f((size_t)(Mo * C4 + 31) / 32)) : nullptr;
+        if (!ar.dry) RC(tfe::bn_apply(s.u3.y, s.u3.scale, s.u3.shift, res, rscale, rshift, 1, Mo, C4, s.out, s.out_lo, mode, s.omask, st));
         return TF_OK;
     }
 
@@ -268,7 +271,8 @@ struct Model {
                                                        PW(u.bn.rv), u.scale, u.shift, u.mean, u.rstd, st));
             }
             a0 = ar.f((size_t)M2 * 64);
-            if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M2, 64, a0, nullptr, 0, st));
+            u.amask = training ? reinterpret_cast<unsigned int*>(ar.f((size_t)(M2 * 64 + 31) / 32)) : nullptr;
+            if (!ar.dry) RC(tfe::bn_apply(u.y, u.scale, u.shift, nullptr, nullptr, nullptr, 1, M2, 64, a0, nullptr, 0, u.amask, st));
         }
         u.a = a0; u.a_lo = a0_lo;
         const long long Mp = (long long)B * Hp * Wp;
@@ -337,13 +341,13 @@ struct Model {
     float* G(void* const* grads, int idx) const { return (grads && idx >= 0) ? reinterpret_cast<float*>(grads[idx]) : nullptr; }
 
     // BN backward of unit u: dout (masked by act > 0 when act != null) -> dy (+lo); dgamma/dbeta into the caller's grads
-    int unit_bn_bwd(const Unit& u, const float* dout, const float* act, float* gmask_out, float** dy, float** dy_lo,
+    int unit_bn_bwd(const Unit& u, const float* dout, const unsigned int* mask, float* gmask_out, float** dy, float** dy_lo,
                     void* const* grads, cudaStream_t st) {
         const long long M = (long long)u.B * u.Ho * u.Wo;
         const int C = u.bn.C;
         *dy = ar.f((size_t)M * C);
         *dy_lo = mode == 2 ? ar.f((size_t)M * C) : nullptr;
-        if (!ar.dry) RC(tfe::bn_backward(dout, act, u.y, u.mean, u.rstd, P(u.bn.gamma), M, C, G(grads, u.bn.gamma), G(grads, u.bn.beta),
+        if (!ar.dry) RC(tfe::bn_backward(dout, nullptr, mask, u.y, u.mean, u.rstd, P(u.bn.gamma), M, C, G(grads, u.bn.gamma), G(grads, u.bn.beta),
                                          *dy, *dy_lo, gmask_out, mode, partial, coef, st));
         return TF_OK;
     }
@@ -402,17 +406,17 @@ struct Model {
         const bool has_ds = s.has_ds;
         // G = dout * [out > 0]: with an identity shortcut dx simply starts as G, otherwise G feeds the downsample BN
         float* g = has_ds ? ar.f((size_t)Mo * C4) : dx;
-        RC(unit_bn_bwd(s.u3, dout, s.out, g, &dy3, &dy3_lo, grads, st));
+        RC(unit_bn_bwd(s.u3, dout, s.omask, g, &dy3, &dy3_lo, grads, st));
         const long long M2o = (long long)s.B * s.u2.Ho * s.u2.Wo;
         float* da2 = ar.f((size_t)M2o * s.u2.c.cout);
         RC(unit_conv_bwd(s.u3, dy3, dy3_lo, da2, 0, s.Ho, s.Wo, grads, st));
         float *dy2, *dy2_lo;
-        RC(unit_bn_bwd(s.u2, da2, s.u2.a, nullptr, &dy2, &dy2_lo, grads, st));
+        RC(unit_bn_bwd(s.u2, da2, s.u2.amask, nullptr, &dy2, &dy2_lo, grads, st));
         const long long M1 = (long long)s.B * s.H * s.W;
         float* da1 = ar.f((size_t)M1 * s.u1.c.cout);
         RC(unit_conv_bwd(s.u2, dy2, dy2_lo, da1, 0, s.H, s.W, grads, st));
         float *dy1, *dy1_lo;
-        RC(unit_bn_bwd(s.u1, da1, s.u1.a, nullptr, &dy1, &dy1_lo, grads, st));
+        RC(unit_bn_bwd(s.u1, da1, s.u1.amask, nullptr, &dy1, &dy1_lo, grads, st));
         if (has_ds) {
             float *dyd, *dyd_lo;
             RC(unit_bn_bwd(s.ud, g, nullptr, nullptr, &dyd, &dyd_lo, grads, st));
@@ -458,7 +462,7 @@ struct Model {
         float* da0 = ar.f((size_t)M2 * 64);
         if (!ar.dry) RC(tfe::maxpool_bwd(pool_argmax, dcur, B, H2, W2, 64, Hp, Wp, da0, st));
         float *dy0, *dy0_lo;
-        RC(unit_bn_bwd(stem_u, da0, stem_u.a, nullptr, &dy0, &dy0_lo, grads, st));
+        RC(unit_bn_bwd(stem_u, da0, stem_u.amask, nullptr, &dy0, &dy0_lo, grads, st));
         float* gw = G(grads, stem.w);
         if (gw && !ar.dry) {
             TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)64 * 160 * 4, st));
