@@ -261,6 +261,7 @@ struct WgradParams {
     int spatial, tiles_x, tiles_y, tw, th;     // pixel blocks of 32: flat or (tw x th) patches of one image
     int num_pblocks;                            // total pixel blocks
     int cin, cout;                              // dW is [cout][taps*cin]; column = tap * cin + ci
+    int b_groups;                               // 32-channel groups fetched per B-operand TMA (= min(BN, cin) / 32)
     int plain_store;                            // debug: overwrite instead of reduce-add (needs splits == 1)
     int* err_flag;
 };
@@ -298,8 +299,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     const int n0 = (unit % p.n_tiles) * BN;
     const int m0 = (unit / p.n_tiles) * BLOCK_M;
     const int ncols = p.taps * p.cin;
-    const int a_boxes = min(BLOCK_M / 32, (p.cout - m0 + 31) / 32);     // boxes beyond Cout / taps*Cin are not loaded:
-    const int b_boxes = min(BN / 32, (ncols - n0 + 31) / 32);           // their accumulator rows / columns are never stored
+    const int b_boxes = min(BN / 32, (ncols - n0 + 31) / 32);           // 32-column chunks of this tile that exist in dW
     const int pb0 = (int)((long long)p.num_pblocks * split / p.splits);
     const int pb1 = (int)((long long)p.num_pblocks * (split + 1) / p.splits);
     const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -313,18 +313,27 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 11);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    mbar_expect_tx(&full[stage], (a_boxes + b_boxes) * 4096);
+                    // One TMA per operand (per tap for B): the channel axis is split into (32, C/32) so that a box
+                    // (32 ch, 32 px, g groups) lands as g consecutive [32 px][128 B] slabs -- the MN-major layout the
+                    // MMA wants -- instead of g separate 4 KB copies.  Groups past the tensor edge are zero-filled.
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    const int gb = p.b_groups;                       // 32-channel groups per B instruction
                     if (p.spatial) {
                         const int img = pb / tiles_per_img, r = pb % tiles_per_img;
                         const int y0 = (r / p.tiles_x) * p.th, x0 = (r % p.tiles_x) * p.tw;
-                        for (int i = 0; i < a_boxes; ++i) tma_load_4d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, x0, y0, img);
-                        for (int j = 0; j < b_boxes; ++j) {
-                            const int col = n0 + j * 32, tap = col / p.cin, ci = col - tap * p.cin;
-                            tma_load_4d(sb + j * 4096, &maps.b[seg], &full[stage], ci, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                        tma_load_5d(sa, &maps.a[seg], &full[stage], 0, x0, y0, img, m0 / 32);
+                        for (int j = 0; j < BN / 32; j += gb) {
+                            const int col = n0 + j * 32;
+                            const int tap = col < ncols ? col / p.cin : 0;
+                            const int grp = col < ncols ? (col - tap * p.cin) / 32 : p.cin / 32;    // past the end: all zero
+                            tma_load_5d(sb + j * 4096, &maps.b[seg], &full[stage], 0, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img, grp);
                         }
                     } else {
-                        for (int i = 0; i < a_boxes; ++i) tma_load_2d(sa + i * 4096, &maps.a[seg], &full[stage], m0 + i * 32, pb * 32);
-                        for (int j = 0; j < b_boxes; ++j) tma_load_2d(sb + j * 4096, &maps.b[seg], &full[stage], n0 + j * 32, pb * 32);
+                        tma_load_3d(sa, &maps.a[seg], &full[stage], 0, pb * 32, m0 / 32);
+                        for (int j = 0; j < BN / 32; j += gb) {
+                            const int col = n0 + j * 32;
+                            tma_load_3d(sb + j * 4096, &maps.b[seg], &full[stage], 0, pb * 32, col < ncols ? col / 32 : p.cin / 32);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -433,6 +442,37 @@ int encode_4d(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(4d C=%llu W=%llu H=%llu B=%llu box=%u,%u,%u) failed: %d",
                                           (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, bc, bw, bh, (int)r); return TF_ERR_CUDA; }
+    return TF_OK;
+}
+
+// MN-major operand views for wgrad: channels split as (32, C/32) with the group axis outermost in the box
+int encode_3d_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t rows, uint32_t box_rows, uint32_t groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
+    cuuint64_t dims[3] = {32, rows, C / 32};
+    cuuint64_t strides[2] = {C * 4, 128};
+    cuuint32_t box[3] = {32, box_rows, groups};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(3d grouped C=%llu rows=%llu box=%u,%u) failed: %d",
+                                          (unsigned long long)C, (unsigned long long)rows, box_rows, groups, (int)r); return TF_ERR_CUDA; }
+    return TF_OK;
+}
+int encode_5d_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t bw, uint32_t bh,
+                      uint32_t groups) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
+    cuuint64_t dims[5] = {32, W, H, B, C / 32};
+    cuuint64_t strides[4] = {C * 4, W * C * 4, H * W * C * 4, 128};
+    cuuint32_t box[5] = {32, bw, bh, 1, groups};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(5d grouped C=%llu W=%llu H=%llu B=%llu box=%u,%u,%u) failed: %d",
+                                          (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, bw, bh, groups, (int)r); return TF_ERR_CUDA; }
     return TF_OK;
 }
 
@@ -581,6 +621,12 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
     p.nseg = a.x_lo ? 3 : 1;
     p.m_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = (ncols + BN - 1) / BN;
+    {   // groups per B instruction: must divide both the tile (BN/32) and a tap's channel groups (Cin/32)
+        int x = (Cin < BN ? Cin : BN) / 32, y = BN / 32;
+        while (y) { const int t = x % y; x = y; y = t; }
+        p.b_groups = x;
+    }
+    TF_REQUIRE(Cin >= BN || BN % Cin == 0 || a.ksize == 1, "conv_wgrad: Cin=%d does not tile BN=%d", Cin, BN);
     const float* as[3] = {a.dy, a.dy_lo, a.dy};
     const float* bs[3] = {a.x, a.x, a.x_lo};
     const long long M = (long long)B * H * W;
@@ -588,8 +634,8 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
         p.spatial = 0; p.tiles_x = p.tiles_y = 1; p.tw = 32; p.th = 1;
         p.num_pblocks = (int)((M + 31) / 32);
         for (int s = 0; s < p.nseg; ++s) {
-            if ((rc = encode_2d(&maps.a[s], as[s], Cout, M, Cout, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-            if ((rc = encode_2d(&maps.b[s], bs[s], Cin, M, Cin, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+            if ((rc = encode_3d_grouped(&maps.a[s], as[s], Cout, M, 32, BLOCK_M / 32))) return rc;
+            if ((rc = encode_3d_grouped(&maps.b[s], bs[s], Cin, M, 32, p.b_groups))) return rc;
         }
     } else {
         p.spatial = 1;
@@ -597,8 +643,8 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
         p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
         p.num_pblocks = B * p.tiles_x * p.tiles_y;
         for (int s = 0; s < p.nseg; ++s) {
-            if ((rc = encode_4d(&maps.a[s], as[s], Cout, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-            if ((rc = encode_4d(&maps.b[s], bs[s], Cin, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+            if ((rc = encode_5d_grouped(&maps.a[s], as[s], Cout, W, H, B, p.tw, p.th, BLOCK_M / 32))) return rc;
+            if ((rc = encode_5d_grouped(&maps.b[s], bs[s], Cin, W, H, B, p.tw, p.th, p.b_groups))) return rc;
         }
     }
     if ((rc = encode_2d(&maps.d, a.dw, (uint64_t)p.taps * Cin, Cout, (uint64_t)p.taps * Cin, 32, BLOCK_M))) return rc;

@@ -66,7 +66,7 @@ class _TrunkFunction(torch.autograd.Function):
         h3, w3 = ctypes.c_int(), ctypes.c_int()
         check(lib().tf_model_output_shape(ex.handle, H, W, ctypes.byref(h3), ctypes.byref(w3)), "tf_model_output_shape")
         out = torch.empty((B, 5 * module.num_templates, h3.value, w3.value), dtype=torch.float32, device=x.device)
-        check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, 0.1, out.data_ptr(),
+        check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, float(module.bn_momentum), out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
         if training:
             for m in module.modules():
@@ -117,6 +117,7 @@ class DetectionModel(nn.Module):
         self.score4_upsample = nn.ConvTranspose2d(output, output, kernel_size=4, stride=2, padding=1, bias=False)
         self._init_bilinear()
         self.precision = "fast"
+        self.bn_momentum = 0.1                                # nn.BatchNorm2d default
         self._executor_obj = None
         self._checked_upsample = False
 
