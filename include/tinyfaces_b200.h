@@ -62,6 +62,11 @@ int tf_conv2d_nhwc(const float* x, const float* x_lo, int B, int H, int W, int C
                    const float* w_lo, int Cout, int ksize, const float* bias, float* y, void* stream);
 int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
                          float* dw_packed /* accumulated */, void* stream);
+/* stride 1 or 2 (padding ksize/2): y / dy are [B, ceil(H/s), ceil(W/s), Cout]; the stride is a TMA traversal stride */
+int tf_conv2d_nhwc_strided(const float* x, int B, int H, int W, int Cin, const float* w_packed, int Cout, int ksize,
+                           int stride, const float* bias, float* y, void* stream);
+int tf_conv2d_wgrad_nhwc_strided(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
+                                 int stride, float* dw_packed /* accumulated */, void* stream);
 
 /* ---- whole-model executor: replaces DetectionModel.forward (tinyfaces/models/model.py:89-128) and the backward
  * autograd derives from it (tinyfaces/trainer.py:86).  params / grads: HOST arrays of tf_model_num_params()

@@ -241,6 +241,35 @@ def test_conv2d_wgrad_vs_torch_cpu(B, H, W, Cin, Cout, k):
     assert err < 2e-5, "rel err %g" % err
 
 
+STRIDED_CASES = [(1, 16, 16, 64, 64, 3), (2, 17, 23, 128, 128, 3), (1, 31, 40, 256, 256, 3), (2, 17, 23, 256, 512, 1),
+                 (1, 30, 41, 512, 1024, 1)]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", STRIDED_CASES)
+def test_conv2d_stride2_fprop_and_wgrad_vs_torch_cpu(B, H, W, Cin, Cout, k):
+    """stride-2 convolutions through the TMA traversal stride (no subsample / zero-insert passes)."""
+    from tinyfaces_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(B + H + Cin + k)
+    x = _tf32(torch.randn(B, Cin, H, W, generator=gen))
+    w = _tf32(torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5).double().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(x.double(), w, stride=2, padding=k // 2)
+    dy = _tf32(torch.randn(ref.shape, generator=gen))
+    ref.backward(dy.double())
+    xn = x.permute(0, 2, 3, 1).contiguous().to(d)
+    wp = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous().to(d)
+    y = ops.conv2d_nhwc_strided(xn, wp, k, 2)
+    dw = ops.conv2d_wgrad_nhwc_strided(xn, dy.permute(0, 2, 3, 1).contiguous().to(d), k, 2)
+    torch.cuda.synchronize()
+    assert ops.gemm_error_flag() == 0
+    got = y.cpu().permute(0, 3, 1, 2)
+    assert tuple(got.shape) == tuple(ref.shape)
+    e = (got - ref.detach().float()).abs().max().item() / ref.abs().max().item()
+    gw = dw.cpu().reshape(Cout, k, k, Cin).permute(0, 3, 1, 2)
+    ew = (gw - w.grad.float()).abs().max().item() / w.grad.abs().max().item()
+    assert e < 2e-5 and ew < 2e-5, (e, ew)
+
+
 def test_conv2d_3xtf32_parity_mode():
     """hi/lo split operands through the 3-segment K loop recover fp32-level accuracy on arbitrary fp32 data."""
     from tinyfaces_b200 import ops

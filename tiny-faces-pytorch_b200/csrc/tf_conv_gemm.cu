@@ -43,6 +43,7 @@ struct GemmParams {
     int spatial;                  // 0: A/D are 2-D [pixels, C]; 1: 4-D (C, W, H, B) with spatial tiles
     int tiles_x, tiles_y, tw, th; // spatial tiling of one image (tw * th == 128)
     int taps, kblocks, nseg;      // K loop = nseg x taps x kblocks blocks of 32 channels
+    int stride;                   // spatial mode: input coordinate = stride * output coordinate + tap offset (TMA elementStrides)
     const float* scale;           // optional per-output-channel epilogue: v = v * scale[n] + shift[n]
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
     int relu, round_out;
@@ -128,7 +129,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                             uint8_t* sb = sa + A_STAGE_BYTES;
                             mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                             if (p.spatial)
-                                tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img);
+                                tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
                             else
                                 tma_load_2d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, m0);
                             tma_load_2d(sb, &maps.b[seg], &full[stage], (tap * p.kblocks + kb) * BLOCK_K, n0);
@@ -262,6 +263,7 @@ struct WgradParams {
     int num_pblocks;                            // total pixel blocks
     int cin, cout;                              // dW is [cout][taps*cin]; column = tap * cin + ci
     int b_groups;                               // 32-channel groups fetched per B-operand TMA (= min(BN, cin) / 32)
+    int stride;                                 // X coordinate = stride * dY coordinate + tap offset
     int plain_store;                            // debug: overwrite instead of reduce-add (needs splits == 1)
     int* err_flag;
 };
@@ -326,7 +328,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                             const int col = n0 + j * 32;
                             const int tap = col < ncols ? col / p.cin : 0;
                             const int grp = col < ncols ? (col - tap * p.cin) / 32 : p.cin / 32;    // past the end: all zero
-                            tma_load_5d(sb + j * 4096, &maps.b[seg], &full[stage], 0, x0 + tap_dx(p.taps, tap), y0 + tap_dy(p.taps, tap), img, grp);
+                            tma_load_5d(sb + j * 4096, &maps.b[seg], &full[stage], 0, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img, grp);
                         }
                     } else {
                         tma_load_3d(sa, &maps.a[seg], &full[stage], 0, pb * 32, m0 / 32);
@@ -430,13 +432,14 @@ int encode_2d(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uin
 }
 // 4-D NHWC fp32 tensor viewed as (C, W, H, B), box (bc<=32, bw, bh, 1)
 int encode_4d(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t bc, uint32_t bw,
-              uint32_t bh, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+              uint32_t bh, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint32_t estride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
     cuuint64_t dims[4] = {C, W, H, B};
     cuuint64_t strides[3] = {C * 4, W * C * 4, H * W * C * 4};
-    cuuint32_t box[4] = {bc, bw, bh, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    // with a traversal stride s the box spans s*n coordinates and loads every s-th element (n of them)
+    cuuint32_t box[4] = {bc, bw * estride, bh * estride, 1};
+    cuuint32_t es[4] = {1, estride, estride, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -461,13 +464,13 @@ int encode_3d_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t rows
     return TF_OK;
 }
 int encode_5d_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t bw, uint32_t bh,
-                      uint32_t groups) {
+                      uint32_t groups, uint32_t estride = 1) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
     cuuint64_t dims[5] = {32, W, H, B, C / 32};
     cuuint64_t strides[4] = {C * 4, W * C * 4, H * W * C * 4, 128};
-    cuuint32_t box[5] = {32, bw, bh, 1, groups};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    cuuint32_t box[5] = {32, bw * estride, bh * estride, 1, groups};
+    cuuint32_t es[5] = {1, estride, estride, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -547,16 +550,20 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     TF_REQUIRE(a.B > 0 && a.H > 0 && a.W > 0 && a.Cin > 0 && a.Cin % 32 == 0 && a.Cout >= 64 && a.Cout % 64 == 0,
                "conv_fprop: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d", a.B, a.H, a.W, a.Cin, a.Cout);
     TF_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_fprop: ksize must be 1 or 3");
+    TF_REQUIRE(a.stride == 0 || a.stride == 1 || a.stride == 2, "conv_fprop: stride must be 1 or 2");
     int rc = ensure_device_state();
     if (rc) return rc;
     const int B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout;
     const int taps = a.ksize * a.ksize;
     GemmMaps maps;
     GemmParams p = {};
-    const long long Mtot = (long long)B * H * W;
+    const int stride = a.stride == 2 ? 2 : 1;
+    const int Ho = stride == 2 ? (H + 1) / 2 : H, Wo = stride == 2 ? (W + 1) / 2 : W;      // output size
+    const bool spatial = a.ksize == 3 || stride == 2;
+    const long long Mtot = (long long)B * Ho * Wo;
     int m_tiles;
-    if (a.ksize == 1) m_tiles = (int)((Mtot + BLOCK_M - 1) / BLOCK_M);
-    else { int tw, th; pick_tile(W, H, BLOCK_M, &tw, &th); m_tiles = B * ((W + tw - 1) / tw) * ((H + th - 1) / th); }
+    if (!spatial) m_tiles = (int)((Mtot + BLOCK_M - 1) / BLOCK_M);
+    else { int tw, th; pick_tile(Wo, Ho, BLOCK_M, &tw, &th); m_tiles = B * ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th); }
     // tile width: fewest (rounds over the SMs) x (time per tile ~ BN); narrower tiles pay more smem bandwidth per MMA
     int BN = 64; double best = 1e30;
     for (int cand = 256; cand >= 64; cand >>= 1) {
@@ -570,13 +577,14 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     p.taps = taps; p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
-    p.stats_partial = a.stats_partial; p.cout = Cout; p.img_w = W; p.img_h = H;
+    p.stats_partial = a.stats_partial; p.cout = Cout; p.img_w = Wo; p.img_h = Ho;
     p.err_flag = g_err_flag;
     p.num_n_tiles = Cout / BN;
     const float* as[3] = {a.x, a.x_lo, a.x};
     const float* bs[3] = {a.w, a.w, a.w_lo};
-    const long long M = (long long)B * H * W;
-    if (a.ksize == 1) {
+    const long long M = Mtot;
+    p.stride = stride;
+    if (!spatial) {
         p.spatial = 0;
         p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
         p.tiles_x = p.tiles_y = 1; p.tw = 128; p.th = 1;
@@ -585,12 +593,12 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         if ((rc = encode_2d(&maps.d, a.y, Cout, M, Cout, 32, BLOCK_M))) return rc;
     } else {
         p.spatial = 1;
-        pick_tile(W, H, BLOCK_M, &p.tw, &p.th);
-        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
+        pick_tile(Wo, Ho, BLOCK_M, &p.tw, &p.th);
+        p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th;
         p.num_m_tiles = B * p.tiles_x * p.tiles_y;
         for (int s = 0; s < p.nseg; ++s)
-            if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th))) return rc;
-        if ((rc = encode_4d(&maps.d, a.y, Cout, W, H, B, 32, p.tw, p.th))) return rc;
+            if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B, stride))) return rc;
+        if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, p.tw, p.th))) return rc;
     }
     for (int s = 0; s < p.nseg; ++s)
         if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
@@ -629,8 +637,11 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
     TF_REQUIRE(Cin >= BN || BN % Cin == 0 || a.ksize == 1, "conv_wgrad: Cin=%d does not tile BN=%d", Cin, BN);
     const float* as[3] = {a.dy, a.dy_lo, a.dy};
     const float* bs[3] = {a.x, a.x, a.x_lo};
-    const long long M = (long long)B * H * W;
-    if (a.ksize == 1) {
+    const int stride = a.stride == 2 ? 2 : 1;
+    const int Ho = stride == 2 ? (H + 1) / 2 : H, Wo = stride == 2 ? (W + 1) / 2 : W;      // dy is [B,Ho,Wo,Cout], x is [B,H,W,Cin]
+    const long long M = (long long)B * Ho * Wo;
+    p.stride = stride;
+    if (a.ksize == 1 && stride == 1) {
         p.spatial = 0; p.tiles_x = p.tiles_y = 1; p.tw = 32; p.th = 1;
         p.num_pblocks = (int)((M + 31) / 32);
         for (int s = 0; s < p.nseg; ++s) {
@@ -639,12 +650,12 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
         }
     } else {
         p.spatial = 1;
-        pick_tile(W, H, 32, &p.tw, &p.th);
-        p.tiles_x = (W + p.tw - 1) / p.tw; p.tiles_y = (H + p.th - 1) / p.th;
+        pick_tile(Wo, Ho, 32, &p.tw, &p.th);
+        p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th;
         p.num_pblocks = B * p.tiles_x * p.tiles_y;
         for (int s = 0; s < p.nseg; ++s) {
-            if ((rc = encode_5d_grouped(&maps.a[s], as[s], Cout, W, H, B, p.tw, p.th, BLOCK_M / 32))) return rc;
-            if ((rc = encode_5d_grouped(&maps.b[s], bs[s], Cin, W, H, B, p.tw, p.th, p.b_groups))) return rc;
+            if ((rc = encode_5d_grouped(&maps.a[s], as[s], Cout, Wo, Ho, B, p.tw, p.th, BLOCK_M / 32))) return rc;
+            if ((rc = encode_5d_grouped(&maps.b[s], bs[s], Cin, W, H, B, p.tw, p.th, p.b_groups, stride))) return rc;
         }
     }
     if ((rc = encode_2d(&maps.d, a.dw, (uint64_t)p.taps * Cin, Cout, (uint64_t)p.taps * Cin, 32, BLOCK_M))) return rc;
@@ -679,6 +690,21 @@ TF_API int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, i
                                 float* dw_packed, void* stream) {
     tfg::WgradArgs a = {};
     a.x = x; a.dy = dy; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.dw = dw_packed;
+    return tfg::conv_wgrad(a, (cudaStream_t)stream);
+}
+
+// Strided variants (stride 1 or 2, padding ksize/2): y is [B, ceil(H/s), ceil(W/s), Cout]; dy likewise.
+TF_API int tf_conv2d_nhwc_strided(const float* x, int B, int H, int W, int Cin, const float* w_packed, int Cout, int ksize,
+                                  int stride, const float* bias, float* y, void* stream) {
+    tfg::ConvArgs a = {};
+    a.x = x; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.w = w_packed; a.Cout = Cout; a.ksize = ksize; a.stride = stride;
+    a.shift = bias; a.y = y;
+    return tfg::conv_fprop(a, (cudaStream_t)stream);
+}
+TF_API int tf_conv2d_wgrad_nhwc_strided(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
+                                        int stride, float* dw_packed, void* stream) {
+    tfg::WgradArgs a = {};
+    a.x = x; a.dy = dy; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.stride = stride; a.dw = dw_packed;
     return tfg::conv_wgrad(a, (cudaStream_t)stream);
 }
 

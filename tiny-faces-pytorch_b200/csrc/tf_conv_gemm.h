@@ -7,7 +7,8 @@ struct ConvArgs {
     const float* x; const float* x_lo;     // NHWC input (+ low-order split part in 3xTF32 mode)
     int B, H, W, Cin;
     const float* w; const float* w_lo;     // packed [Cout][k*k][Cin]
-    int Cout, ksize;                       // stride 1, "same" padding
+    int Cout, ksize;                       // padding ksize/2
+    int stride;                            // 0/1 or 2 (strided TMA traversal); output is ceil(H/s) x ceil(W/s)
     const float* scale; const float* shift;// optional per-channel epilogue (shift alone = bias)
     int relu, round_out, accumulate;
     float* y;                              // NHWC output
@@ -20,6 +21,7 @@ struct WgradArgs {
     const float* x; const float* x_lo;
     const float* dy; const float* dy_lo;
     int B, H, W, Cin, Cout, ksize;
+    int stride;                            // x is [B,H,W,Cin]; dy is [B,ceil(H/s),ceil(W/s),Cout]
     float* dw;                             // packed [Cout][k*k][Cin], accumulated into
 };
 int conv_wgrad(const WgradArgs& a, cudaStream_t st);

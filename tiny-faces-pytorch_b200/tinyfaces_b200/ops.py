@@ -140,6 +140,28 @@ def conv2d_wgrad_nhwc(x, dy, ksize, out=None):
     return dw
 
 
+def conv2d_nhwc_strided(x, w_packed, ksize, stride, bias=None):
+    """Strided variant (TMA traversal stride): y [B, ceil(H/s), ceil(W/s), Cout]."""
+    require_cuda(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    Ho, Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    check(lib().tf_conv2d_nhwc_strided(ptr(x), B, H, W, Cin, ptr(w_packed), Cout, ksize, stride, ptr(bias), ptr(y),
+                                       stream_ptr(x.device)), "tf_conv2d_nhwc_strided")
+    return y
+
+
+def conv2d_wgrad_nhwc_strided(x, dy, ksize, stride):
+    require_cuda(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[3]
+    dw = torch.zeros((Cout, ksize * ksize, Cin), dtype=torch.float32, device=x.device)
+    check(lib().tf_conv2d_wgrad_nhwc_strided(ptr(x), ptr(dy), B, H, W, Cin, Cout, ksize, stride, ptr(dw),
+                                             stream_ptr(x.device)), "tf_conv2d_wgrad_nhwc_strided")
+    return dw
+
+
 def gemm_error_flag():
     v = ctypes.c_int(0)
     check(lib().tf_gemm_error_flag(ctypes.byref(v)), "tf_gemm_error_flag")
