@@ -119,35 +119,19 @@ struct Model {
         tfg::ConvArgs a = {};
         a.B = B_; a.Cin = c.cin; a.Cout = c.cout; a.ksize = c.k; a.w = u.wp; a.w_lo = u.wp_lo;
         if (fused) { a.scale = u.scale; a.shift = u.shift; a.relu = relu; a.round_out = 1; }
-        if (c.k == 1 && c.stride == 2) {
-            float* xs = ar.f((size_t)B_ * Ho * Wo * c.cin);
-            float* xs_lo = x_lo ? ar.f((size_t)B_ * Ho * Wo * c.cin) : nullptr;
-            if (!ar.dry) RC(tfe::subsample2(x, x_lo, B_, H_, W_, c.cin, xs, xs_lo, st));
-            u.x = xs; u.x_lo = xs_lo; u.H = Ho; u.W = Wo;
-        } else {
-            u.x = x; u.x_lo = x_lo; u.H = H_; u.W = W_;
-        }
-        a.x = u.x; a.x_lo = u.x_lo; a.H = u.H; a.W = u.W;
+        // stride 2 is a TMA traversal stride: the GEMM reads the full-resolution input directly
+        u.x = x; u.x_lo = x_lo; u.H = H_; u.W = W_;
+        a.x = u.x; a.x_lo = u.x_lo; a.H = u.H; a.W = u.W; a.stride = c.stride;
         float* dst = fused_out ? fused_out : ar.f((size_t)B_ * Ho * Wo * c.cout);
-        if (c.k == 3 && c.stride == 2) {
-            float* yf = ar.f((size_t)B_ * H_ * W_ * c.cout);
-            a.y = yf;
-            if (!ar.dry) { RC(tfg::conv_fprop(a, st)); RC(tfe::subsample2(yf, nullptr, B_, H_, W_, c.cout, dst, nullptr, st)); }
-        } else {
-            a.y = dst;
-            if (stats_blocks) { a.stats_partial = partial; a.stats_blocks = stats_blocks; }   // BN statistics in the epilogue
-            if (!ar.dry) RC(tfg::conv_fprop(a, st));
-        }
+        a.y = dst;
+        if (stats_blocks) { a.stats_partial = partial; a.stats_blocks = stats_blocks; }   // BN statistics in the epilogue
+        if (!ar.dry) RC(tfg::conv_fprop(a, st));
         u.y = dst;
         return TF_OK;
     }
     // conv whose training-mode BN statistics come out of the GEMM epilogue (separate reduction only for 3x3/s2)
     int conv_with_stats(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, cudaStream_t st) {
         if (!training) return run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st);
-        if (u.c.k == 3 && u.c.stride == 2) {
-            RC(run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st));
-            return bn_stats(u, st);
-        }
         int nblk = 0;
         RC(run_conv(u, x, x_lo, B_, H_, W_, 0, 0, nullptr, st, &nblk));
         RC(alloc_bn(u));
@@ -357,20 +341,13 @@ struct Model {
                       void* const* grads, cudaStream_t st) {
         const ConvP& c = u.c;
         const int taps = c.k * c.k;
-        const float* dyg = dy; const float* dyg_lo = dy_lo;         // dy at the resolution the GEMM ran at
-        if (c.k == 3 && c.stride == 2) {
-            float* z = ar.f((size_t)u.B * u.H * u.W * c.cout);
-            float* z_lo = dy_lo ? ar.f((size_t)u.B * u.H * u.W * c.cout) : nullptr;
-            if (!ar.dry) RC(tfe::zero_insert2(dy, dy_lo, u.B, u.H, u.W, c.cout, z, z_lo, st));
-            dyg = z; dyg_lo = z_lo;
-        }
-        // ---- wgrad
+        // ---- wgrad (a stride-2 conv reads x through the TMA traversal stride; dy stays at the output resolution)
         float* gw = G(grads, c.w);
         if (gw && !ar.dry) {
             TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)c.cout * taps * c.cin * 4, st));
             tfg::WgradArgs w = {};
-            w.x = u.x; w.x_lo = u.x_lo; w.dy = dyg; w.dy_lo = dyg_lo; w.B = u.B; w.H = u.H; w.W = u.W; w.Cin = c.cin; w.Cout = c.cout;
-            w.ksize = c.k; w.dw = dwtmp;
+            w.x = u.x; w.x_lo = u.x_lo; w.dy = dy; w.dy_lo = dy_lo; w.B = u.B; w.H = u.H; w.W = u.W; w.Cin = c.cin; w.Cout = c.cout;
+            w.ksize = c.k; w.stride = c.stride; w.dw = dwtmp;
             if (w.x_lo == nullptr || w.dy_lo == nullptr) { w.x_lo = nullptr; w.dy_lo = nullptr; }
             RC(tfg::conv_wgrad(w, st));
             RC(tfe::unpack_wgrad(dwtmp, c.cout, c.cin, taps, c.cin, gw, st));
@@ -381,19 +358,28 @@ struct Model {
             ConvP ct = c;
             RC(pack(ct, c.cin, c.cout, 1, &wt, &wt_lo, st));        // [Cin][taps][Cout]
             tfg::ConvArgs a = {};
-            a.x = dyg; a.x_lo = dyg_lo; a.B = u.B; a.H = u.H; a.W = u.W; a.Cin = c.cout; a.w = wt; a.w_lo = wt_lo; a.Cout = c.cin; a.ksize = c.k;
-            if (a.x_lo == nullptr) a.w_lo = nullptr;
-            if (c.k == 1 && c.stride == 2) {
-                // gradient w.r.t. the subsampled input, then scatter to the even positions of dx
-                float* dxs = ar.f((size_t)u.B * u.H * u.W * c.cin);
-                a.y = dxs;
+            a.B = u.B; a.Cin = c.cout; a.w = wt; a.w_lo = wt_lo; a.Cout = c.cin; a.ksize = c.k;
+            if (c.stride == 2 && c.k == 3) {
+                // zero-insert dy to the input resolution, then a stride-1 conv with the flipped kernel
+                float* z = ar.f((size_t)u.B * u.H * u.W * c.cout);
+                float* z_lo = dy_lo ? ar.f((size_t)u.B * u.H * u.W * c.cout) : nullptr;
+                if (!ar.dry) RC(tfe::zero_insert2(dy, dy_lo, u.B, u.H, u.W, c.cout, z, z_lo, st));
+                a.x = z; a.x_lo = z_lo; a.H = u.H; a.W = u.W; a.y = dx; a.accumulate = dx_accumulate;
+                if (a.x_lo == nullptr) a.w_lo = nullptr;
+                if (!ar.dry) RC(tfg::conv_fprop(a, st));
+            } else if (c.stride == 2) {
+                // 1x1/s2: gradient w.r.t. the sampled pixels at the output resolution, scattered to the even positions
+                float* dxs = ar.f((size_t)u.B * u.Ho * u.Wo * c.cin);
+                a.x = dy; a.x_lo = dy_lo; a.H = u.Ho; a.W = u.Wo; a.y = dxs;
+                if (a.x_lo == nullptr) a.w_lo = nullptr;
                 if (!ar.dry) {
                     RC(tfg::conv_fprop(a, st));
                     TF_REQUIRE(!dx_accumulate, "unit_conv_bwd: accumulate into a strided dgrad is not supported");
                     RC(tfe::zero_insert2(dxs, nullptr, u.B, dxH, dxW, c.cin, dx, nullptr, st));
                 }
             } else {
-                a.y = dx; a.accumulate = dx_accumulate;
+                a.x = dy; a.x_lo = dy_lo; a.H = u.H; a.W = u.W; a.y = dx; a.accumulate = dx_accumulate;
+                if (a.x_lo == nullptr) a.w_lo = nullptr;
                 if (!ar.dry) RC(tfg::conv_fprop(a, st));
             }
         }
