@@ -183,10 +183,20 @@ __global__ void __launch_bounds__(1024) scan_kernel(const Box<T>* __restrict__ s
         }
         for (int wd = c + 1 + tid; wd < nchunks; wd += blockDim.x) {
             unsigned long long acc = removed[wd], rest = kb;
-            while (rest) {
-                const int i = __ffsll((long long)rest) - 1;
-                rest &= rest - 1;
-                acc |= mask[(size_t)(c * 64 + i) * words_per_row + wd];
+            const unsigned long long* col = mask + (size_t)(c * 64) * words_per_row + wd;
+            while (rest) {                      // 8 independent row loads in flight per step (latency-bound otherwise)
+                unsigned long long v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = 0ull;
+                    if (rest) {
+                        const int i = __ffsll((long long)rest) - 1;
+                        rest &= rest - 1;
+                        v[u] = __ldg(col + (size_t)i * words_per_row);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc |= v[u];
             }
             removed[wd] = acc;
         }
