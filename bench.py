@@ -238,13 +238,24 @@ def main():
     line["step_tflops"] = STEP_GFLOP_PER_IMG * value / 1000.0
     line["step_frac_of_tf32_sustained"] = line["step_tflops"] / (pk["tf32_sustained"] * world)
 
-    if rank == 0:
-        # ---- kernel launch census of one step (CUPTI via torch.profiler; not timed)
-        try:
+    # ---- kernel launch census of one step (CUPTI via torch.profiler; not timed).  The step contains the gradient
+    #      all-reduce, so EVERY rank runs it; only rank 0 records.
+    prof = None
+    try:
+        if rank == 0:
             from torch.profiler import ProfilerActivity, profile
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
                 step_resident()
                 torch.cuda.synchronize()
+        else:
+            step_resident()
+            torch.cuda.synchronize()
+    except Exception as ex:      # noqa: BLE001
+        line["profiler_error"] = str(ex)[:200]
+    if rank == 0:
+        try:
+            if prof is None:
+                raise RuntimeError("no profile")
             ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
             mine = [e for e in ev if any(s in e.name for s in ("conv_gemm_kernel", "conv_wgrad_kernel", "kernel<", "_kernel"))
                     and "at::native" not in e.name and "nccl" not in e.name.lower()]

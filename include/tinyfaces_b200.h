@@ -28,6 +28,7 @@ int tf_gemm_error_flag(int* value_host);         /* HOST out: non-zero if a tcge
  * kept ORIGINAL indices in descending-score order; num_keep is a device int64.  Bit-identical to the CPU op:
  * stable descending sort, area (x2-x1)*(y2-y1), suppress iff inter/(a_i+a_j-inter) > thr. */
 int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes_host);
+int tf_nms_set_algorithm(int algo);   /* test hook: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep + parallel resolution */
 int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int64_t* keep,
            int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
 

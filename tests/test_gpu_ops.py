@@ -16,40 +16,74 @@ def _dev():
     return torch.device("cuda:0")
 
 
-def _nms(boxes, scores, thr):
-    from tinyfaces_b200 import ops
+def _nms(boxes, scores, thr, algo=0):
+    from tinyfaces_b200 import _lib, ops
     d = _dev()
-    keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr)
-    return keep[: int(count.item())].cpu().numpy()
+    _lib.lib().tf_nms_set_algorithm(algo)          # 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep
+    try:
+        keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr)
+        return keep[: int(count.item())].cpu().numpy()
+    finally:
+        _lib.lib().tf_nms_set_algorithm(0)
 
 
 # ------------------------------------------------------------------------------------------- NMS
+@pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_case_f32"])
-def test_nms_golden_bit_exact(name):
+def test_nms_golden_bit_exact(name, algo):
     g = np.load(os.path.join(G, name + ".npz"))
-    assert np.array_equal(_nms(g["boxes"], g["scores"], float(g["thr"])), g["keep"])
+    assert np.array_equal(_nms(g["boxes"], g["scores"], float(g["thr"]), algo), g["keep"])
 
 
 def test_nms_known_answers():
     with open(os.path.join(G, "nms_known.json")) as f:
         cases = json.load(f)["cases"]
     for c in cases:
-        k = _nms(np.array(c["boxes"], np.float64), np.array(c["scores"], np.float64), c["thr"])
-        assert k.tolist() == c["keep"], c
+        for algo in (1, 2):
+            k = _nms(np.array(c["boxes"], np.float64), np.array(c["scores"], np.float64), c["thr"], algo)
+            assert k.tolist() == c["keep"], (c, algo)
     from tinyfaces_b200 import ops
     keep, count = ops.nms_device(torch.zeros((0, 4), dtype=torch.float64, device=_dev()),
                                  torch.zeros(0, dtype=torch.float64, device=_dev()), 0.3)
     assert keep.numel() == 0 and keep.dtype == torch.int64 and int(count.item()) == 0
 
 
+@pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("n,extent,thr", [(1, 10.0, 0.3), (63, 50.0, 0.3), (4097, 600.0, 0.3), (20000, 1500.0, 0.5),
-                                          (40000, 1800.0, 0.3)])
-def test_nms_vs_c_oracle(n, extent, thr):
-    """bit-exact keep indices incl. the multi-block path (n > 32768), ties and duplicates."""
+                                          (40000, 1800.0, 0.3), (30000, 300.0, 0.3), (20000, 1200.0, 0.0)])
+def test_nms_vs_c_oracle(n, extent, thr, algo):
+    """bit-exact keep indices for both algorithms: the blocked bit-matrix path (incl. n > 32768) and the
+    sort-and-sweep path (incl. a dense case with long suppression chains); ties and duplicates."""
     from oracle import nms_oracle, synth
     boxes, scores = synth.synthetic_boxes(n, seed=n, extent=extent, dup_frac=0.02)
     scores = np.round(scores, 3)            # many exact score ties
-    assert np.array_equal(_nms(boxes, scores, thr), nms_oracle.nms(boxes, scores, thr))
+    assert np.array_equal(_nms(boxes, scores, thr, algo), nms_oracle.nms(boxes, scores, thr))
+
+
+def test_nms_large_n_property():
+    """N = 1e6 (beyond what the O(N^2) oracle can check): the kept set is conflict-free among the top kept boxes and
+    every sampled removed box has a kept suppressor with a higher-or-equal score."""
+    from oracle import synth
+    n = 1000000
+    boxes, scores = synth.synthetic_boxes(n, seed=1, dup_frac=0.001)
+    keep = _nms(boxes, scores, 0.3)
+    assert len(np.unique(keep)) == len(keep) and np.all(np.diff(scores[keep]) <= 0)          # unique, score-descending
+
+    def iou(a, b):
+        w = np.maximum(np.minimum(a[2], b[:, 2]) - np.maximum(a[0], b[:, 0]), 0)
+        h = np.maximum(np.minimum(a[3], b[:, 3]) - np.maximum(a[1], b[:, 1]), 0)
+        inter = w * h
+        return inter / ((a[2] - a[0]) * (a[3] - a[1]) + (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1]) - inter)
+    kb = boxes[keep]
+    r = np.random.RandomState(0)
+    for i in r.choice(len(keep), 200, replace=False):                  # kept boxes do not suppress each other
+        ov = iou(kb[i], kb)
+        ov[i] = 0
+        assert not np.any((ov > 0.3) & (np.arange(len(keep)) < i))
+    removed = np.setdiff1d(np.arange(n), keep)
+    for j in r.choice(removed, 200, replace=False):                    # every removed box has a kept suppressor
+        ov = iou(boxes[j], kb)
+        assert np.any((ov > 0.3) & (scores[keep] >= scores[j]))
 
 
 def test_nms_degenerate_nothing_suppressed():

@@ -69,6 +69,37 @@ struct Model {
     float *w3p = nullptr, *w3p_lo = nullptr, *w4p = nullptr, *w4p_lo = nullptr, *b3p = nullptr, *b4p = nullptr, *up = nullptr, *offdiag = nullptr;
     float* partial = nullptr; float* coef = nullptr; float* dwtmp = nullptr; size_t fwd_mark = 0;
     float eps = 1e-5f, momentum = 0.1f;
+    // weight-gradient GEMMs run on a side stream: they depend only on (x, dy) and nothing in the backward chain
+    // depends on them, so their tensor-core time overlaps the HBM-bound BN-backward kernels of the main stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_region[2] = {nullptr, nullptr};
+    size_t bwd_region_bytes = 0;
+    bool side_enabled = true;
+    int ensure_side() {
+        if (!side_enabled || side) return TF_OK;
+        TF_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_region[i], cudaEventDisableTiming));
+        return TF_OK;
+    }
+    ~Model() {
+        if (side) { cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_region[0]); cudaEventDestroy(ev_region[1]); }
+    }
+    // dW (OIHW) = unpack(wgrad(x, dy)): enqueued behind everything already on `st`, executed on the side stream
+    int wgrad_async(tfg::WgradArgs w, size_t dw_elems, int O, int I, int taps, int I_pad, float* gw, cudaStream_t st) {
+        cudaStream_t s2 = st;
+        if (side) {
+            TF_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+            TF_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+            s2 = side;
+        }
+        TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, dw_elems * 4, s2));
+        w.dw = dwtmp;
+        RC(tfg::conv_wgrad(w, s2));
+        RC(tfe::unpack_wgrad(dwtmp, O, I, taps, I_pad, gw, s2));
+        return TF_OK;
+    }
 
     int add(const std::string& n) { names.push_back(n); return (int)names.size() - 1; }
     ConvP conv(const std::string& p, int cin, int cout, int k, int stride) { ConvP c; c.w = add(p + ".weight"); c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; return c; }
@@ -344,13 +375,11 @@ struct Model {
         // ---- wgrad (a stride-2 conv reads x through the TMA traversal stride; dy stays at the output resolution)
         float* gw = G(grads, c.w);
         if (gw && !ar.dry) {
-            TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)c.cout * taps * c.cin * 4, st));
             tfg::WgradArgs w = {};
             w.x = u.x; w.x_lo = u.x_lo; w.dy = dy; w.dy_lo = dy_lo; w.B = u.B; w.H = u.H; w.W = u.W; w.Cin = c.cin; w.Cout = c.cout;
-            w.ksize = c.k; w.stride = c.stride; w.dw = dwtmp;
+            w.ksize = c.k; w.stride = c.stride;
             if (w.x_lo == nullptr || w.dy_lo == nullptr) { w.x_lo = nullptr; w.dy_lo = nullptr; }
-            RC(tfg::conv_wgrad(w, st));
-            RC(tfe::unpack_wgrad(dwtmp, c.cout, c.cin, taps, c.cin, gw, st));
+            RC(wgrad_async(w, (size_t)c.cout * taps * c.cin, c.cout, c.cin, taps, c.cin, gw, st));
         }
         // ---- dgrad: dx = conv(dy, w^T flipped)
         if (dx) {
@@ -430,18 +459,30 @@ struct Model {
         size_t mx = 0;
         for (const BlockS& s : bs) mx = std::max(mx, (size_t)s.B * s.H * s.W * s.u1.c.cin);
         float* dxbuf[2] = {ar.f(mx), ar.f(mx)};
-        const size_t scratch_mark = ar.off;
+        if (!ar.dry) RC(ensure_side());
         RC(head_bwd(h4, ds4, dres4, 0, grads, st));
+        const size_t scratch_mark = ar.off;
+        // Two scratch regions alternate between blocks: the side stream may still be reading block i's dy tensors
+        // (weight gradients) while the main stream already works on block i-1; region r is reused only after the
+        // side-stream work that read it has finished (ev_region[r]).
+        const size_t region = ar.dry ? 0 : bwd_region_bytes;
+        size_t max_used = 0;
         // ---- layer3 .. layer1
         const float* dcur = dres4;
         for (int i = (int)blocks.size() - 1; i >= 0; --i) {
             const BlockS& s = bs[i];
-            ar.off = scratch_mark;
+            const int r = i & 1;
+            ar.off = scratch_mark + (size_t)r * region;
+            if (!ar.dry && side) TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[r], 0));
             float* dx = dxbuf[i & 1];
             RC(block_backward(s, dcur, dx, grads, st));
             if (i == 7) RC(head_bwd(h3, ds3, dx, 1, grads, st));   // res3 also feeds score_res3: dx(block 7 input) += head dgrad
+            if (!ar.dry && side) TF_CHECK_CUDA(cudaEventRecord(ev_region[r], side));
+            max_used = std::max(max_used, ar.off - (scratch_mark + (size_t)r * region));
             dcur = dx;
         }
+        if (ar.dry) { bwd_region_bytes = tf_align_up(max_used, 1024); ar.peak = std::max(ar.peak, scratch_mark + 2 * bwd_region_bytes + 4096); }
+        else if (side) { TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[0], 0)); TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[1], 0)); }
         ar.off = scratch_mark;
         // ---- stem
         const long long M2 = (long long)B * H2 * W2;
@@ -451,12 +492,14 @@ struct Model {
         RC(unit_bn_bwd(stem_u, da0, stem_u.amask, nullptr, &dy0, &dy0_lo, grads, st));
         float* gw = G(grads, stem.w);
         if (gw && !ar.dry) {
-            TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)64 * 160 * 4, st));
             tfg::WgradArgs w = {};
-            w.x = col; w.x_lo = col_lo; w.dy = dy0; w.dy_lo = dy0_lo; w.B = 1; w.H = 1; w.W = (int)M2; w.Cin = 160; w.Cout = 64; w.ksize = 1; w.dw = dwtmp;
+            w.x = col; w.x_lo = col_lo; w.dy = dy0; w.dy_lo = dy0_lo; w.B = 1; w.H = 1; w.W = (int)M2; w.Cin = 160; w.Cout = 64; w.ksize = 1;
             if (!w.x_lo || !w.dy_lo) { w.x_lo = nullptr; w.dy_lo = nullptr; }
-            RC(tfg::conv_wgrad(w, st));
-            RC(tfe::unpack_wgrad(dwtmp, 64, 147, 1, 160, gw, st));
+            RC(wgrad_async(w, (size_t)64 * 160, 64, 147, 1, 160, gw, st));
+        }
+        if (!ar.dry && side) {                       // join: the caller's stream sees every gradient
+            TF_CHECK_CUDA(cudaEventRecord(ev_join, side));
+            TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
         }
         return TF_OK;
     }
@@ -465,11 +508,9 @@ struct Model {
         const ConvP& c = h.c;
         float* gw = G(grads, c.w);
         if (gw && !ar.dry) {
-            TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, (size_t)Cp * c.cin * 4, st));
             tfg::WgradArgs w = {};
-            w.x = h.x; w.dy = ds; w.B = h.B; w.H = h.H; w.W = h.W; w.Cin = c.cin; w.Cout = Cp; w.ksize = 1; w.dw = dwtmp;
-            RC(tfg::conv_wgrad(w, st));
-            RC(tfe::unpack_wgrad(dwtmp, Cn, c.cin, 1, c.cin, gw, st));
+            w.x = h.x; w.dy = ds; w.B = h.B; w.H = h.H; w.W = h.W; w.Cin = c.cin; w.Cout = Cp; w.ksize = 1;
+            RC(wgrad_async(w, (size_t)Cp * c.cin, Cn, c.cin, 1, c.cin, gw, st));
         }
         float *wt, *wt_lo;
         ConvP ct = c; ct.cout = Cn;

@@ -13,6 +13,7 @@
 // explicit round-to-nearest intrinsics (no FMA contraction), so keep indices are identical.
 // HBM-bound for N <~ 1e4, pair-test (ALU) bound above.
 #include "tf_common.cuh"
+#include "tf_nms_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
@@ -20,40 +21,7 @@ namespace {
 constexpr int NB = 32768;        // sorted boxes per block
 constexpr int COLS_PER_CTA = 256;
 
-template <typename T> struct Arith;
-template <> struct Arith<double> {
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-};
-template <> struct Arith<float> {
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-};
-
-template <typename T> struct alignas(4 * sizeof(T)) Box { T x1, y1, x2, y2; };
-
-// torchvision nms_kernel_impl: ovr = inter / (iarea + jarea - inter); suppress iff ovr > thr
-template <typename T>
-__device__ __forceinline__ bool suppresses(const Box<T>& a, T aa, const Box<T>& b, T ba, double thr,
-                                           bool prefilter) {
-    using A = Arith<T>;
-    T xx1 = a.x1 > b.x1 ? a.x1 : b.x1;       // std::max(ix1, x1[j])
-    T yy1 = a.y1 > b.y1 ? a.y1 : b.y1;
-    T xx2 = b.x2 < a.x2 ? b.x2 : a.x2;       // std::min(ix2, x2[j])
-    T yy2 = b.y2 < a.y2 ? b.y2 : a.y2;
-    T w = A::sub(xx2, xx1), h = A::sub(yy2, yy1);
-    // thr >= 0: a pair without positive overlap has ovr == 0 or NaN and can never suppress
-    if (prefilter && !(w > (T)0 && h > (T)0)) return false;
-    w = w > (T)0 ? w : (T)0;                 // std::max(0, w)
-    h = h > (T)0 ? h : (T)0;
-    T inter = A::mul(w, h);
-    T ovr = A::div(inter, A::sub(A::add(aa, ba), inter));
-    return (double)ovr > thr;
-}
+using namespace tfnms;
 
 __global__ void iota_kernel(int* v, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,12 +242,31 @@ int run_nms(const void* boxes, const void* scores, int64_t n, double thr, long l
     return TF_OK;
 }
 
+int g_nms_algo = 0;          // 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep
+constexpr int64_t SWEEP_MIN_N = 4096;
+
 }  // namespace
+
+namespace tfnms {
+size_t sweep_workspace_bytes(int64_t n, int elem_bytes);
+template <typename T>
+int run_nms_sweep(const void* boxes, const void* scores, int64_t n, double thr, long long* keep, long long* num_keep,
+                  void* ws, size_t ws_bytes, cudaStream_t st);
+}
+
+// test hook: 0 = automatic choice, 1 = force the blocked bit-matrix path, 2 = force the sort-and-sweep path
+TF_API int tf_nms_set_algorithm(int algo) {
+    TF_REQUIRE(algo >= 0 && algo <= 2, "tf_nms_set_algorithm: bad value");
+    g_nms_algo = algo;
+    return TF_OK;
+}
 
 TF_API int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes) {
     TF_REQUIRE(bytes && n >= 0 && n < (1ll << 31) && (elem_bytes == 8 || elem_bytes == 4), "tf_nms_workspace_bytes: bad args");
     if (n == 0) { *bytes = 256; return TF_OK; }
-    *bytes = elem_bytes == 8 ? Plan<double>(n).total : Plan<float>(n).total;
+    const size_t a = elem_bytes == 8 ? Plan<double>(n).total : Plan<float>(n).total;
+    const size_t b = tfnms::sweep_workspace_bytes(n, elem_bytes);
+    *bytes = a > b ? a : b;
     return TF_OK;
 }
 
@@ -290,6 +277,13 @@ TF_API int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_byt
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { TF_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st)); return TF_OK; }
     TF_REQUIRE(boxes && scores && keep && workspace, "tf_nms: null pointer");
+    const bool sweep = iou_threshold >= 0.0 && (g_nms_algo == 2 || (g_nms_algo == 0 && n >= SWEEP_MIN_N));
+    if (sweep) {
+        const int rc = elem_bytes == 8
+            ? tfnms::run_nms_sweep<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st)
+            : tfnms::run_nms_sweep<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
+        if (rc <= 0) return rc;          // > 0: conflict list too large for the workspace -> exact fallback below
+    }
     if (elem_bytes == 8)
         return run_nms<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
     return run_nms<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);

@@ -1,0 +1,193 @@
+// Near-linear exact greedy NMS for large N (same result as the sequential algorithm of torchvision.ops.nms,
+// the op the reference calls at /root/reference/tinyfaces/evaluation.py:84; bit-identical keep indices).
+//
+//   1. stable descending radix sort by score -> rank order (ties: lower original index first)
+//   2. sort-and-sweep along x: boxes are sorted by x1; box a only meets boxes whose x1 lies in [x1_a, x2_a], so
+//      the number of exact IoU tests is sum_a #{b : x1_a <= x1_b <= x2_a} instead of N^2/2
+//   3. every conflicting pair (IoU > thr, evaluated with the reference's operation order) becomes an edge
+//      earlier-rank -> later-rank, stored CSR by the later box (count pass, scan, fill pass)
+//   4. greedy resolution as a monotone fixed point: a box is KEPT once all its earlier conflicting boxes are
+//      REMOVED, REMOVED once any of them is KEPT.  Every round decides at least the first undecided box and in
+//      practice the dependency chains are short, so a few rounds settle all N boxes in parallel.
+//   5. order-preserving compaction of the kept ranks -> original indices, descending score.
+//
+// Greedy NMS is defined by exactly this recurrence (keep(j) <=> no kept i < j with IoU(i, j) > thr), so the
+// fixed point equals the sequential answer.  Used for thr >= 0 (a negative threshold makes every pair conflict)
+// when the edge list fits the workspace; otherwise tf_nms falls back to the blocked bit-matrix path.
+#include "tf_common.cuh"
+#include "tf_nms_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
+using namespace tfnms;
+
+namespace {
+
+enum : unsigned char { UNDECIDED = 0, KEPT = 1, REMOVED = 2 };
+
+__global__ void iota2_kernel(int* v, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = i;
+}
+template <typename T>
+__global__ void gather_rank_kernel(const T* __restrict__ boxes, const int* __restrict__ order, int n,
+                                   Box<T>* __restrict__ sb, T* __restrict__ area, T* __restrict__ xkey) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Box<T> b = reinterpret_cast<const Box<T>*>(boxes)[order[i]];
+    sb[i] = b;
+    area[i] = Arith<T>::mul(Arith<T>::sub(b.x2, b.x1), Arith<T>::sub(b.y2, b.y1));
+    xkey[i] = b.x1;
+}
+// FILL == 0: count conflicts per later box; FILL == 1: write the earlier box of each conflict into the CSR rows
+template <typename T, int FILL>
+__global__ void __launch_bounds__(128) sweep_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area,
+                                                    const int* __restrict__ xorder, const T* __restrict__ xsorted, int n,
+                                                    double thr, unsigned int* __restrict__ count,
+                                                    const unsigned int* __restrict__ offset, unsigned int* __restrict__ cursor,
+                                                    int* __restrict__ edges) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int a = xorder[p];
+    const Box<T> A = sb[a];
+    const T aa = area[a];
+    for (int q = p + 1; q < n && xsorted[q] <= A.x2; ++q) {
+        const int b = xorder[q];
+        const Box<T> Bx = sb[b];
+        if (!(Bx.y1 < A.y2 && A.y1 < Bx.y2)) continue;                     // no overlap in y (exact pre-test)
+        const int lo = a < b ? a : b, hi = a < b ? b : a;                 // lo has the higher score
+        const bool hit = a < b ? suppresses<T>(A, aa, Bx, area[b], thr, true) : suppresses<T>(Bx, area[b], A, aa, thr, true);
+        if (!hit) continue;
+        if (FILL) edges[offset[hi] + atomicAdd(&cursor[hi], 1u)] = lo;
+        else atomicAdd(&count[hi], 1u);
+    }
+}
+// one relaxation round; states only move UNDECIDED -> KEPT / REMOVED, so racing reads are harmless
+__global__ void resolve_kernel(const unsigned int* __restrict__ offset, const int* __restrict__ edges, int n,
+                               volatile unsigned char* state, int* __restrict__ undecided) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || state[j] != UNDECIDED) return;
+    bool all_removed = true;
+    for (unsigned int e = offset[j]; e < offset[j + 1]; ++e) {
+        const unsigned char s = state[edges[e]];
+        if (s == KEPT) { state[j] = REMOVED; return; }
+        if (s == UNDECIDED) all_removed = false;
+    }
+    if (all_removed) state[j] = KEPT;
+    else if (undecided) atomicAdd(undecided, 1);
+}
+__global__ void flags_kernel(const unsigned char* __restrict__ state, int n, unsigned char* __restrict__ flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) flags[j] = state[j] == KEPT ? 1 : 0;
+}
+__global__ void widen_kernel(const int* __restrict__ sel, const int* __restrict__ nsel, long long* __restrict__ keep,
+                             long long* __restrict__ num_keep, int n) {
+    const int k = *nsel;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) keep[i] = sel[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *num_keep = k;
+}
+
+template <typename T>
+struct SweepPlan {
+    size_t sort_bytes = 0, scan_bytes = 0, select_bytes = 0, total = 0;
+    size_t edge_cap = 0;
+    explicit SweepPlan(int64_t n) {
+        cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const T*)nullptr, (T*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n);
+        size_t s2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, s2, (const T*)nullptr, (T*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n);
+        sort_bytes = sort_bytes > s2 ? sort_bytes : s2;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr, (int)n + 1);
+        cub::DeviceSelect::Flagged(nullptr, select_bytes, (const int*)nullptr, (const unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
+        edge_cap = (size_t)n * 64 + (1u << 20);
+        if (edge_cap > 0xF0000000ull) edge_cap = 0xF0000000ull;
+        size_t a = 0;
+        auto add = [&](size_t b) { a = tf_align_up(a, 256) + b; };
+        add(4 * n); add(4 * n); add(sizeof(T) * n);                      // iota, order, sorted keys
+        add(sort_bytes); add(scan_bytes); add(select_bytes);
+        add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas by rank
+        add(sizeof(T) * n); add(sizeof(T) * n); add(4 * n);               // x keys, sorted x keys, x order
+        add(4 * (n + 1)); add(4 * (n + 1)); add(4 * n);                   // counts, offsets, cursors
+        add(4 * edge_cap);                                                // CSR edges
+        add(n); add(n); add(4 * n);                                       // state, flags, selected
+        add(256);
+        total = a + 256;
+    }
+};
+
+}  // namespace
+
+namespace tfnms {
+
+size_t sweep_workspace_bytes(int64_t n, int elem_bytes) {
+    return elem_bytes == 8 ? SweepPlan<double>(n).total : SweepPlan<float>(n).total;
+}
+
+// returns TF_OK, an error, or +1 when the edge list does not fit (caller falls back to the bit-matrix path)
+template <typename T>
+int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr, long long* keep, long long* num_keep,
+                  void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int n = (int)n64;
+    SweepPlan<T> plan(n);
+    if (ws_bytes < plan.total) { tf_set_error("tf_nms(sweep): workspace %zu < required %zu", ws_bytes, plan.total); return TF_ERR_WORKSPACE; }
+    TfArena ar(ws, ws_bytes);
+    int* iota = ar.take<int>(n);
+    int* order = ar.take<int>(n);
+    T* keys = ar.take<T>(n);
+    void* sort_tmp = ar.take<char>(plan.sort_bytes);
+    void* scan_tmp = ar.take<char>(plan.scan_bytes);
+    void* select_tmp = ar.take<char>(plan.select_bytes);
+    Box<T>* sb = ar.take<Box<T>>(n);
+    T* area = ar.take<T>(n);
+    T* xkey = ar.take<T>(n);
+    T* xsorted = ar.take<T>(n);
+    int* xorder = ar.take<int>(n);
+    unsigned int* count = ar.take<unsigned int>(n + 1);
+    unsigned int* offset = ar.take<unsigned int>(n + 1);
+    unsigned int* cursor = ar.take<unsigned int>(n);
+    int* edges = ar.take<int>(plan.edge_cap);
+    unsigned char* state = ar.take<unsigned char>(n);
+    unsigned char* flags = ar.take<unsigned char>(n);
+    int* selected = ar.take<int>(n);
+    int* scalars = ar.take<int>(16);                       // [0] undecided, [1] selected count
+    const int nb = (n + 255) / 256;
+
+    iota2_kernel<<<nb, 256, 0, st>>>(iota, n);
+    size_t sb_bytes = plan.sort_bytes;
+    TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(sort_tmp, sb_bytes, (const T*)scores, keys, (const int*)iota, order, n,
+                                                            0, (int)sizeof(T) * 8, st));
+    gather_rank_kernel<T><<<nb, 256, 0, st>>>((const T*)boxes, order, n, sb, area, xkey);
+    sb_bytes = plan.sort_bytes;
+    TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sb_bytes, (const T*)xkey, xsorted, (const int*)iota, xorder, n, 0,
+                                                  (int)sizeof(T) * 8, st));
+    TF_CHECK_CUDA(cudaMemsetAsync(count, 0, 4 * (size_t)(n + 1), st));
+    sweep_kernel<T, 0><<<(n + 127) / 128, 128, 0, st>>>(sb, area, xorder, xsorted, n, thr, count, nullptr, nullptr, nullptr);
+    size_t sc_bytes = plan.scan_bytes;
+    TF_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, sc_bytes, count, offset, n + 1, st));
+    unsigned int total_edges = 0;
+    TF_CHECK_CUDA(cudaMemcpyAsync(&total_edges, offset + n, 4, cudaMemcpyDeviceToHost, st));
+    TF_CHECK_CUDA(cudaStreamSynchronize(st));
+    if ((size_t)total_edges > plan.edge_cap) return 1;
+    TF_CHECK_CUDA(cudaMemsetAsync(cursor, 0, 4 * (size_t)n, st));
+    sweep_kernel<T, 1><<<(n + 127) / 128, 128, 0, st>>>(sb, area, xorder, xsorted, n, thr, nullptr, offset, cursor, edges);
+    TF_CHECK_CUDA(cudaMemsetAsync(state, 0, n, st));
+    for (int round = 0; round < n + 8;) {
+        TF_CHECK_CUDA(cudaMemsetAsync(scalars, 0, 4, st));
+        for (int k = 0; k < 4; ++k, ++round) resolve_kernel<<<nb, 256, 0, st>>>(offset, edges, n, state, k == 3 ? scalars : nullptr);
+        int undecided = 0;
+        TF_CHECK_CUDA(cudaMemcpyAsync(&undecided, scalars, 4, cudaMemcpyDeviceToHost, st));
+        TF_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (undecided == 0) break;
+    }
+    flags_kernel<<<nb, 256, 0, st>>>(state, n, flags);
+    size_t sel_bytes = plan.select_bytes;
+    TF_CHECK_CUDA(cub::DeviceSelect::Flagged(select_tmp, sel_bytes, (const int*)order, flags, selected, scalars + 1, n, st));
+    widen_kernel<<<nb < 1024 ? nb : 1024, 256, 0, st>>>(selected, scalars + 1, keep, num_keep, n);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+
+template int run_nms_sweep<double>(const void*, const void*, int64_t, double, long long*, long long*, void*, size_t, cudaStream_t);
+template int run_nms_sweep<float>(const void*, const void*, int64_t, double, long long*, long long*, void*, size_t, cudaStream_t);
+
+}  // namespace tfnms

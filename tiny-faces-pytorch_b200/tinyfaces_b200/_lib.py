@@ -18,6 +18,7 @@ _SIGS = {
     "tf_version": (c_i32, []),
     "tf_debug_set": (c_i32, [c_i32, c_i32]),
     "tf_gemm_error_flag": (c_i32, [ctypes.POINTER(c_i32)]),
+    "tf_nms_set_algorithm": (c_i32, [c_i32]),
     "tf_nms_workspace_bytes": (c_i32, [c_i64, c_i32, ctypes.POINTER(c_sz)]),
     "tf_nms": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "tf_decode_workspace_bytes": (c_i32, [c_i64, c_i64, c_i64, ctypes.POINTER(c_sz)]),
