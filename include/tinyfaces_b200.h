@@ -69,6 +69,14 @@ int tf_conv2d_nhwc_strided(const float* x, int B, int H, int W, int Cin, const f
 int tf_conv2d_wgrad_nhwc_strided(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
                                  int stride, float* dw_packed /* accumulated */, void* stream);
 
+/* ---- one image-pyramid level with the exact arithmetic of tinyfaces/evaluation.py:40-50 (to_pil_image, PIL bilinear
+ * resize, ToTensor, Normalize).  img: float32 [3,H,W] in [0,1]; the int32 tables hold Pillow's fixed-point resampling
+ * coefficients (bounds [out,2], taps [out,ksize]; NULL when that axis keeps its size); out: float32 [3,Ho,Wo]. */
+int tf_pyramid_workspace_bytes(int H, int W, int Wo, size_t* bytes_host);
+int tf_pyramid_level(const float* img, int H, int W, int Ho, int Wo, const int* bounds_h, const int* kk_h, int ksize_h,
+                     const int* bounds_v, const int* kk_v, int ksize_v, const float* mean_host, const float* std_host,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- whole-model executor: replaces DetectionModel.forward (tinyfaces/models/model.py:89-128) and the backward
  * autograd derives from it (tinyfaces/trainer.py:86).  params / grads: HOST arrays of tf_model_num_params()
  * device pointers in tf_model_param_name() order (reference state_dict names; OIHW weights, BN vectors).

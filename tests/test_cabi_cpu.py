@@ -81,3 +81,39 @@ def test_no_cpu_fallback():
     from tinyfaces_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.nms_device(torch.zeros(3, 4, dtype=torch.float64), torch.zeros(3, dtype=torch.float64), 0.3)
+
+
+def test_pil_resize_tables_are_bit_exact():
+    """The host-side restatement of Pillow's bilinear resampling (coefficient tables + two integer passes) that
+    feeds tf_pyramid_level matches the real PIL call the reference makes (evaluation.py:46-47) bit for bit."""
+    from PIL import Image
+    from torchvision import transforms
+    from tinyfaces_b200.pyramid import PRECISION_BITS, bilinear_coeffs, resized_size
+
+    def emulate(arr, size):
+        H, W, _ = arr.shape
+        Wo, Ho = resized_size(W, H, size)
+        a = arr.astype(np.int64)
+        if Wo != W:
+            b, k, _ = bilinear_coeffs(W, Wo)
+            out = np.zeros((H, Wo, 3), np.int64)
+            for xx in range(Wo):
+                x0, c = b[xx]
+                ss = (1 << (PRECISION_BITS - 1)) + (a[:, x0:x0 + c, :] * k[xx, :c][None, :, None]).sum(1)
+                out[:, xx, :] = np.clip(ss >> PRECISION_BITS, 0, 255)
+            a = out
+        if Ho != H:
+            b, k, _ = bilinear_coeffs(H, Ho)
+            out = np.zeros((Ho, a.shape[1], 3), np.int64)
+            for yy in range(Ho):
+                y0, c = b[yy]
+                ss = (1 << (PRECISION_BITS - 1)) + (a[y0:y0 + c] * k[yy, :c][:, None, None]).sum(0)
+                out[yy] = np.clip(ss >> PRECISION_BITS, 0, 255)
+            a = out
+        return a.astype(np.uint8)
+
+    r = np.random.RandomState(0)
+    for (H, W, size) in [(50, 64, 25), (50, 64, 100), (37, 53, 12), (64, 50, 200), (31, 31, 44), (40, 60, 40), (200, 216, 282)]:
+        arr = r.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        ref = np.asarray(transforms.functional.resize(Image.fromarray(arr), size))
+        assert np.array_equal(ref, emulate(arr, size)), (H, W, size)

@@ -86,6 +86,21 @@ def test_nms_shim_is_torchvision_compatible():
     assert nms(torch.zeros((0, 4), dtype=torch.float64), torch.zeros(0, dtype=torch.float64), 0.3).shape == (0,)
 
 
+@pytest.mark.parametrize("H,W,size", [(200, 216, 200), (200, 216, 282), (200, 216, 400), (200, 216, 50), (125, 93, 31),
+                                      (64, 80, 300)])
+def test_gpu_pyramid_level_is_bit_identical_to_pil_path(H, W, size):
+    """tf_pyramid_level == to_pil_image -> PIL resize -> ToTensor -> Normalize (evaluation.py:40-50), bit for bit."""
+    from torchvision import transforms
+    from tinyfaces_b200.pyramid import pyramid_level
+    img = torch.rand(3, H, W, generator=torch.Generator().manual_seed(H + W + size))
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean, std)])
+    ref = tf(transforms.functional.resize(transforms.functional.to_pil_image(img), size)).unsqueeze(0)
+    got = pyramid_level(img.cuda(), size, mean, std).cpu()
+    assert got.shape == ref.shape
+    assert torch.equal(got, ref)
+
+
 def _match_fraction(a, b, tol):
     """fraction of rows of b that have a row of a within tol (max-abs)"""
     if len(b) == 0:

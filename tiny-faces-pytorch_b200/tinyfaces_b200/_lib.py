@@ -40,6 +40,9 @@ _SIGS = {
     "tf_model_backward": (c_i32, [c_vp, c_vp, ctypes.POINTER(c_vp), c_vp]),
     "tf_model_get_tensor": (c_i32, [c_vp, ctypes.c_char_p, c_vp, c_i64, ctypes.POINTER(c_i32), c_vp]),
     "tf_model_upsample_offdiag": (c_i32, [c_vp, ctypes.POINTER(c_f32), c_vp]),
+    "tf_pyramid_workspace_bytes": (c_i32, [c_i32, c_i32, c_i32, ctypes.POINTER(c_sz)]),
+    "tf_pyramid_level": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32,
+                                 ctypes.POINTER(c_f32), ctypes.POINTER(c_f32), c_vp, c_vp, c_sz, c_vp]),
     "tf_conv2d_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "tf_conv2d_nhwc_strided": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "tf_conv2d_wgrad_nhwc_strided": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

@@ -12,6 +12,40 @@ from torchvision import transforms
 
 from . import ops
 from .models.utils import _bitmask, invalid_template_ids
+from .pyramid import pyramid_level
+
+
+def _normalize_params(img_transforms):
+    """(mean, std) if ``img_transforms`` is the reference's Compose([ToTensor(), Normalize(mean, std)])
+    (evaluate_model.py / detect_image.py), else None -> the PIL host path is used."""
+    ts = getattr(img_transforms, "transforms", None)
+    if ts is not None and len(ts) == 2 and isinstance(ts[0], transforms.ToTensor) and isinstance(ts[1], transforms.Normalize):
+        return [float(v) for v in ts[1].mean], [float(v) for v in ts[1].std]
+    return None
+
+
+class _Pyramid:
+    """Produces the per-scale network input exactly as evaluation.py:40-56 does.  With the standard transforms the
+    whole level (uint8 quantisation, PIL-exact bilinear resize, ToTensor, Normalize) is built on the GPU
+    (tf_pyramid_level); any other transform falls back to the reference's own PIL call sequence on the host."""
+
+    def __init__(self, img, img_transforms, device, gpu_pyramid=True):
+        self.device = device
+        self.tf = img_transforms
+        self.params = _normalize_params(img_transforms) if gpu_pyramid else None
+        if self.params is not None:
+            self.img = img.to(device=device, dtype=torch.float32).contiguous()
+            self.min_side = min(img.shape[1], img.shape[2])
+        else:
+            self.image = transforms.functional.to_pil_image(img)            # evaluation.py:40
+            self.min_side = np.min(self.image.size)
+
+    def level(self, scale):
+        size = int(self.min_side * scale)                                   # evaluation.py:46-47
+        if self.params is not None:
+            return pyramid_level(self.img, size, *self.params)
+        scaled = transforms.functional.resize(self.image, size)
+        return self.tf(scaled).unsqueeze(0).float().to(self.device, non_blocking=True)
 
 
 def nms(boxes, scores, iou_threshold):
@@ -44,18 +78,16 @@ def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True):
 
 
 def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3, scales=(-2, -1, 0, 1),
-                   device=None, return_scores=False):
+                   device=None, return_scores=False, gpu_pyramid=True):
     """evaluation.py:20-87.  img: CHW float tensor in [0,1]; scales are exponents of 2; returns ndarray [K,4] float64."""
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     model = model.to(device)
     model.eval()
     templates = np.asarray(templates, dtype=np.float64)
-    image = transforms.functional.to_pil_image(img)                 # evaluation.py:40
-    min_side = np.min(image.size)
+    pyr = _Pyramid(img, img_transforms, device, gpu_pyramid)
     all_boxes, all_scores = [], []
     for scale in [2 ** x for x in scales]:                          # evaluation.py:37,44
-        scaled = transforms.functional.resize(image, int(min_side * scale))
-        x = img_transforms(scaled).unsqueeze(0).float().to(device, non_blocking=True)
+        x = pyr.level(scale)
         with torch.no_grad():
             output = model(x)
         b, s = decode_level(output, templates, prob_thresh, rf, scale)
@@ -124,8 +156,7 @@ def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thres
     model = model.to(device)
     model.eval()
     templates = np.asarray(templates, dtype=np.float64)
-    image = transforms.functional.to_pil_image(img)
-    min_side = np.min(image.size)
+    pyr = _Pyramid(img, img_transforms, device)
     levels = [2 ** x for x in scales]
     # largest levels first onto distinct ranks (cost ~ 4^exponent): simple longest-processing-time packing
     order = sorted(range(len(levels)), key=lambda i: -levels[i])
@@ -139,8 +170,7 @@ def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thres
     for i, scale in enumerate(levels):
         if owner[i] != rank:
             continue
-        scaled = transforms.functional.resize(image, int(min_side * scale))
-        x = img_transforms(scaled).unsqueeze(0).float().to(device, non_blocking=True)
+        x = pyr.level(scale)
         with torch.no_grad():
             output = model(x)
         per_level[i] = decode_level(output, templates, prob_thresh, rf, scale)
