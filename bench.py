@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nms-n", type=int, default=100000)
+    ap.add_argument("--no-inference", action="store_true")
     ap.add_argument("--breakdown", default="", help="write a per-kernel time table of one step to this file")
     ap.add_argument("--profile-mode", action="store_true", help="only the timed steps (for runs under ncu)")
     args = ap.parse_args()
@@ -318,6 +319,14 @@ def main():
         line["nms"] = dict(n=n, kept=k, boxes_per_s=n / t_nms, ms=t_nms * 1e3, dtype="f64",
                            algorithmic_gbs=nms_bytes / t_nms / 1e9, hbm_frac=nms_bytes / t_nms / 1e9 / pk["hbm_gbs"],
                            note="pair-test (ALU) bound at this N, see DESIGN.md")
+
+        # ---- pyramid inference (BASELINE.json configs[2]) with the same (now partly trained) weights
+        if not args.no_inference:
+            try:
+                from tinyfaces_b200 import inference_bench
+                line["inference"] = inference_bench.run(model, base=1250, target_candidates=args.nms_n)
+            except Exception as ex:  # noqa: BLE001
+                line["inference"] = dict(error=str(ex)[:300])
 
         # ---- CPU baseline beside it (bounded sample)
         if world == 1 and not args.no_cpu_baseline:

@@ -5,13 +5,21 @@
 // and its autograd backward.  All tensors are [pixels, C] with C % 4 == 0; accesses are float4.
 #include "tf_common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
 constexpr int EW_THREADS = 256;
+// Grid cap of the grid-stride kernels (CTAs of 256 threads per SM).  Measured on B200: capping lower to leave room
+// for side-stream GEMM CTAs does not pay (50.1 ms/step at 32 vs 50.7 at 6).  TF_EW_BLOCKS_PER_SM overrides.
+inline int ew_blocks_per_sm() {
+    static int v = 0;
+    if (!v) { const char* e = getenv("TF_EW_BLOCKS_PER_SM"); v = e ? atoi(e) : 32; if (v < 1) v = 1; }
+    return v;
+}
 inline int ew_blocks(long long n, int per_thread = 1) {
     long long b = (n + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
-    return (int)std::min<long long>(std::max<long long>(b, 1), 148LL * 32);
+    return (int)std::min<long long>(std::max<long long>(b, 1), 148LL * ew_blocks_per_sm());
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -97,19 +105,20 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
     }
 }
 
-// sum the per-block partials of 32 channels with 8 lanes per channel (fp64), result valid for threadIdx.y == 0
+// sum the per-block partials of 32 channels with FIN_LANES lanes per channel (fp64), result valid for threadIdx.y == 0
+constexpr int FIN_LANES = 32;
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
-    __shared__ double sh[2][8][32];
+    __shared__ double sh[2][FIN_LANES][32];
     s = 0; q = 0;
     if (c < C)
-        for (int b = threadIdx.y; b < nblk; b += 8) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+        for (int b = threadIdx.y; b < nblk; b += FIN_LANES) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
     sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = q;
     __syncthreads();
     if (threadIdx.y == 0)
-        for (int l = 1; l < 8; ++l) { s += sh[0][l][threadIdx.x]; q += sh[1][l][threadIdx.x]; }
+        for (int l = 1; l < FIN_LANES; ++l) { s += sh[0][l][threadIdx.x]; q += sh[1][l][threadIdx.x]; }
 }
 // BN forward finalize (training): batch mean / biased var -> scale, shift, saved mean / rstd, running stats
-__global__ void __launch_bounds__(256) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(1024) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
@@ -144,7 +153,7 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
     shift[c] = beta[c] - run_mean[c] * sc;
 }
 // BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef /* [3][C]: gamma*rstd, mean(g), mean(g*xhat) */) {
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     coef[C + c] = (float)(s / (double)M);
     coef[2 * C + c] = (float)(q / (double)M);
 }
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
+__global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
                                        float* __restrict__ out) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s, q;
@@ -489,7 +498,7 @@ int bn_stats_train(const float* y, long long M, int C, const float* gamma, const
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_stats_train: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
+    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -497,7 +506,7 @@ int bn_stats_train(const float* y, long long M, int C, const float* gamma, const
 int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st) {
-    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
+    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -522,7 +531,7 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_backward: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, partial);
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
                                                                 gmask_out, mode);
@@ -533,7 +542,7 @@ int column_sum(const float* a, long long M, int C, int Cout, float* out, float* 
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "column_sum: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, nb, C, Cout, out);
+    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

@@ -1,0 +1,79 @@
+"""Timing helper for the pyramid-inference workload (BASELINE.json configs[2]): per-level GPU pyramid + forward +
+device decode, then one global NMS.  Used by bench.py and tools/bench_inference.py."""
+import json
+import os
+
+import numpy as np
+import torch
+from torchvision import transforms
+
+from . import ops
+from .evaluation import _Pyramid, decode_level
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+RF = {"size": [859, 859], "stride": [8, 8], "offset": [-1, -1]}          # wider_face.py:55
+FWD_GFLOP_1250 = {-2: 28.4, -1: 114.4, 0: 448.0, 1: 1773.3, 2: 7057.3}    # SURVEY.md section 8a (base 1250)
+
+
+def load_templates():
+    with open(os.path.join(_HERE, "templates.json")) as f:
+        return np.array(json.load(f), dtype=np.float64)
+
+
+def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nms_thresh=0.3, seed=1, reps=2):
+    """Returns a dict of per-stage device times (ms) for one synthetic base x base image."""
+    dev = next(model.parameters()).device
+    templates = load_templates()
+    img = torch.rand(3, base, base, generator=torch.Generator().manual_seed(seed))
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+    was_training = model.training
+    model.eval()
+    pyr = _Pyramid(img, tf, dev)
+    lv = [2 ** s for s in scales]
+    # threshold that yields ~target_candidates over all levels (the random-init net has no meaningful scores)
+    probs = []
+    with torch.no_grad():
+        for s in lv:
+            o = model(pyr.level(s))
+            pr = torch.sigmoid(o[:, :25])
+            pr[:, :, :, [0, 1, 2, 3] + list(range(12, 25))] = 0          # utils.py:44 column quirk
+            probs.append(pr.flatten())
+    allp = torch.cat(probs)
+    thr = float(torch.topk(allp, min(target_candidates, allp.numel() - 1)).values[-1])
+    del probs, allp
+    out = None
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        pyr_ms, fwd_ms, dec_ms, boxes, scores = [], [], [], [], []
+        with torch.no_grad():
+            for s in lv:
+                ev[0].record()
+                x = pyr.level(s)
+                ev[1].record()
+                o = model(x)
+                ev[2].record()
+                b, sc = decode_level(o, templates, thr, RF, s)
+                ev[3].record()
+                torch.cuda.synchronize()
+                pyr_ms.append(ev[0].elapsed_time(ev[1]))
+                fwd_ms.append(ev[1].elapsed_time(ev[2]))
+                dec_ms.append(ev[2].elapsed_time(ev[3]))
+                boxes.append(b)
+                scores.append(sc)
+        bx, sx = torch.cat(boxes), torch.cat(scores)
+        ev[0].record()
+        keep, cnt = ops.nms_device(bx, sx, nms_thresh)
+        ev[1].record()
+        torch.cuda.synchronize()
+        nms_ms = ev[0].elapsed_time(ev[1])
+        n, kept = int(bx.shape[0]), int(cnt.item())
+        out = dict(workload="BASELINE.json configs[2]: %d-scale pyramid of a %dx%d image (levels %s px) + dense NMS"
+                            % (len(lv), base, base, [int(base * s) for s in lv]),
+                   candidates=n, kept=kept, prob_thresh=thr, pyramid_ms=pyr_ms, forward_ms=fwd_ms, decode_ms=dec_ms,
+                   nms_ms=nms_ms, total_gpu_ms=sum(pyr_ms) + sum(fwd_ms) + sum(dec_ms) + nms_ms,
+                   nms_boxes_per_s=n / (nms_ms / 1e3) if nms_ms > 0 else None)
+        if base == 1250:
+            out["forward_tflops_per_level"] = [FWD_GFLOP_1250[s] / ms for s, ms in zip(scales, fwd_ms) if s in FWD_GFLOP_1250]
+    if was_training:
+        model.train()
+    return out

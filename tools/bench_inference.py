@@ -1,99 +1,27 @@
-"""Pyramid inference benchmark (BASELINE.json configs[2]): base 1250x1250 image, scales (-2..2) -> 312..5000 px,
-forward + device decode + global NMS on one GPU.  Prints one JSON line with per-stage times."""
+"""Pyramid inference benchmark (BASELINE.json configs[2]).  python tools/bench_inference.py [target_N] [base]"""
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tiny-faces-pytorch_b200"))
-sys.path.insert(0, ROOT)
-import numpy as np
 import torch
-from torchvision import transforms
 
-from tinyfaces_b200 import ops
-from tinyfaces_b200.evaluation import decode_level
+from tinyfaces_b200 import inference_bench
 from tinyfaces_b200.models.model import DetectionModel
 
-TEMPLATES = np.array(json.load(open(os.path.join(ROOT, "tests", "golden", "templates.json"))), dtype=np.float64)
-RF = {"size": [859, 859], "stride": [8, 8], "offset": [-1, -1]}
-
-
-def main():
+if __name__ == "__main__":
     target_n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
     base = int(sys.argv[2]) if len(sys.argv) > 2 else 1250
-    scales = (-2, -1, 0, 1, 2)
-    dev = torch.device("cuda:0")
     torch.manual_seed(0)
     m = DetectionModel(pretrained_weights=None, num_templates=25)
-    for mod in m.modules():
-        if isinstance(mod, torch.nn.Bottleneck if hasattr(torch.nn, "Bottleneck") else ()):
-            pass
     for name, p in m.named_parameters():
         if name.endswith("bn3.weight"):
             p.data.fill_(0.25)
-    m = m.to(dev)
-    # calibrate BN running statistics (momentum 1.0 = take the batch statistics), otherwise eval logits overflow
+    m = m.cuda()
     m.train()
-    m.bn_momentum = 1.0
+    m.bn_momentum = 1.0                      # calibrate running statistics, else eval logits overflow
     with torch.no_grad():
-        m(torch.randn(2, 3, 512, 512, device=dev))
+        m(torch.randn(2, 3, 512, 512, device="cuda"))
     m.bn_momentum = 0.1
-    m.eval()
-    img = torch.rand(3, base, base, generator=torch.Generator().manual_seed(1))
-    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
-    image = transforms.functional.to_pil_image(img)
-    levels = []
-    t0 = time.perf_counter()
-    for s in [2 ** x for x in scales]:
-        levels.append((s, tf(transforms.functional.resize(image, int(base * s))).unsqueeze(0).float().pin_memory()))
-    t_pyr = time.perf_counter() - t0
-    # pick the threshold that yields ~target_n candidates
-    probs = []
-    with torch.no_grad():
-        for s, x in levels:
-            o = m(x.to(dev))
-            pr = torch.sigmoid(o[:, :25])
-            pr[:, :, :, [0, 1, 2, 3] + list(range(12, 25))] = 0      # the shipped column quirk
-            probs.append(pr.flatten())
-    allp = torch.cat(probs)
-    k = min(target_n, allp.numel() - 1)
-    thr = float(torch.topk(allp, k).values[-1])
-    del probs, allp
-
-    def run():
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        boxes, scores, fwd_ms, dec_ms = [], [], [], []
-        with torch.no_grad():
-            for s, x in levels:
-                ev[0].record()
-                o = m(x.to(dev, non_blocking=True))
-                ev[1].record()
-                b, sc = decode_level(o, TEMPLATES, thr, RF, s)
-                ev[2].record()
-                torch.cuda.synchronize()
-                fwd_ms.append(ev[0].elapsed_time(ev[1]))
-                dec_ms.append(ev[1].elapsed_time(ev[2]))
-                boxes.append(b)
-                scores.append(sc)
-        bx, sx = torch.cat(boxes), torch.cat(scores)
-        ev[0].record()
-        keep, cnt = ops.nms_device(bx, sx, 0.3)
-        ev[1].record()
-        torch.cuda.synchronize()
-        return fwd_ms, dec_ms, ev[0].elapsed_time(ev[1]), bx.shape[0], int(cnt.item())
-
-    run()
-    fwd_ms, dec_ms, nms_ms, n, kept = run()
-    gflop = [28.4, 114.4, 448.0, 1773.3, 7057.3] if base == 1250 else None
-    out = dict(workload="BASELINE.json configs[2]: 5-scale pyramid, base %d, + dense NMS" % base, candidates=n, kept=kept,
-               prob_thresh=thr, pyramid_cpu_ms=t_pyr * 1e3, forward_ms=fwd_ms, decode_ms=dec_ms, nms_ms=nms_ms,
-               total_gpu_ms=sum(fwd_ms) + sum(dec_ms) + nms_ms, nms_boxes_per_s=n / (nms_ms / 1e3))
-    if gflop:
-        out["forward_tflops_per_level"] = [g / ms for g, ms in zip(gflop, fwd_ms)]
-    print(json.dumps(out))
-
-
-if __name__ == "__main__":
-    main()
+    print(json.dumps(inference_bench.run(m, base=base, target_candidates=target_n)))
