@@ -298,9 +298,18 @@ def main():
         t_launch = e0.elapsed_time(e1) / reps / 1000.0
         flops = 2.0 * Bc * Hc * Wc * C * C * 9
         ach = flops / t_launch / 1e12
+        traffic, pipe = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                rec = json.load(f)["conv_gemm_kernel<256> 3x3 256->256 M=38400"]
+            traffic, pipe = rec["dram_read_bytes"] + rec["dram_write_bytes"], rec["tensor_pipe_active_pct"]
+        except Exception:  # noqa: BLE001
+            pass
         line["roofline"] = dict(bound="tensor", kernel="conv_gemm_kernel<256> (3x3 256->256, M=%d)" % (Bc * Hc * Wc),
                                 achieved=ach, peak=pk["tf32_burst"], unit="TFLOP/s", frac=ach / pk["tf32_burst"],
-                                traffic=None, peak_source=pk["source"], us_per_launch=t_launch * 1e6)
+                                traffic=traffic, traffic_source="profiles/roofline_traffic.json (ncu --set full)",
+                                ncu_tensor_pipe_active_pct=pipe, algorithmic_flops_per_launch=flops,
+                                peak_source=pk["source"], us_per_launch=t_launch * 1e6)
 
         # ---- NMS boxes/s (the second half of BASELINE.json's metric), N random boxes, float64
         bx, sc = synthetic.boxes(args.nms_n, seed=0)

@@ -4,6 +4,7 @@
 // of /root/reference/tinyfaces/models/model.py:89-128 (torchvision Bottleneck.forward, resnet.py:143-163)
 // and its autograd backward.  All tensors are [pixels, C] with C % 4 == 0; accesses are float4.
 #include "tf_common.cuh"
+#include "tf_elementwise.h"
 #include <algorithm>
 #include <cstdlib>
 
@@ -394,6 +395,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int O_src, int I
         else dst[t] = v;
     }
 }
+// all weight tensors of one pass in a single launch: element t belongs to the job whose [begin, next begin) holds it
+__global__ void pack_weights_batched_kernel(const tfe::PackJob* __restrict__ jobs, int njobs, long long total, int mode) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].begin <= t) lo = mid; else hi = mid - 1; }
+        const tfe::PackJob j = jobs[lo];
+        const long long u = t - j.begin;
+        const int i = (int)(u % j.I_pad), tp = (int)((u / j.I_pad) % j.taps), o = (int)(u / ((long long)j.I_pad * j.taps));
+        float v = 0.f;
+        if (!j.transpose) { if (o < j.O_src && i < j.I_src) v = j.src[((long long)o * j.I_src + i) * j.taps + tp]; }
+        else              { if (i < j.O_src && o < j.I_src) v = j.src[((long long)i * j.I_src + o) * j.taps + (j.taps - 1 - tp)]; }
+        if (mode == 1) j.dst[u] = tf_round_tf32(v);
+        else if (mode == 2) { const float h = hi_part(v); j.dst[u] = h; j.dst_lo[u] = v - h; }
+        else j.dst[u] = v;
+    }
+}
 // OIHW gradient from the packed [O_pad][taps][I_pad] wgrad output
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int O, int I, int taps, int I_pad,
                                     float* __restrict__ dw) {
@@ -481,8 +498,7 @@ __global__ void extract_upsample_diag_kernel(const float* __restrict__ w, int Cn
 }  // namespace
 
 // ================================================================================================ host API
-// (internal C++ interface used by tf_model.cu; the unit-testable subset is also exported through the C-ABI)
-#include "tf_elementwise.h"
+// (internal C++ interface used by tf_model.cu)
 
 namespace tfe {
 
@@ -583,6 +599,11 @@ int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C
 int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, int O_pad, int I_pad, float* dst,
                 float* dst_lo, int mode, cudaStream_t st) {
     pack_weight_kernel<<<ew_blocks((long long)O_pad * taps * I_pad), EW_THREADS, 0, st>>>(w, O_src, I_src, taps, transpose, O_pad, I_pad, dst, dst_lo, mode);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int pack_weights_batched(const PackJob* jobs_device, int njobs, long long total, int mode, cudaStream_t st) {
+    pack_weights_batched_kernel<<<ew_blocks(total), EW_THREADS, 0, st>>>(jobs_device, njobs, total, mode);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

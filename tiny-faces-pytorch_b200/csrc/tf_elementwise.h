@@ -31,6 +31,12 @@ int subsample2(const float* x, const float* x_lo, int B, int H, int W, int C, fl
 int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
 int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, int O_pad, int I_pad, float* dst,
                 float* dst_lo, int mode, cudaStream_t st);
+struct PackJob {                              // one weight tensor of a batched packing launch
+    const float* src; float* dst; float* dst_lo;
+    int O_src, I_src, taps, transpose, O_pad, I_pad;
+    long long begin;                          // first global element index of this job
+};
+int pack_weights_batched(const PackJob* jobs_device, int njobs, long long total, int mode, cudaStream_t st);
 int unpack_wgrad(const float* dwp, int O, int I, int taps, int I_pad, float* dw, cudaStream_t st);
 int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, int H3, int W3, int H4, int W4, int Cn,
                      int Cp, float* out_nchw, cudaStream_t st);

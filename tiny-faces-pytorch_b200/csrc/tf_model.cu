@@ -15,7 +15,9 @@
 #include "tf_conv_gemm.h"
 #include "tf_elementwise.h"
 #include <algorithm>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -131,7 +133,37 @@ struct Model {
     float* PW(int i) const { return reinterpret_cast<float*>(const_cast<void*>(params[i])); }
 
     // ------------------------------------------------------------------------------------------ forward pieces
+    // Weight packing is batched: prepack_begin/prepack_add/prepack_flush re-layout every weight of a pass in ONE
+    // launch; pack() then only looks the result up (key = parameter index, transposed?).
+    std::map<std::pair<int, int>, std::pair<float*, float*>> packed;
+    std::vector<tfe::PackJob> jobs;
+    long long jobs_total = 0;
+    void prepack_add(const ConvP& c, int O_pad, int I_pad, int transpose) {
+        const int taps = c.k * c.k;
+        const size_t n = (size_t)O_pad * taps * I_pad;
+        float* wp = ar.f(n);
+        float* wp_lo = mode == 2 ? ar.f(n) : nullptr;
+        packed[{c.w, transpose}] = {wp, wp_lo};
+        tfe::PackJob j;
+        j.src = ar.dry ? nullptr : P(c.w); j.dst = wp; j.dst_lo = wp_lo;
+        j.O_src = c.cout; j.I_src = c.cin; j.taps = taps; j.transpose = transpose; j.O_pad = O_pad; j.I_pad = I_pad;
+        j.begin = jobs_total;
+        jobs_total += (long long)n;
+        jobs.push_back(j);
+    }
+    int prepack_flush(cudaStream_t st) {
+        const size_t bytes = jobs.size() * sizeof(tfe::PackJob);
+        tfe::PackJob* dev = reinterpret_cast<tfe::PackJob*>(ar.f((bytes + 3) / 4 + 16));
+        if (!ar.dry && !jobs.empty()) {
+            TF_CHECK_CUDA(cudaMemcpyAsync(dev, jobs.data(), bytes, cudaMemcpyHostToDevice, st));
+            RC(tfe::pack_weights_batched(dev, (int)jobs.size(), jobs_total, mode, st));
+        }
+        jobs.clear(); jobs_total = 0;
+        return TF_OK;
+    }
     int pack(const ConvP& c, int O_pad, int I_pad, int transpose, float** wp, float** wp_lo, cudaStream_t st) {
+        auto it = packed.find({c.w, transpose});
+        if (it != packed.end()) { *wp = it->second.first; *wp_lo = it->second.second; return TF_OK; }
         const int taps = c.k * c.k;
         const size_t n = (size_t)O_pad * taps * I_pad;
         *wp = ar.f(n);
@@ -251,6 +283,20 @@ struct Model {
         coef = ar.f(3 * 1024);
         dwtmp = ar.f((size_t)1024 * 1024 + 4096);
         offdiag = ar.f(64);
+        {   // every fprop weight of this pass, one launch
+            packed.clear(); jobs.clear(); jobs_total = 0;
+            ConvP c = stem; c.cin = 147; c.k = 1;
+            prepack_add(c, 64, 160, 0);
+            for (const BlockP& bp : blocks) {
+                prepack_add(bp.c1, bp.c1.cout, bp.c1.cin, 0); prepack_add(bp.c2, bp.c2.cout, bp.c2.cin, 0);
+                prepack_add(bp.c3, bp.c3.cout, bp.c3.cin, 0);
+                if (bp.has_ds) prepack_add(bp.cd, bp.cd.cout, bp.cd.cin, 0);
+            }
+            ConvP h3; h3.w = s3_w; h3.cin = 512; h3.cout = Cn; h3.k = 1;
+            ConvP h4; h4.w = s4_w; h4.cin = 1024; h4.cout = Cn; h4.k = 1;
+            prepack_add(h3, Cp, 512, 0); prepack_add(h4, Cp, 1024, 0);
+            RC(prepack_flush(st));
+        }
         // ---- stem: im2col + GEMM (K = 147 padded to 160), BN, ReLU, max-pool
         const long long M2 = (long long)B * H2 * W2;
         col = ar.f((size_t)M2 * 160);
@@ -455,6 +501,18 @@ struct Model {
         Unit h3; h3.c.w = s3_w; h3.c.cin = 512; h3.c.cout = Cp; h3.c.k = 1; h3.x = res3; h3.x_lo = nullptr; h3.B = B; h3.H = H3; h3.W = W3; h3.Ho = H3; h3.Wo = W3;
         Unit h4 = h3; h4.c.w = s4_w; h4.c.cin = 1024; h4.x = res4; h4.H = H4; h4.W = W4; h4.Ho = H4; h4.Wo = W4;
         float* dres4 = ar.f((size_t)M4 * 1024);
+        {   // every dgrad (transposed, tap-flipped) weight of this pass, one launch
+            jobs.clear(); jobs_total = 0;
+            for (const BlockP& bp : blocks) {
+                prepack_add(bp.c1, bp.c1.cin, bp.c1.cout, 1); prepack_add(bp.c2, bp.c2.cin, bp.c2.cout, 1);
+                prepack_add(bp.c3, bp.c3.cin, bp.c3.cout, 1);
+                if (bp.has_ds) prepack_add(bp.cd, bp.cd.cin, bp.cd.cout, 1);
+            }
+            ConvP t3; t3.w = s3_w; t3.cin = 512; t3.cout = Cn; t3.k = 1;
+            ConvP t4; t4.w = s4_w; t4.cin = 1024; t4.cout = Cn; t4.k = 1;
+            prepack_add(t3, 512, Cp, 1); prepack_add(t4, 1024, Cp, 1);
+            RC(prepack_flush(st));
+        }
         // input gradients ping-pong between two buffers; one scratch region is reused by every block (single stream)
         size_t mx = 0;
         for (const BlockS& s : bs) mx = std::max(mx, (size_t)s.B * s.H * s.W * s.u1.c.cin);
