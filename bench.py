@@ -329,11 +329,13 @@ def main():
                            algorithmic_gbs=nms_bytes / t_nms / 1e9, hbm_frac=nms_bytes / t_nms / 1e9 / pk["hbm_gbs"],
                            note="pair-test (ALU) bound at this N, see DESIGN.md")
 
-        # ---- pyramid inference (BASELINE.json configs[2]) with the same (now partly trained) weights
+        # ---- pyramid inference (BASELINE.json configs[2])
         if not args.no_inference:
             try:
                 from tinyfaces_b200 import inference_bench
-                line["inference"] = inference_bench.run(model, base=1250, target_candidates=args.nms_n)
+                imodel = inference_bench.make_calibrated_model(dev)      # fresh weights with calibrated BN statistics
+                line["inference"] = inference_bench.run(imodel, base=1250, target_candidates=args.nms_n)
+                del imodel
             except Exception as ex:  # noqa: BLE001
                 line["inference"] = dict(error=str(ex)[:300])
 

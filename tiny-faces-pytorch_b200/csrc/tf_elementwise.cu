@@ -153,6 +153,18 @@ __global__ void bn_finalize_eval_kernel(int C, const float* __restrict__ gamma, 
     scale[c] = sc;
     shift[c] = beta[c] - run_mean[c] * sc;
 }
+// every eval-mode BN of the network in one launch
+__global__ void bn_eval_batched_kernel(const tfe::BnEvalJob* __restrict__ jobs, int njobs, int total, float eps) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].begin <= t) lo = mid; else hi = mid - 1; }
+    const tfe::BnEvalJob j = jobs[lo];
+    const int c = t - j.begin;
+    const float sc = j.gamma[c] / sqrtf(j.run_var[c] + eps);
+    j.scale[c] = sc;
+    j.shift[c] = j.beta[c] - j.run_mean[c] * sc;
+}
 // BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
@@ -530,6 +542,11 @@ int bn_finalize_train(const float* partial, int nblk, long long M, int C, const 
 int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
                         float eps, float* scale, float* shift, cudaStream_t st) {
     bn_finalize_eval_kernel<<<(C + 127) / 128, 128, 0, st>>>(C, gamma, beta, run_mean, run_var, eps, scale, shift);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int bn_scale_shift_eval_batched(const BnEvalJob* jobs_device, int njobs, int total_channels, float eps, cudaStream_t st) {
+    bn_eval_batched_kernel<<<(total_channels + 255) / 256, 256, 0, st>>>(jobs_device, njobs, total_channels, eps);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

@@ -14,6 +14,8 @@ int bn_finalize_train(const float* partial, int nblk, long long M, int C, const 
                       float* save_rstd, cudaStream_t st);
 int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
                         float eps, float* scale, float* shift, cudaStream_t st);
+struct BnEvalJob { const float *gamma, *beta, *run_mean, *run_var; float *scale, *shift; int begin; };
+int bn_scale_shift_eval_batched(const BnEvalJob* jobs_device, int njobs, int total_channels, float eps, cudaStream_t st);
 int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
              const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode,
              unsigned int* mask_out /* optional 1-bit ReLU mask, (M*C+31)/32 words */, cudaStream_t st);

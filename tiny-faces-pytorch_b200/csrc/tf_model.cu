@@ -76,6 +76,7 @@ struct Model {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_region[2] = {nullptr, nullptr};
     size_t bwd_region_bytes = 0;
+    int plan_B = 0, plan_H = 0, plan_W = 0, plan_training = -1, plan_mode = 0; size_t plan_need = 0;   // cached dry run
     bool side_enabled = true;
     int ensure_side() {
         if (!side_enabled || side) return TF_OK;
@@ -208,7 +209,35 @@ struct Model {
         u.scale = ar.f(C); u.shift = ar.f(C); u.mean = ar.f(C); u.rstd = ar.f(C);
         return TF_OK;
     }
+    // eval-mode scale/shift of every BN are computed by ONE launch at the start of the forward (prepare_eval_all)
+    std::map<int, std::pair<float*, float*>> eval_ss;
+    int prepare_eval_all(cudaStream_t st) {
+        eval_ss.clear();
+        std::vector<tfe::BnEvalJob> ej;
+        int total = 0;
+        auto add = [&](const BnP& b) {
+            float* sc = ar.f(b.C); float* sh = ar.f(b.C);
+            eval_ss[b.gamma] = {sc, sh};
+            tfe::BnEvalJob j;
+            j.gamma = ar.dry ? nullptr : P(b.gamma); j.beta = ar.dry ? nullptr : P(b.beta);
+            j.run_mean = ar.dry ? nullptr : P(b.rm); j.run_var = ar.dry ? nullptr : P(b.rv);
+            j.scale = sc; j.shift = sh; j.begin = total;
+            total += b.C;
+            ej.push_back(j);
+        };
+        add(stem_bn);
+        for (const BlockP& bp : blocks) { add(bp.b1); add(bp.b2); add(bp.b3); if (bp.has_ds) add(bp.bd); }
+        const size_t bytes = ej.size() * sizeof(tfe::BnEvalJob);
+        tfe::BnEvalJob* dev = reinterpret_cast<tfe::BnEvalJob*>(ar.f((bytes + 3) / 4 + 16));
+        if (!ar.dry) {
+            TF_CHECK_CUDA(cudaMemcpyAsync(dev, ej.data(), bytes, cudaMemcpyHostToDevice, st));
+            RC(tfe::bn_scale_shift_eval_batched(dev, (int)ej.size(), total, eps, st));
+        }
+        return TF_OK;
+    }
     int bn_prepare_eval(Unit& u, cudaStream_t st) {
+        auto it = eval_ss.find(u.bn.gamma);
+        if (it != eval_ss.end()) { u.scale = it->second.first; u.shift = it->second.second; u.mean = nullptr; u.rstd = nullptr; return TF_OK; }
         RC(alloc_bn(u));
         if (!ar.dry) RC(tfe::bn_scale_shift_eval(u.bn.C, P(u.bn.gamma), P(u.bn.beta), P(u.bn.rm), P(u.bn.rv), eps, u.scale, u.shift, st));
         return TF_OK;
@@ -297,6 +326,7 @@ struct Model {
             prepack_add(h3, Cp, 512, 0); prepack_add(h4, Cp, 1024, 0);
             RC(prepack_flush(st));
         }
+        if (!training) RC(prepare_eval_all(st)); else eval_ss.clear();
         // ---- stem: im2col + GEMM (K = 147 padded to 160), BN, ReLU, max-pool
         const long long M2 = (long long)B * H2 * W2;
         col = ar.f((size_t)M2 * 160);
@@ -603,6 +633,7 @@ TF_API int tf_model_output_shape(void* handle, int H, int W, int* H3, int* W3) {
 TF_API int tf_model_workspace_bytes(void* handle, int B, int H, int W, int training, int mode, size_t* bytes) {
     TF_REQUIRE(handle && bytes && B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_workspace_bytes: bad args");
     Model* m = reinterpret_cast<Model*>(handle);
+    m->plan_training = -1;                       // any explicit query invalidates the cached plan of tf_model_forward
     m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode;
     m->ar = Arena(); m->ar.dry = true; m->ar.base = nullptr;
     RC(m->forward(nullptr, nullptr, nullptr));
@@ -619,7 +650,13 @@ TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, c
     TF_REQUIRE(B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_forward: bad shape/mode");
     Model* m = reinterpret_cast<Model*>(handle);
     size_t need;
-    RC(tf_model_workspace_bytes(handle, B, H, W, training, mode, &need));
+    if (m->plan_B == B && m->plan_H == H && m->plan_W == W && m->plan_training == training && m->plan_mode == mode) {
+        need = m->plan_need;                     // same shape as the last call: the dry-run plan is still valid
+    } else {
+        RC(tf_model_workspace_bytes(handle, B, H, W, training, mode, &need));
+        m->plan_B = B; m->plan_H = H; m->plan_W = W; m->plan_training = training; m->plan_mode = mode; m->plan_need = need;
+    }
+    m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode;
     if (workspace_bytes < need) { tf_set_error("tf_model_forward: workspace %zu < required %zu", workspace_bytes, need); return TF_ERR_WORKSPACE; }
     m->params.assign(params, params + m->names.size()); m->momentum = bn_momentum;
     m->ar = Arena(); m->ar.dry = false; m->ar.base = reinterpret_cast<char*>(workspace); m->ar.cap = workspace_bytes;

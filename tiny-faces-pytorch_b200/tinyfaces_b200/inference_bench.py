@@ -20,6 +20,25 @@ def load_templates():
         return np.array(json.load(f), dtype=np.float64)
 
 
+def make_calibrated_model(device, seed=0):
+    """Random-init detector whose eval-mode logits are finite: bn3 gamma = 0.25 and BN running
+    statistics taken from one training-mode pass (momentum 1.0) over a random batch."""
+    from .models.model import DetectionModel
+    torch.manual_seed(seed)
+    m = DetectionModel(pretrained_weights=None, num_templates=25)
+    for name, p in m.named_parameters():
+        if name.endswith("bn3.weight"):
+            p.data.fill_(0.25)
+    m = m.to(device)
+    m.train()
+    m.bn_momentum = 1.0
+    with torch.no_grad():
+        m(torch.randn(2, 3, 512, 512, device=device))
+    m.bn_momentum = 0.1
+    m.eval()
+    return m
+
+
 def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nms_thresh=0.3, seed=1, reps=2):
     """Returns a dict of per-stage device times (ms) for one synthetic base x base image."""
     dev = next(model.parameters()).device

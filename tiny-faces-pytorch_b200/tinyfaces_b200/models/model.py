@@ -29,6 +29,7 @@ class _Executor:
         n = lib().tf_model_num_params(h)
         self.names = [lib().tf_model_param_name(h, i).decode() for i in range(n)]
         self.workspace = None
+        self._sizes = {}
 
     def __del__(self):
         try:
@@ -37,12 +38,16 @@ class _Executor:
             pass
 
     def ensure_workspace(self, device, B, H, W, training, mode):
-        sz = ctypes.c_size_t()
-        check(lib().tf_model_workspace_bytes(self.handle, B, H, W, int(training), mode, ctypes.byref(sz)),
-              "tf_model_workspace_bytes")
-        if self.workspace is None or self.workspace.numel() < sz.value or self.workspace.device != device:
+        key = (B, H, W, bool(training), mode)
+        need = self._sizes.get(key)
+        if need is None:
+            sz = ctypes.c_size_t()
+            check(lib().tf_model_workspace_bytes(self.handle, B, H, W, int(training), mode, ctypes.byref(sz)),
+                  "tf_model_workspace_bytes")
+            need = self._sizes[key] = sz.value
+        if self.workspace is None or self.workspace.numel() < need or self.workspace.device != device:
             self.workspace = None
-            self.workspace = torch.empty(sz.value + 4096, dtype=torch.uint8, device=device)
+            self.workspace = torch.empty(need + 4096, dtype=torch.uint8, device=device)
         return self.workspace
 
 
@@ -58,10 +63,12 @@ class _TrunkFunction(torch.autograd.Function):
         mode = PRECISION[module.precision]
         training = bool(module.training)
         ws = ex.ensure_workspace(x.device, B, H, W, training, mode)
-        table = module._tensor_table()
-        for t in table:
-            if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
-                raise RuntimeError("DetectionModel parameters must be contiguous float32 tensors on the input's device")
+        table = module._tables()[0]
+        if module.__dict__.get("_checked_for") != (x.device, id(table)):
+            for t in table:
+                if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError("DetectionModel parameters must be contiguous float32 tensors on the input's device")
+            module.__dict__["_checked_for"] = (x.device, id(table))
         ptrs = (ctypes.c_void_p * len(table))(*[t.data_ptr() for t in table])
         h3, w3 = ctypes.c_int(), ctypes.c_int()
         check(lib().tf_model_output_shape(ex.handle, H, W, ctypes.byref(h3), ctypes.byref(w3)), "tf_model_output_shape")
@@ -69,11 +76,9 @@ class _TrunkFunction(torch.autograd.Function):
         check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, float(module.bn_momentum), out.data_ptr(),
                                      ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
         if training:
-            for m in module.modules():
-                if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None:
-                    m.num_batches_tracked += 1
+            for b in module._bn_counters():
+                b += 1
         ctx.module = module
-        ctx.table = table
         return out
 
     @staticmethod
@@ -81,7 +86,7 @@ class _TrunkFunction(torch.autograd.Function):
         module = ctx.module
         ex = module._executor
         grad_out = grad_out.contiguous()
-        named = dict(module.named_parameters())
+        named = dict(zip(module._tables()[2], module._tables()[1]))
         grads = {}
         ptrs = (ctypes.c_void_p * len(ex.names))()
         for i, name in enumerate(ex.names):
@@ -145,19 +150,39 @@ class DetectionModel(nn.Module):
                 {'params': self.score_res4.parameters(), 'lr': 1 * lr},
                 {'params': self.score4_upsample.parameters(), 'lr': 0}]
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() may replace parameter storage: drop the cached tensor tables
+        self.__dict__.pop("_cache", None)
+        self.__dict__.pop("_bn_cnt", None)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _bn_counters(self):
+        c = self.__dict__.get("_bn_cnt")
+        if c is None:
+            c = [m.num_batches_tracked for m in self.modules()
+                 if isinstance(m, nn.BatchNorm2d) and m.num_batches_tracked is not None]
+            self.__dict__["_bn_cnt"] = c
+        return c
+
+    def _tables(self):
+        """(parameter/buffer tensors in executor order, autograd parameter list) -- cached, the walk over
+        named_parameters() costs more host time than a small pyramid level takes on the GPU."""
+        c = self.__dict__.get("_cache")
+        if c is None:
+            named = dict(self.named_parameters())
+            params = [named[n] for n in self._executor.names if n in named]
+            named.update(dict(self.named_buffers()))
+            c = ([named[n] for n in self._executor.names], params,
+                 [n for n in self._executor.names if n in dict(self.named_parameters())])
+            self.__dict__["_cache"] = c
+        return c
+
     def _tensor_table(self):
-        named = dict(self.named_parameters())
-        named.update(dict(self.named_buffers()))
-        return [named[n].data for n in self._executor.names]
+        return [t.data for t in self._tables()[0]]
 
     @property
     def _autograd_names(self):
-        names = getattr(self, "_ag_names", None)
-        if names is None:
-            params = dict(self.named_parameters())
-            names = [n for n in self._executor.names if n in params]
-            object.__setattr__(self, "_ag_names", names)
-        return names
+        return self._tables()[2]
 
     def debug_tensor(self, name):
         """Test hook: NHWC copy of an internal activation of the last forward (see tf_model_get_tensor)."""
@@ -171,9 +196,7 @@ class DetectionModel(nn.Module):
         return t
 
     def forward(self, x):
-        params = dict(self.named_parameters())
-        tensors = [params[n] for n in self._autograd_names]
-        out = _TrunkFunction.apply(x, self, *tensors)
+        out = _TrunkFunction.apply(x, self, *self._tables()[1])
         if not self._checked_upsample:
             v = ctypes.c_float()
             check(lib().tf_model_upsample_offdiag(self._executor.handle, ctypes.byref(v), stream_ptr(x.device)),
