@@ -86,6 +86,15 @@ def test_nms_large_n_property():
         assert np.any((ov > 0.3) & (scores[keep] >= scores[j]))
 
 
+def test_nms_negative_threshold_and_ties_small():
+    """thr < 0: every later box is suppressed (ovr = 0 > thr), as in the reference; handled by the bit-matrix path."""
+    from oracle import nms_oracle, synth
+    boxes, scores = synth.synthetic_boxes(700, seed=3, extent=200.0)
+    for algo in (0, 1, 2):
+        k = _nms(boxes, scores, -0.1, algo)
+        assert np.array_equal(k, nms_oracle.nms(boxes, scores, -0.1)) and len(k) == 1
+
+
 def test_nms_degenerate_nothing_suppressed():
     from oracle import nms_oracle
     r = np.random.RandomState(5)

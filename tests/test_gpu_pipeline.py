@@ -73,6 +73,30 @@ def test_get_bboxes_shim(case):
         get_bboxes(z, np.zeros((1, 4, 20, 100), np.float32), z.copy(), synth.load_templates(), 0.5, synth.RF, 1)
 
 
+def test_get_bboxes_template_mask_mode():
+    """bug_compat=False masks templates (the behaviour utils.py:17-44 intends) instead of heat-map columns."""
+    from oracle import decode_oracle, synth
+    from tinyfaces_b200.models.utils import get_bboxes
+    from test_gpu_ops import _assert_boxes_close
+    g = np.load(os.path.join(G, "decode_case1.npz"))
+    tpl = synth.load_templates()
+    prob = g["prob_cls"].copy()
+    boxes, scores = get_bboxes(g["score_cls"], g["score_reg"], prob, tpl, float(g["thresh"]), synth.RF, float(g["scale"]),
+                               bug_compat=False)
+    # oracle for the intended behaviour: zero the invalid templates by hand, then decode with no column quirk
+    pr = g["prob_cls"].copy()
+    inv = decode_oracle.invalid_ids(tpl, float(g["scale"]))
+    pr[:, :, :, inv] = 0
+    saved = decode_oracle.invalid_ids
+    decode_oracle.invalid_ids = lambda t, s: np.array([], dtype=np.int64)
+    try:
+        rb, rs = decode_oracle.get_bboxes(g["score_cls"], g["score_reg"], pr, tpl, float(g["thresh"]), synth.RF, float(g["scale"]))
+    finally:
+        decode_oracle.invalid_ids = saved
+    assert np.array_equal(scores, rs)
+    _assert_boxes_close(boxes, rb)
+
+
 def test_nms_shim_is_torchvision_compatible():
     from tinyfaces_b200.evaluation import nms
     g = np.load(os.path.join(G, "nms_case0.npz"))

@@ -44,6 +44,7 @@ struct GemmParams {
     int tiles_x, tiles_y, tw, th; // spatial tiling of one image (tw * th == 128)
     int taps, kblocks, nseg;      // K loop = nseg x taps x kblocks blocks of 32 channels
     int stride;                   // spatial mode: input coordinate = stride * output coordinate + tap offset (TMA elementStrides)
+    int m_tile_begin;             // this launch covers m-tiles [m_tile_begin, m_tile_begin + num_m_tiles)
     const float* scale;           // optional per-output-channel epilogue: v = v * scale[n] + shift[n]
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
     int relu, round_out;
@@ -113,7 +114,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n0 = (tile % p.num_n_tiles) * BN;
-                const int mt = tile / p.num_n_tiles;
+                const int mt = tile / p.num_n_tiles + p.m_tile_begin;
                 int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
                 if (p.spatial) {
                     img = mt / tiles_per_img;
@@ -180,7 +181,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n0 = (tile % p.num_n_tiles) * BN;
-            const int mt = tile / p.num_n_tiles;
+            const int mt = tile / p.num_n_tiles + p.m_tile_begin;
             int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
             if (p.spatial) {
                 img = mt / tiles_per_img;
@@ -600,16 +601,50 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
             if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B, stride))) return rc;
         if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, p.tw, p.th))) return rc;
     }
-    for (int s = 0; s < p.nseg; ++s)
-        if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
-    if (a.stats_blocks) {
-        const int tiles = p.num_m_tiles * p.num_n_tiles;
-        const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / p.num_n_tiles * p.num_n_tiles;
-        *a.stats_blocks = grid / p.num_n_tiles * 4;
+    // One launch covers m-tiles [m_begin, m_begin + m_count) with tile width bn; returns the number of
+    // statistics partial rows it writes.
+    const int total_m_tiles = p.num_m_tiles;
+    auto launch = [&](int bn, int m_begin, int m_count, float* stats_ptr, int* stats_rows) -> int {
+        GemmParams q = p;
+        q.num_m_tiles = m_count; q.m_tile_begin = m_begin; q.num_n_tiles = Cout / bn; q.stats_partial = stats_ptr;
+        for (int s = 0; s < q.nseg; ++s)
+            if (int e = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, bn)) return e;
+        const int tiles = q.num_m_tiles * q.num_n_tiles;
+        const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / q.num_n_tiles * q.num_n_tiles;
+        if (stats_rows) *stats_rows = grid / q.num_n_tiles * 4;
+        if (bn == 256) return launch_gemm<256>(maps, q, st);
+        if (bn == 128) return launch_gemm<128>(maps, q, st);
+        return launch_gemm<64>(maps, q, st);
+    };
+    // Tail-wave split: when the last round over the SMs is mostly empty (e.g. 300 tiles on 148 SMs = 2.03 waves),
+    // the leftover m-tiles are processed by a second launch with narrower tiles that fills the machine.
+    int m_main = total_m_tiles, bn_tail = 0;
+    if (!g_debug[3]) {
+        const long long tiles = (long long)total_m_tiles * (Cout / BN);
+        const long long full = tiles / g_num_sms;
+        if (full >= 1 && tiles % g_num_sms != 0) {
+            const int m_split = (int)((full * g_num_sms) / (Cout / BN));
+            const int tail_m = total_m_tiles - m_split;
+            const double pen[3] = {1.0, 1.45, 2.2};
+            const double base = (double)(full + 1) * BN * pen[BN == 256 ? 0 : (BN == 128 ? 1 : 2)];
+            double best_cost = base;
+            for (int cand = BN / 2; cand >= 64; cand >>= 1) {
+                if (Cout % cand) continue;
+                const long long tt = (long long)tail_m * (Cout / cand);
+                const double c = (double)full * BN * pen[BN == 256 ? 0 : (BN == 128 ? 1 : 2)] +
+                                 (double)((tt + g_num_sms - 1) / g_num_sms) * cand * pen[cand == 256 ? 0 : (cand == 128 ? 1 : 2)];
+                if (c < 0.93 * best_cost && m_split > 0) { best_cost = c; m_main = m_split; bn_tail = cand; }
+            }
+        }
     }
-    if (BN == 256) return launch_gemm<256>(maps, p, st);
-    if (BN == 128) return launch_gemm<128>(maps, p, st);
-    return launch_gemm<64>(maps, p, st);
+    int rows_main = 0, rows_tail = 0;
+    if ((rc = launch(BN, 0, m_main, a.stats_partial, &rows_main))) return rc;
+    if (bn_tail) {
+        float* sp = a.stats_partial ? a.stats_partial + (size_t)rows_main * 2 * Cout : nullptr;
+        if ((rc = launch(bn_tail, m_main, total_m_tiles - m_main, sp, &rows_tail))) return rc;
+    }
+    if (a.stats_blocks) *a.stats_blocks = rows_main + rows_tail;
+    return TF_OK;
 }
 
 int conv_wgrad(const WgradArgs& a, cudaStream_t st) {

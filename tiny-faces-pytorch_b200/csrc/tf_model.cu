@@ -308,7 +308,7 @@ struct Model {
     int forward(const float* x_nchw, float* out_nchw, cudaStream_t st) {
         H2 = (H - 1) / 2 + 1; W2 = (W - 1) / 2 + 1;
         Hp = (H2 - 1) / 2 + 1; Wp = (W2 - 1) / 2 + 1;
-        partial = ar.f((size_t)tfe::COLREDUCE_MAX_BLOCKS * 2 * 1024);
+        partial = ar.f((size_t)tfe::COLREDUCE_MAX_BLOCKS * 2 * 2 * 1024);   // main + tail-launch statistics rows
         coef = ar.f(3 * 1024);
         dwtmp = ar.f((size_t)1024 * 1024 + 4096);
         offdiag = ar.f(64);

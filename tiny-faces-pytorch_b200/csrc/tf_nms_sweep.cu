@@ -40,27 +40,66 @@ __global__ void gather_rank_kernel(const T* __restrict__ boxes, const int* __res
     area[i] = Arith<T>::mul(Arith<T>::sub(b.x2, b.x1), Arith<T>::sub(b.y2, b.y1));
     xkey[i] = b.x1;
 }
-// FILL == 0: count conflicts per later box; FILL == 1: write the earlier box of each conflict into the CSR rows
+// x-ordered copies of the boxes so that the sweep streams them instead of gathering through xorder
+template <typename T>
+__global__ void gather_x_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area, const int* __restrict__ xorder, int n,
+                                Box<T>* __restrict__ xb, T* __restrict__ xarea) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = xorder[i];
+    xb[i] = sb[r];
+    xarea[i] = area[r];
+}
+// One WARP per box a (position p in x order): the 32 lanes test 32 consecutive x-successors per step, so dense
+// inputs (real detections overlap thousands of x-neighbours) stay parallel.
+// FILL == 0: count conflicts per later box; FILL == 1: write the earlier box of each conflict into the CSR rows.
 template <typename T, int FILL>
-__global__ void __launch_bounds__(128) sweep_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area,
-                                                    const int* __restrict__ xorder, const T* __restrict__ xsorted, int n,
-                                                    double thr, unsigned int* __restrict__ count,
-                                                    const unsigned int* __restrict__ offset, unsigned int* __restrict__ cursor,
-                                                    int* __restrict__ edges) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ xb, const T* __restrict__ xarea,
+                                                    const int* __restrict__ xorder, int n, double thr,
+                                                    unsigned int* __restrict__ count, const unsigned int* __restrict__ offset,
+                                                    unsigned int* __restrict__ cursor, int* __restrict__ edges) {
+    const int p = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
     if (p >= n) return;
-    const int a = xorder[p];
-    const Box<T> A = sb[a];
-    const T aa = area[a];
-    for (int q = p + 1; q < n && xsorted[q] <= A.x2; ++q) {
-        const int b = xorder[q];
-        const Box<T> Bx = sb[b];
-        if (!(Bx.y1 < A.y2 && A.y1 < Bx.y2)) continue;                     // no overlap in y (exact pre-test)
-        const int lo = a < b ? a : b, hi = a < b ? b : a;                 // lo has the higher score
-        const bool hit = a < b ? suppresses<T>(A, aa, Bx, area[b], thr, true) : suppresses<T>(Bx, area[b], A, aa, thr, true);
-        if (!hit) continue;
-        if (FILL) edges[offset[hi] + atomicAdd(&cursor[hi], 1u)] = lo;
-        else atomicAdd(&count[hi], 1u);
+    const int a = xorder[p];                       // rank (score order) of this box
+    const Box<T> A = xb[p];
+    const T aa = xarea[p];
+    unsigned int mine = 0;                         // conflicts whose later box is a (lane-private count)
+    for (int base = p + 1; base < n; base += 32) {
+        const int q = base + lane;
+        bool live = false, hit = false;
+        int b = 0;
+        if (q < n) {
+            const Box<T> Bx = xb[q];
+            live = Bx.x1 <= A.x2;                  // x order: once this fails, it fails for every later q
+            if (live && Bx.y1 < A.y2 && A.y1 < Bx.y2) {
+                b = xorder[q];
+                hit = a < b ? suppresses<T>(A, aa, Bx, xarea[q], thr, true) : suppresses<T>(Bx, xarea[q], A, aa, thr, true);
+            }
+        }
+        if (hit) {
+            if (b > a) {                           // the neighbour is the later box: its own row
+                if (FILL) edges[offset[b] + atomicAdd(&cursor[b], 1u)] = a;
+                else atomicAdd(&count[b], 1u);
+            } else {                               // a is the later box: aggregate in the warp
+                if (!FILL) ++mine;
+            }
+        }
+        if (FILL) {
+            const unsigned int m = __ballot_sync(0xffffffffu, hit && b < a);
+            if (m) {
+                unsigned int start = 0;
+                if (lane == 0) start = atomicAdd(&cursor[a], (unsigned int)__popc(m));
+                start = __shfl_sync(0xffffffffu, start, 0);
+                if (hit && b < a) edges[offset[a] + start + __popc(m & ((1u << lane) - 1u))] = b;
+            }
+        }
+        if (!__any_sync(0xffffffffu, live)) break;
+        if (!__shfl_sync(0xffffffffu, (int)live, 31) ) break;      // lane 31 past the x range: so is everything after
+    }
+    if (!FILL) {
+        mine = (unsigned int)tf_warp_sum((int)mine);
+        if (lane == 0 && mine) atomicAdd(&count[a], mine);
     }
 }
 // one relaxation round; states only move UNDECIDED -> KEPT / REMOVED, so racing reads are harmless
@@ -99,7 +138,7 @@ struct SweepPlan {
         sort_bytes = sort_bytes > s2 ? sort_bytes : s2;
         cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr, (int)n + 1);
         cub::DeviceSelect::Flagged(nullptr, select_bytes, (const int*)nullptr, (const unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
-        edge_cap = (size_t)n * 64 + (1u << 20);
+        edge_cap = (size_t)n * 256 + (1u << 20);
         if (edge_cap > 0xF0000000ull) edge_cap = 0xF0000000ull;
         size_t a = 0;
         auto add = [&](size_t b) { a = tf_align_up(a, 256) + b; };
@@ -107,6 +146,7 @@ struct SweepPlan {
         add(sort_bytes); add(scan_bytes); add(select_bytes);
         add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas by rank
         add(sizeof(T) * n); add(sizeof(T) * n); add(4 * n);               // x keys, sorted x keys, x order
+        add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas in x order
         add(4 * (n + 1)); add(4 * (n + 1)); add(4 * n);                   // counts, offsets, cursors
         add(4 * edge_cap);                                                // CSR edges
         add(n); add(n); add(4 * n);                                       // state, flags, selected
@@ -142,6 +182,8 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     T* xkey = ar.take<T>(n);
     T* xsorted = ar.take<T>(n);
     int* xorder = ar.take<int>(n);
+    Box<T>* xb = ar.take<Box<T>>(n);
+    T* xarea = ar.take<T>(n);
     unsigned int* count = ar.take<unsigned int>(n + 1);
     unsigned int* offset = ar.take<unsigned int>(n + 1);
     unsigned int* cursor = ar.take<unsigned int>(n);
@@ -160,8 +202,10 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     sb_bytes = plan.sort_bytes;
     TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sb_bytes, (const T*)xkey, xsorted, (const int*)iota, xorder, n, 0,
                                                   (int)sizeof(T) * 8, st));
+    gather_x_kernel<T><<<nb, 256, 0, st>>>(sb, area, xorder, n, xb, xarea);
     TF_CHECK_CUDA(cudaMemsetAsync(count, 0, 4 * (size_t)(n + 1), st));
-    sweep_kernel<T, 0><<<(n + 127) / 128, 128, 0, st>>>(sb, area, xorder, xsorted, n, thr, count, nullptr, nullptr, nullptr);
+    const int sweep_blocks = (int)(((long long)n * 32 + 255) / 256);
+    sweep_kernel<T, 0><<<sweep_blocks, 256, 0, st>>>(xb, xarea, xorder, n, thr, count, nullptr, nullptr, nullptr);
     size_t sc_bytes = plan.scan_bytes;
     TF_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, sc_bytes, count, offset, n + 1, st));
     unsigned int total_edges = 0;
@@ -169,7 +213,7 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     TF_CHECK_CUDA(cudaStreamSynchronize(st));
     if ((size_t)total_edges > plan.edge_cap) return 1;
     TF_CHECK_CUDA(cudaMemsetAsync(cursor, 0, 4 * (size_t)n, st));
-    sweep_kernel<T, 1><<<(n + 127) / 128, 128, 0, st>>>(sb, area, xorder, xsorted, n, thr, nullptr, offset, cursor, edges);
+    sweep_kernel<T, 1><<<sweep_blocks, 256, 0, st>>>(xb, xarea, xorder, n, thr, nullptr, offset, cursor, edges);
     TF_CHECK_CUDA(cudaMemsetAsync(state, 0, n, st));
     for (int round = 0; round < n + 8;) {
         TF_CHECK_CUDA(cudaMemsetAsync(scalars, 0, 4, st));
