@@ -170,9 +170,13 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
     } else {
         // ---------------------------------------------------------------- epilogue (warps 2..5)
+        // Each warp owns TMEM lanes [32q, 32q+32) = 32 rows of the tile and works independently: tcgen05.ld of the
+        // next 32-column chunk is in flight while the current one is scaled / staged (two private 4 KB swizzled
+        // buffers) and stored by the warp's own TMA (box = 32 rows), so there is no block-level barrier in the loop.
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const bool store_thread = threadIdx.x == 64;
+        uint8_t* wbuf = epi + q * 2 * 4096;
+        int wx = 0, wy = 0;                     // position of the warp's 32 rows inside a spatial patch
+        if (p.spatial) { wy = (q * 32) / p.tw; wx = (q * 32) % p.tw; }
         int it = 0, ebuf = 0;
         float st_sum[BN / 32], st_sq[BN / 32];
 #pragma unroll
@@ -191,12 +195,15 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            uint32_t rr[2][32];
+            tmem_ld_32x32(taddr, rr[0]);
 #pragma unroll
             for (int chunk = 0; chunk < BN / 32; ++chunk) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + chunk * 32, r);
-                tmem_ld_wait();
-                if (chunk == BN / 32 - 1) { tc_fence_before(); mbar_arrive(&tempty[acc]); }
+                uint32_t (&r)[32] = rr[chunk & 1];
+                tmem_ld_wait();                                              // this chunk's registers are valid
+                if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, rr[(chunk + 1) & 1]);
+                else { tc_fence_before(); mbar_arrive(&tempty[acc]); }        // accumulator stage fully read
                 if (p.scale || p.shift || p.relu || p.round_out) {
                     const int nb = n0 + chunk * 32;
 #pragma unroll
@@ -209,30 +216,30 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                         r[j] = __float_as_uint(v);
                     }
                 }
-                uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
-                if (store_thread) tma_store_wait_read<1>();      // the store that last used this buffer has drained
-                named_bar_sync_epi();
-                store_row_swizzled(buf, row, r);
+                uint8_t* buf = wbuf + ebuf * 4096;
+                if (lane == 0) tma_store_wait_read<1>();         // the store that last used this buffer has drained
+                __syncwarp();
+                store_row_swizzled(buf, lane, r);
                 fence_proxy_async();
-                named_bar_sync_epi();
-                if (store_thread) {
+                __syncwarp();
+                if (lane == 0) {
                     if (p.accumulate) {
-                        if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0, y0, img);
-                        else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                        if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
+                        else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
                     } else {
-                        if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0, y0, img);
-                        else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0);
+                        if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
+                        else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
                     }
                     tma_store_commit();
                 }
                 if (p.stats_partial) {
-                    // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged tile
+                    // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged rows
                     // (a 3x3 tap can pull in-image data into an out-of-image output row, so those rows are masked)
                     float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int rw = q * 32 + rr;
-                        float v = *reinterpret_cast<const float*>(buf + rw * 128 + (((lane >> 2) ^ (rw & 7)) << 4) + ((lane & 3) << 2));
+                    for (int l = 0; l < 32; ++l) {
+                        const int rw = q * 32 + l;
+                        float v = *reinterpret_cast<const float*>(buf + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
                         if (p.spatial && (x0 + rw % p.tw >= p.img_w || y0 + rw / p.tw >= p.img_h)) v = 0.f;
                         s0 += v; s1 += v * v;
                     }
@@ -250,7 +257,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 dst[p.cout + n0 + c * 32 + lane] = st_sq[c];
             }
         }
-        if (store_thread) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();
     }
     __syncthreads();
     if (warp == 1) { __syncwarp(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
@@ -591,7 +598,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         p.tiles_x = p.tiles_y = 1; p.tw = 128; p.th = 1;
         for (int s = 0; s < p.nseg; ++s)
             if ((rc = encode_2d(&maps.a[s], as[s], Cin, M, Cin, 32, BLOCK_M))) return rc;
-        if ((rc = encode_2d(&maps.d, a.y, Cout, M, Cout, 32, BLOCK_M))) return rc;
+        if ((rc = encode_2d(&maps.d, a.y, Cout, M, Cout, 32, 32))) return rc;          // one store box per epilogue warp
     } else {
         p.spatial = 1;
         pick_tile(Wo, Ho, BLOCK_M, &p.tw, &p.th);
@@ -599,7 +606,10 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         p.num_m_tiles = B * p.tiles_x * p.tiles_y;
         for (int s = 0; s < p.nseg; ++s)
             if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B, stride))) return rc;
-        if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, p.tw, p.th))) return rc;
+        {   // per-warp store box: 32 consecutive tile rows = (bw x bh) pixels of the patch
+            const int bw = p.tw < 32 ? p.tw : 32, bh = 32 / bw;
+            if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, bw, bh))) return rc;
+        }
     }
     // One launch covers m-tiles [m_begin, m_begin + m_count) with tile width bn; returns the number of
     // statistics partial rows it writes.

@@ -356,21 +356,7 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const unsigned 
     }
 }
 
-// out[b,oy,ox,:] = x[b,2oy,2ox,:]
-__global__ void __launch_bounds__(EW_THREADS) subsample2_kernel(const float* __restrict__ x, const float* __restrict__ x_lo,
-                                                                int B, int H, int W, int C, int Ho, int Wo,
-                                                                float* __restrict__ out, float* __restrict__ out_lo) {
-    const long long total = (long long)B * Ho * Wo * (C / 4);
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(t % (C / 4));
-        const long long pix = t / (C / 4);
-        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-        const long long src = (((long long)b * H + oy * 2) * W + ox * 2) * C + cg * 4;
-        st4(out + pix * C + cg * 4, ld4(x + src));
-        if (x_lo) st4(out_lo + pix * C + cg * 4, ld4(x_lo + src));
-    }
-}
-// out[b,y,x,:] = (y,x both even) ? xs[b,y/2,x/2,:] : 0     (adjoint of subsample2)
+// out[b,y,x,:] = (y,x both even) ? xs[b,y/2,x/2,:] : 0     (adjoint of a stride-2 subsampling)
 __global__ void __launch_bounds__(EW_THREADS) zero_insert2_kernel(const float* __restrict__ xs, const float* __restrict__ xs_lo,
                                                                   int B, int H, int W, int C, int Ho, int Wo,
                                                                   float* __restrict__ out, float* __restrict__ out_lo) {
@@ -520,17 +506,6 @@ static int reduce_blocks(long long M, int C) {
     return (int)std::min<long long>(std::max<long long>(b, 1), COLREDUCE_MAX_BLOCKS);
 }
 
-int bn_stats_train(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
-                   float* run_mean, float* run_var, float* scale, float* shift, float* save_mean, float* save_rstd,
-                   float* partial, cudaStream_t st) {
-    TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_stats_train: C=%d unsupported", C);
-    const int nb = reduce_blocks(M, C);
-    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, M, gamma, beta, eps, momentum, run_mean,
-                                                              run_var, scale, shift, save_mean, save_rstd);
-    TF_LAUNCH_CHECK();
-    return TF_OK;
-}
 int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st) {
@@ -598,12 +573,6 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, floa
 }
 int maxpool_bwd(const unsigned char* argmax, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st) {
     maxpool_bwd_kernel<<<ew_blocks((long long)B * H * W * C / 4), EW_THREADS, 0, st>>>(argmax, dout, B, H, W, C, Ho, Wo, dx);
-    TF_LAUNCH_CHECK();
-    return TF_OK;
-}
-int subsample2(const float* x, const float* x_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st) {
-    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
-    subsample2_kernel<<<ew_blocks((long long)B * Ho * Wo * C / 4), EW_THREADS, 0, st>>>(x, x_lo, B, H, W, C, Ho, Wo, out, out_lo);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

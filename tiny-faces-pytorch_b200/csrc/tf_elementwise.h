@@ -6,9 +6,6 @@ namespace tfe {
 constexpr int COLREDUCE_MAX_BLOCKS = 592;     // partial buffers hold COLREDUCE_MAX_BLOCKS * 2 * C floats
 // `mode` of every activation producer: 0 = store as is, 1 = round to TF32 (fast mode operands),
 // 2 = store the (hi, lo) TF32 split into (out, out_lo) (3xTF32 parity mode)
-int bn_stats_train(const float* y, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
-                   float* run_mean, float* run_var, float* scale, float* shift, float* save_mean, float* save_rstd,
-                   float* partial, cudaStream_t st);
 int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st);
@@ -29,7 +26,6 @@ int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_
 int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode,
                 unsigned char* argmax /* optional [B,Ho,Wo,C] window index of the first maximum */, cudaStream_t st);
 int maxpool_bwd(const unsigned char* argmax, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st);
-int subsample2(const float* x, const float* x_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
 int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st);
 int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, int O_pad, int I_pad, float* dst,
                 float* dst_lo, int mode, cudaStream_t st);

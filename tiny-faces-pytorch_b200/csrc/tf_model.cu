@@ -242,13 +242,6 @@ struct Model {
         if (!ar.dry) RC(tfe::bn_scale_shift_eval(u.bn.C, P(u.bn.gamma), P(u.bn.beta), P(u.bn.rm), P(u.bn.rv), eps, u.scale, u.shift, st));
         return TF_OK;
     }
-    int bn_stats(Unit& u, cudaStream_t st) {
-        RC(alloc_bn(u));
-        const long long M = (long long)u.B * u.Ho * u.Wo;
-        if (!ar.dry) RC(tfe::bn_stats_train(u.y, M, u.bn.C, P(u.bn.gamma), P(u.bn.beta), eps, momentum, PW(u.bn.rm), PW(u.bn.rv),
-                                            u.scale, u.shift, u.mean, u.rstd, partial, st));
-        return TF_OK;
-    }
     // conv + BN + ReLU -> activation (u.a)
     int conv_bn_relu(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, cudaStream_t st) {
         const int Ho = u.c.stride == 2 ? (H_ + 1) / 2 : H_, Wo = u.c.stride == 2 ? (W_ + 1) / 2 : W_;
