@@ -263,6 +263,211 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     if (warp == 1) { __syncwarp(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
+// ------------------------------------------------------------------------------------------------ 2-CTA fprop/dgrad
+// conv_gemm2_kernel: the same implicit GEMM with tcgen05.mma.cta_group::2 -- a cluster of two CTAs (one TPC) computes a
+// 256-pixel x 256-channel tile: each CTA stages ITS 128 pixel rows of A and HALF (128 channels) of the B tile, the
+// leader's single MMA thread issues M=256 x N=256 x K=8 instructions that read both CTAs' shared memory, and each CTA
+// owns the accumulator rows of its pixels in its own TMEM.  Per CTA the operand traffic drops from 48 KB to 32 KB per
+// K=32 step (the one-CTA kernel is shared-memory-bandwidth bound on the K=256 layers), 6 pipeline stages fit.
+// Barrier protocol: full[s] lives in the leader (count 1 = the leader producer's expect_tx of BOTH CTAs' bytes; both
+// producers' TMA complete_tx on it); empty[s] / tfull[a] exist in both CTAs and are signalled by multicast commits;
+// tempty[a] lives in the leader and collects the 256 epilogue threads of both CTAs.
+constexpr bool TWO_CTA_DEFAULT = false;     // flipped once the kernel is validated and faster on the GPU
+constexpr int G2_BN = 256;
+constexpr int G2_STAGES = 6;
+constexpr int G2_B_STAGE_BYTES = 128 * 128;                        // this CTA's half of the B tile
+constexpr int G2_STAGE_BYTES = A_STAGE_BYTES + G2_B_STAGE_BYTES;   // 32 KB
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+    constexpr int BN = G2_BN;
+    constexpr int STAGES = G2_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* epi = smem + STAGES * G2_STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(epi + 2 * EPI_BUF_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&maps.a[s]); prefetch_tmap(&maps.b[s]); }
+        prefetch_tmap(&maps.d);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc2<2 * BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                      // the peer's barriers are initialised too
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;     // a "tile" = two consecutive m-tiles x BN
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------------------ TMA producer (both CTAs)
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < pair_tiles; tile += num_clusters) {
+                const int n0 = (tile % p.num_n_tiles) * BN;
+                const int mt = 2 * (tile / p.num_n_tiles) + (int)rank + p.m_tile_begin;
+                int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
+                if (p.spatial) {
+                    img = mt / tiles_per_img;                 // an odd tail m-tile lands in image index B: fully OOB -> zeros
+                    const int r = mt % tiles_per_img;
+                    y0 = (r / p.tiles_x) * p.th;
+                    x0 = (r % p.tiles_x) * p.tw;
+                }
+                for (int seg = 0; seg < p.nseg; ++seg)
+                    for (int tap = 0; tap < p.taps; ++tap)
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 21);
+                            uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+                            uint8_t* sb = sa + A_STAGE_BYTES;
+                            const uint32_t lead_full = map_to_cta(smem_u32(&full[stage]), 0);
+                            if (rank == 0) mbar_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
+                            if (p.spatial)
+                                tma2_load_4d(sa, &maps.a[seg], lead_full, kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
+                            else
+                                tma2_load_2d(sa, &maps.a[seg], lead_full, kb * BLOCK_K, m0);
+                            tma2_load_2d(sb, &maps.b[seg], lead_full, (tap * p.kblocks + kb) * BLOCK_K, n0 + (int)rank * 128);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------------------ MMA issuer (leader CTA only)
+            constexpr uint32_t idesc = make_idesc_tf32(256, BN, MAJOR_K, MAJOR_K);
+            const int kiters = p.nseg * p.taps * p.kblocks;
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < pair_tiles; tile += num_clusters, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tempty[acc], acc_phase ^ 1, p.err_flag, 22);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int k = 0; k < kiters; ++k) {
+                    mbar_wait(&full[stage], phase, p.err_flag, 23);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < BLOCK_K / 8; ++j) {
+                        const uint64_t ad = make_smem_desc(sa + j * 32, 16, 1024);
+                        const uint64_t bd = make_smem_desc(sb + j * 32, 16, 1024);
+                        mma2_tf32(d_tmem, ad, bd, idesc, (k | j) != 0);
+                    }
+                    tc_commit2(&empty[stage]);               // frees the stage in BOTH CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit2(&tfull[acc]);                     // accumulators ready in BOTH CTAs
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (warps 2..5, both CTAs)
+        const int q = warp & 3;
+        uint8_t* wbuf = epi + q * 2 * 4096;
+        int wx = 0, wy = 0;
+        if (p.spatial) { wy = (q * 32) / p.tw; wx = (q * 32) % p.tw; }
+        int it = 0, ebuf = 0;
+        float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+        for (int tile = cluster_id; tile < pair_tiles; tile += num_clusters, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int n0 = (tile % p.num_n_tiles) * BN;
+            const int mt = 2 * (tile / p.num_n_tiles) + (int)rank + p.m_tile_begin;
+            int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
+            if (p.spatial) {
+                img = mt / tiles_per_img;
+                const int r = mt % tiles_per_img;
+                y0 = (r / p.tiles_x) * p.th;
+                x0 = (r % p.tiles_x) * p.tw;
+            }
+            const bool real_tile = mt < p.num_m_tiles + p.m_tile_begin;     // the odd tail pair has one phantom half
+            mbar_wait(&tfull[acc], acc_phase, p.err_flag, 24);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            uint32_t rr[2][32];
+            tmem_ld_32x32(taddr, rr[0]);
+#pragma unroll
+            for (int chunk = 0; chunk < BN / 32; ++chunk) {
+                uint32_t (&r)[32] = rr[chunk & 1];
+                tmem_ld_wait();
+                if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, rr[(chunk + 1) & 1]);
+                else { tc_fence_before(); mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[acc]), 0)); }
+                if (!real_tile) continue;
+                if (p.scale || p.shift || p.relu || p.round_out) {
+                    const int nb = n0 + chunk * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float v = __uint_as_float(r[j]);
+                        if (p.scale) v *= __ldg(p.scale + nb + j);
+                        if (p.shift) v += __ldg(p.shift + nb + j);
+                        if (p.relu) v = fmaxf(v, 0.f);
+                        if (p.round_out) v = tf_round_tf32(v);
+                        r[j] = __float_as_uint(v);
+                    }
+                }
+                uint8_t* buf = wbuf + ebuf * 4096;
+                if (lane == 0) tma_store_wait_read<1>();
+                __syncwarp();
+                store_row_swizzled(buf, lane, r);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.accumulate) {
+                        if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
+                        else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
+                    } else {
+                        if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
+                        else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
+                    }
+                    tma_store_commit();
+                }
+                if (p.stats_partial) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+                    for (int l = 0; l < 32; ++l) {
+                        const int rw = q * 32 + l;
+                        float v = *reinterpret_cast<const float*>(buf + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
+                        if (p.spatial && (x0 + rw % p.tw >= p.img_w || y0 + rw / p.tw >= p.img_h)) v = 0.f;
+                        s0 += v; s1 += v * v;
+                    }
+                    st_sum[chunk] += s0; st_sq[chunk] += s1;
+                }
+                ebuf ^= 1;
+            }
+        }
+        if (p.stats_partial) {
+            // every cluster keeps one n-tile (num_clusters % num_n_tiles == 0): row = ((cluster / n_tiles) * 2 + rank) * 4 + q
+            const int n0 = (cluster_id % p.num_n_tiles) * BN;
+            float* dst = p.stats_partial + (size_t)(((cluster_id / p.num_n_tiles) * 2 + (int)rank) * 4 + q) * 2 * p.cout;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                dst[n0 + c * 32 + lane] = st_sum[c];
+                dst[p.cout + n0 + c * 32 + lane] = st_sq[c];
+            }
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                      // neither CTA may exit (or free TMEM) while the peer can still signal it
+    if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc2<2 * BN>(tmem_base); }
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 struct WgradMaps { CUtensorMap a[MAX_SEG], b[MAX_SEG], d; };   // a: dY (Cout, pixels), b: X (Cin, pixels), d: dW [Cout, taps*Cin]
 struct WgradParams {
@@ -525,6 +730,20 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st) {
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        attr_set = true;
+    }
+    const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
+    int clusters = pair_tiles < g_num_sms / 2 ? pair_tiles : g_num_sms / 2;
+    clusters = clusters / p.num_n_tiles * p.num_n_tiles;                 // every cluster keeps one n-tile
+    if (stats_rows) *stats_rows = clusters / p.num_n_tiles * 2 * 4;
+    conv_gemm2_kernel<<<2 * clusters, GEMM_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
 template <int BN>
 int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
@@ -617,8 +836,11 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     auto launch = [&](int bn, int m_begin, int m_count, float* stats_ptr, int* stats_rows) -> int {
         GemmParams q = p;
         q.num_m_tiles = m_count; q.m_tile_begin = m_begin; q.num_n_tiles = Cout / bn; q.stats_partial = stats_ptr;
+        // 2-CTA (cta_group::2) kernel for 256-wide tiles: each CTA of the pair stages half (128 rows) of the B tile
+        const bool two_cta = bn == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || TWO_CTA_DEFAULT) && q.num_m_tiles >= 2;
         for (int s = 0; s < q.nseg; ++s)
-            if (int e = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, bn)) return e;
+            if (int e = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, two_cta ? 128 : bn)) return e;
+        if (two_cta) return launch_gemm2(maps, q, stats_rows, st);
         const int tiles = q.num_m_tiles * q.num_n_tiles;
         const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / q.num_n_tiles * q.num_n_tiles;
         if (stats_rows) *stats_rows = grid / q.num_n_tiles * 4;

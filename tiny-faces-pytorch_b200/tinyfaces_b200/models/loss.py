@@ -1,9 +1,10 @@
 """DetectionCriterion -- drop-in for /root/reference/tinyfaces/models/loss.py:24-97.
 
 OHEM, the masked SoftMargin + SmoothL1 sums and their gradient run in the library's kernels
-(``tf_detloss_ohem``, ``tf_detloss_fwd_bwd``: one fused forward+backward pass); balance sampling is either the
-reference's host-side numpy procedure (``sampler='numpy'``: identical ``np.random`` consumption, identical label
-maps) or the device sampler (``sampler='device'``: statistically equivalent, no host round trip).
+(``tf_detloss_ohem``, ``tf_detloss_fwd_bwd``: one fused forward+backward pass).  Balance sampling runs on the device
+by default (``sampler='device'``: ``tf_detloss_sample_device``, statistically equivalent to the reference, no host
+round trip); ``sampler='numpy'`` reproduces the reference's host-side procedure draw for draw (identical
+``np.random`` consumption, hence identical label maps under the same seed) for bit-exact comparisons.
 """
 import numpy as np
 import torch
@@ -55,7 +56,7 @@ class _LossFunction(torch.autograd.Function):
 class DetectionCriterion(nn.Module):
     """The loss for the Tiny Faces detector (loss.py:24-97)."""
 
-    def __init__(self, n_templates=25, reg_weight=1, pos_fraction=0.5, sampler="numpy", sample_size=256, seed=0):
+    def __init__(self, n_templates=25, reg_weight=1, pos_fraction=0.5, sampler="device", sample_size=256, seed=0):
         super().__init__()
         if sampler not in ("numpy", "device"):
             raise ValueError("sampler must be 'numpy' (reference RNG protocol) or 'device'")

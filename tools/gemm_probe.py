@@ -19,6 +19,13 @@ CASES_OLD = [
 
 
 CASES = [
+    ("fprop+2cta", 1, 30, 40, 256, 256, 1), ("fprop+2cta", 2, 15, 20, 1024, 256, 1), ("fprop+2cta", 1, 13, 29, 256, 1024, 1),
+    ("fprop+2cta", 2, 15, 20, 256, 256, 3), ("fprop+2cta", 1, 63, 63, 256, 256, 3), ("fprop+2cta", 3, 9, 16, 256, 512, 1),
+    ("time", 8, 60, 80, 1024, 256, 1), ("time+2cta", 8, 60, 80, 1024, 256, 1),
+    ("time", 8, 60, 80, 256, 1024, 1), ("time+2cta", 8, 60, 80, 256, 1024, 1),
+    ("time", 8, 60, 80, 256, 256, 3), ("time+2cta", 8, 60, 80, 256, 256, 3),
+]
+CASES_OLD2 = [
     ("wgrad", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 128, 128, 1),
     ("wgrad+plain", 2, 17, 23, 256, 256, 1), ("wgrad+plain", 2, 15, 20, 256, 256, 3),
     ("fprop+acc", 1, 8, 16, 32, 64, 1), ("fprop+acc", 2, 15, 20, 256, 256, 3), ("wgrad", 2, 15, 20, 256, 256, 3),
@@ -31,6 +38,28 @@ def run_case(kind, B, H, W, Cin, Cout, k):
     if kind.endswith("+plain"):
         _lib.lib().tf_debug_set(0, 1)
         kind = "wgrad"
+    if kind.endswith("+2cta"):
+        _lib.lib().tf_debug_set(4, 1)
+        kind = kind[:-5]
+    else:
+        _lib.lib().tf_debug_set(4, 2)
+    if kind == "time":
+        d = torch.device("cuda:0")
+        xn = torch.randn(B, H, W, Cin, device=d)
+        wp = torch.randn(Cout, k * k, Cin, device=d) * 0.02
+        y = torch.empty(B, H, W, Cout, device=d)
+        for _ in range(5):
+            ops.conv2d_nhwc(xn, wp, k, out=y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            ops.conv2d_nhwc(xn, wp, k, out=y)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 50 * 1e3
+        return dict(kind="time", shape=[B, H, W, Cin, Cout, k], us=us, tflops=2.0 * B * H * W * Cin * Cout * k * k / us / 1e6,
+                    flag=ops.gemm_error_flag())
     acc = kind.endswith("+acc")
     if acc:
         _lib.lib().tf_debug_set(1, 1)
