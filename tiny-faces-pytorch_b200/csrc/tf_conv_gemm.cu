@@ -771,6 +771,8 @@ TF_API int tf_debug_set(int key, int value) {
 #include "tf_conv_gemm.h"
 namespace tfg {
 
+int debug_flag(int key) { return (key >= 0 && key < 8) ? g_debug[key] : 0; }
+
 int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     TF_REQUIRE(a.x && a.w && a.y, "conv_fprop: null pointer");
     TF_REQUIRE((a.x_lo == nullptr) == (a.w_lo == nullptr), "conv_fprop: x_lo and w_lo must be given together");

@@ -25,4 +25,5 @@ struct WgradArgs {
     float* dw;                             // packed [Cout][k*k][Cin], accumulated into
 };
 int conv_wgrad(const WgradArgs& a, cudaStream_t st);
+int debug_flag(int key);                  // tf_debug_set(key, value) experiment switches (0 = default behaviour)
 }  // namespace tfg

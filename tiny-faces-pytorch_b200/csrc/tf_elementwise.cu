@@ -73,7 +73,28 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
     float4 mu = s0, rs = s0;
     if (MODE == 1) { mu = ld4(mean + g * 4); rs = ld4(rstd + g * 4); }
     if (rl < lanes) {
-        for (long long r = (long long)blockIdx.x * lanes + rl; r < M; r += (long long)gridDim.x * lanes) {
+        const long long step = (long long)gridDim.x * lanes;
+        long long r = (long long)blockIdx.x * lanes + rl;
+        if (MODE == 1 && mask) {
+            // 4 rows per iteration with every load issued up front: this kernel shares the SMs with side-stream GEMM
+            // CTAs (few resident warps), so the bytes in flight have to come from each thread
+            for (; r + 3 * step < M; r += 4 * step) {
+                float4 v[4], y[4]; unsigned int nib[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long i = (r + u * step) * C + g * 4;
+                    v[u] = ld4(a + i); y[u] = ld4(b + i); nib[u] = mask_nibble(mask, i);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    apply_mask(v[u], nib[u]);
+                    s0.x += v[u].x; s0.y += v[u].y; s0.z += v[u].z; s0.w += v[u].w;
+                    s1.x += v[u].x * (y[u].x - mu.x) * rs.x; s1.y += v[u].y * (y[u].y - mu.y) * rs.y;
+                    s1.z += v[u].z * (y[u].z - mu.z) * rs.z; s1.w += v[u].w * (y[u].w - mu.w) * rs.w;
+                }
+            }
+        }
+        for (; r < M; r += step) {
             const long long i = r * C + g * 4;
             float4 v = ld4(a + i);
             if (MODE == 0) {

@@ -74,7 +74,17 @@ struct Model {
     // weight-gradient GEMMs run on a side stream: they depend only on (x, dy) and nothing in the backward chain
     // depends on them, so their tensor-core time overlaps the HBM-bound BN-backward kernels of the main stream
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_region[2] = {nullptr, nullptr};
+    // The backward chain itself runs on an internal HIGH-priority stream (forked from / joined to the caller's stream):
+    // when a dgrad GEMM of the chain and a weight-gradient GEMM of the side stream are both ready, the block scheduler
+    // hands the SMs to the chain first (both kernels need a whole SM's shared memory, so they cannot co-reside).
+    cudaStream_t chain = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_region[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
+    // wgrad_mode 0: weight gradient forked before its dgrad is enqueued; 1: forked before, enqueued after the dgrad;
+    //            2: deferred -- a block's three weight gradients are enqueued when the NEXT block's bn3 backward
+    //               (the longest HBM-bound stretch of the chain, ~6 passes over a 1024-channel tensor) starts
+    int wgrad_mode = 2, chain_priority = 1;
+    struct PendingWgrad { tfg::WgradArgs w; size_t dw_elems; int O, I, taps, I_pad; float* gw; };
+    std::vector<PendingWgrad> pending;
     size_t bwd_region_bytes = 0;
     int plan_B = 0, plan_H = 0, plan_W = 0, plan_training = -1, plan_mode = 0; size_t plan_need = 0;   // cached dry run
     bool side_enabled = true;
@@ -84,23 +94,52 @@ struct Model {
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_region[i], cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_chain[i], cudaEventDisableTiming));
+        int least = 0, greatest = 0;
+        TF_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        TF_CHECK_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, greatest));
         return TF_OK;
     }
     ~Model() {
-        if (side) { cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_region[0]); cudaEventDestroy(ev_region[1]); }
-    }
-    // dW (OIHW) = unpack(wgrad(x, dy)): enqueued behind everything already on `st`, executed on the side stream
-    int wgrad_async(tfg::WgradArgs w, size_t dw_elems, int O, int I, int taps, int I_pad, float* gw, cudaStream_t st) {
-        cudaStream_t s2 = st;
         if (side) {
-            TF_CHECK_CUDA(cudaEventRecord(ev_fork, st));
-            TF_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-            s2 = side;
+            cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
+            for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_region[i]); cudaEventDestroy(ev_chain[i]); }
         }
-        TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, dw_elems * 4, s2));
+    }
+    // dW (OIHW) = unpack(wgrad(x, dy)) on stream s2 (the side stream, or the chain itself when there is none).
+    // A 1x1 convolution's packed gradient [Cout][1][Cin] IS the OIHW tensor: it is accumulated straight into the
+    // caller's gradient, no staging buffer / unpack pass.
+    int wgrad_run(const PendingWgrad& j, cudaStream_t s2) {
+        tfg::WgradArgs w = j.w;
+        if (j.taps == 1 && j.I_pad == j.I && j.O == w.Cout) {
+            TF_CHECK_CUDA(cudaMemsetAsync(j.gw, 0, j.dw_elems * 4, s2));
+            w.dw = j.gw;
+            return tfg::conv_wgrad(w, s2);
+        }
+        TF_CHECK_CUDA(cudaMemsetAsync(dwtmp, 0, j.dw_elems * 4, s2));
         w.dw = dwtmp;
         RC(tfg::conv_wgrad(w, s2));
-        RC(tfe::unpack_wgrad(dwtmp, O, I, taps, I_pad, gw, s2));
+        RC(tfe::unpack_wgrad(dwtmp, j.O, j.I, j.taps, j.I_pad, j.gw, s2));
+        return TF_OK;
+    }
+    // Enqueue behind everything already on `st`.  fork_recorded: ev_fork was already recorded on st at the point the
+    // inputs became final (wgrad_mode 1 records it before the dgrad so the side stream does not wait for that GEMM).
+    int wgrad_async(tfg::WgradArgs w, size_t dw_elems, int O, int I, int taps, int I_pad, float* gw, cudaStream_t st,
+                    bool fork_recorded = false) {
+        PendingWgrad j = {w, dw_elems, O, I, taps, I_pad, gw};
+        if (!side) return wgrad_run(j, st);
+        if (wgrad_mode == 2) { pending.push_back(j); return TF_OK; }
+        if (!fork_recorded) TF_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+        TF_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+        return wgrad_run(j, side);
+    }
+    // wgrad_mode 2: everything queued so far depends only on work already enqueued on st
+    int wgrad_flush(cudaStream_t st) {
+        if (pending.empty() || !side) return TF_OK;
+        TF_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+        TF_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+        for (const PendingWgrad& j : pending) RC(wgrad_run(j, side));
+        pending.clear();
         return TF_OK;
     }
 
@@ -443,12 +482,14 @@ struct Model {
         const int taps = c.k * c.k;
         // ---- wgrad (a stride-2 conv reads x through the TMA traversal stride; dy stays at the output resolution)
         float* gw = G(grads, c.w);
-        if (gw && !ar.dry) {
-            tfg::WgradArgs w = {};
+        tfg::WgradArgs w = {};
+        const bool want_w = gw && !ar.dry;
+        if (want_w) {
             w.x = u.x; w.x_lo = u.x_lo; w.dy = dy; w.dy_lo = dy_lo; w.B = u.B; w.H = u.H; w.W = u.W; w.Cin = c.cin; w.Cout = c.cout;
             w.ksize = c.k; w.stride = c.stride;
             if (w.x_lo == nullptr || w.dy_lo == nullptr) { w.x_lo = nullptr; w.dy_lo = nullptr; }
-            RC(wgrad_async(w, (size_t)c.cout * taps * c.cin, c.cout, c.cin, taps, c.cin, gw, st));
+            if (wgrad_mode != 1 || !side || !dx) RC(wgrad_async(w, (size_t)c.cout * taps * c.cin, c.cout, c.cin, taps, c.cin, gw, st));
+            else TF_CHECK_CUDA(cudaEventRecord(ev_fork, st));          // inputs are final here; enqueue after the dgrad
         }
         // ---- dgrad: dx = conv(dy, w^T flipped)
         if (dx) {
@@ -480,6 +521,7 @@ struct Model {
                 if (a.x_lo == nullptr) a.w_lo = nullptr;
                 if (!ar.dry) RC(tfg::conv_fprop(a, st));
             }
+            if (want_w && wgrad_mode == 1 && side) RC(wgrad_async(w, (size_t)c.cout * taps * c.cin, c.cout, c.cin, taps, c.cin, gw, st, true));
         }
         return TF_OK;
     }
@@ -510,9 +552,22 @@ struct Model {
         return TF_OK;
     }
 
-    int backward(const float* dout_nchw, void* const* grads, cudaStream_t st) {
+    int backward(const float* dout_nchw, void* const* grads, cudaStream_t caller) {
         TF_REQUIRE(training, "tf_model_backward: the last forward was not a training forward");
         ar.off = fwd_mark;
+        if (!ar.dry) RC(ensure_side());
+        pending.clear();
+        // experiment switches: tf_debug_set(5, 1 + mode) picks the weight-gradient schedule, tf_debug_set(6, 1) keeps the
+        // chain on the caller's stream (no priority)
+        wgrad_mode = tfg::debug_flag(5) ? tfg::debug_flag(5) - 1 : 2;
+        chain_priority = tfg::debug_flag(6) ? 0 : 1;
+        // fork: the whole chain runs on the high-priority stream, the caller's stream waits for it at the end
+        cudaStream_t st = caller;
+        if (!ar.dry && side && chain_priority) {
+            TF_CHECK_CUDA(cudaEventRecord(ev_chain[0], caller));
+            TF_CHECK_CUDA(cudaStreamWaitEvent(chain, ev_chain[0], 0));
+            st = chain;
+        }
         const long long M3 = (long long)B * H3 * W3, M4 = (long long)B * H4 * W4;
         float* ds3 = ar.f((size_t)M3 * Cp); float* ds4 = ar.f((size_t)M4 * Cp);
         if (!ar.dry) {
@@ -536,16 +591,15 @@ struct Model {
             prepack_add(t3, 512, Cp, 1); prepack_add(t4, 1024, Cp, 1);
             RC(prepack_flush(st));
         }
-        // input gradients ping-pong between two buffers; one scratch region is reused by every block (single stream)
+        // input gradients ping-pong between two buffers; one scratch region is reused by every other block
         size_t mx = 0;
         for (const BlockS& s : bs) mx = std::max(mx, (size_t)s.B * s.H * s.W * s.u1.c.cin);
         float* dxbuf[2] = {ar.f(mx), ar.f(mx)};
-        if (!ar.dry) RC(ensure_side());
         RC(head_bwd(h4, ds4, dres4, 0, grads, st));
         const size_t scratch_mark = ar.off;
         // Two scratch regions alternate between blocks: the side stream may still be reading block i's dy tensors
-        // (weight gradients) while the main stream already works on block i-1; region r is reused only after the
-        // side-stream work that read it has finished (ev_region[r]).
+        // (weight gradients) while the chain already works on block i-1 (and, with deferred weight gradients, i-2 has
+        // not started): region r is reused only after the side-stream work that read it has finished (ev_region[r]).
         const size_t region = ar.dry ? 0 : bwd_region_bytes;
         size_t max_used = 0;
         // ---- layer3 .. layer1
@@ -554,16 +608,26 @@ struct Model {
             const BlockS& s = bs[i];
             const int r = i & 1;
             ar.off = scratch_mark + (size_t)r * region;
-            if (!ar.dry && side) TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[r], 0));
+            if (!ar.dry && side) {
+                // deferred weight gradients of block i+1 (other region): start them now, next to this block's bn3 backward
+                RC(wgrad_flush(st));
+                if (wgrad_mode == 2) TF_CHECK_CUDA(cudaEventRecord(ev_region[r ^ 1], side));
+                TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[r], 0));
+            }
             float* dx = dxbuf[i & 1];
             RC(block_backward(s, dcur, dx, grads, st));
             if (i == 7) RC(head_bwd(h3, ds3, dx, 1, grads, st));   // res3 also feeds score_res3: dx(block 7 input) += head dgrad
-            if (!ar.dry && side) TF_CHECK_CUDA(cudaEventRecord(ev_region[r], side));
+            if (!ar.dry && side && wgrad_mode != 2) TF_CHECK_CUDA(cudaEventRecord(ev_region[r], side));
             max_used = std::max(max_used, ar.off - (scratch_mark + (size_t)r * region));
             dcur = dx;
         }
         if (ar.dry) { bwd_region_bytes = tf_align_up(max_used, 1024); ar.peak = std::max(ar.peak, scratch_mark + 2 * bwd_region_bytes + 4096); }
-        else if (side) { TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[0], 0)); TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[1], 0)); }
+        else if (side) {
+            RC(wgrad_flush(st));
+            TF_CHECK_CUDA(cudaEventRecord(ev_region[0], side));
+            TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[0], 0));          // the stem scratch below overlays both regions
+            TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[1], 0));
+        }
         ar.off = scratch_mark;
         // ---- stem
         const long long M2 = (long long)B * H2 * W2;
@@ -579,8 +643,13 @@ struct Model {
             RC(wgrad_async(w, (size_t)64 * 160, 64, 147, 1, 160, gw, st));
         }
         if (!ar.dry && side) {                       // join: the caller's stream sees every gradient
+            RC(wgrad_flush(st));
             TF_CHECK_CUDA(cudaEventRecord(ev_join, side));
             TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+            if (st != caller) {
+                TF_CHECK_CUDA(cudaEventRecord(ev_chain[1], st));
+                TF_CHECK_CUDA(cudaStreamWaitEvent(caller, ev_chain[1], 0));
+            }
         }
         return TF_OK;
     }

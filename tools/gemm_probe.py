@@ -24,6 +24,10 @@ CASES = [
     ("time", 8, 60, 80, 1024, 256, 1), ("time+2cta", 8, 60, 80, 1024, 256, 1),
     ("time", 8, 60, 80, 256, 1024, 1), ("time+2cta", 8, 60, 80, 256, 1024, 1),
     ("time", 8, 60, 80, 256, 256, 3), ("time+2cta", 8, 60, 80, 256, 256, 3),
+    ("time", 8, 120, 160, 512, 128, 1), ("time", 8, 120, 160, 128, 128, 3), ("time", 8, 120, 160, 128, 512, 1),
+    ("time+2cta", 8, 120, 160, 128, 512, 1), ("time", 8, 240, 320, 64, 256, 1), ("time+2cta", 8, 240, 320, 64, 256, 1),
+    ("timew", 8, 60, 80, 256, 1024, 1), ("timew", 8, 60, 80, 1024, 256, 1), ("timew", 8, 60, 80, 256, 256, 3),
+    ("timew", 8, 120, 160, 128, 128, 3), ("timew", 8, 120, 160, 128, 512, 1),
 ]
 CASES_OLD2 = [
     ("wgrad", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 128, 128, 1),
@@ -43,6 +47,23 @@ def run_case(kind, B, H, W, Cin, Cout, k):
         kind = kind[:-5]
     else:
         _lib.lib().tf_debug_set(4, 2)
+    if kind == "timew":
+        d = torch.device("cuda:0")
+        xn = torch.randn(B, H, W, Cin, device=d)
+        dyn = torch.randn(B, H, W, Cout, device=d)
+        dw = torch.zeros(Cout, k * k, Cin, device=d)
+        for _ in range(5):
+            ops.conv2d_wgrad_nhwc(xn, dyn, k, out=dw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            ops.conv2d_wgrad_nhwc(xn, dyn, k, out=dw)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 50 * 1e3
+        return dict(kind="timew", shape=[B, H, W, Cin, Cout, k], us=us, tflops=2.0 * B * H * W * Cin * Cout * k * k / us / 1e6,
+                    flag=ops.gemm_error_flag())
     if kind == "time":
         d = torch.device("cuda:0")
         xn = torch.randn(B, H, W, Cin, device=d)
