@@ -77,6 +77,40 @@ def test_layerwise_against_oracle_taps():
     assert worst < 1e-3 and rec["out"] < 1e-3, rec
 
 
+@pytest.mark.parametrize("precision", ["parity", "fast"])
+def test_large_batch_shape_vs_oracle_autograd(precision):
+    """2 x 400 x 400: large enough that the layer-1 GEMMs (157+ tiles on 148 SMs) take the tail split-K path, whose
+    BN statistics come from a separate reduction -- forward, BN running stats and weight gradients vs the oracle."""
+    from oracle import model_oracle, synth
+    sd = synth.synthetic_state_dict(seed=3, bn3_gamma=0.25, beta_jitter=0.1)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 400, 400, generator=gen)
+    keys = ["model.layer1.1.conv2.weight", "model.layer1.2.conv1.weight", "model.layer1.0.bn2.weight", "model.conv1.weight",
+            "model.layer3.5.conv2.weight", "score_res3.weight"]
+    state = dict(sd)
+    for k in keys:
+        state[k] = sd[k].clone().requires_grad_(True)
+    new = {}
+    ref = model_oracle.forward(state, x, training=True, new_stats=new)
+    cot = torch.randn(ref.shape, generator=gen)
+    (ref * cot).sum().backward()
+    m = _model(sd, precision)
+    m.train()
+    out = m(x.cuda())
+    (out * cot.cuda()).sum().backward()
+    params = dict(m.named_parameters())
+    rec = dict(precision=precision, out_max=_rel(out.detach().cpu().numpy(), ref.detach().numpy()),
+               run_var=_rel(m.state_dict()["model.layer1.1.bn2.running_var"].cpu().numpy(), new["model.layer1.1.bn2.running_var"].numpy()))
+    for k in keys:
+        rec["grad:" + k] = _l2(params[k].grad.cpu().numpy(), state[k].grad.numpy())
+    _record("large_shape", rec)
+    if precision == "parity":
+        assert rec["out_max"] < 1e-3 and rec["run_var"] < 1e-4, rec
+        assert max(v for k, v in rec.items() if k.startswith("grad:")) < 3e-2, rec
+    else:
+        assert rec["out_max"] < 3e-2 and rec["run_var"] < 1e-3, rec
+
+
 @pytest.mark.parametrize("tag,gamma", [("g025", 0.25), ("g100", 1.0)])
 @pytest.mark.parametrize("precision", ["parity", "fast"])
 def test_train_forward_backward_vs_reference_golden(tag, gamma, precision):

@@ -284,6 +284,42 @@ def test_conv2d_wgrad_vs_torch_cpu(B, H, W, Cin, Cout, k):
     assert err < 2e-5, "rel err %g" % err
 
 
+# shapes whose tile count does not fill a whole round over the 148 SMs and whose K loop is long enough to cut: the
+# leftover tiles run as K slices that meet in the output through TMA reduce-add (tail-wave split-K)
+SPLITK_CASES = [(2, 100, 100, 512, 256, 1), (1, 140, 150, 64, 128, 3), (3, 81, 80, 256, 256, 3), (1, 160, 125, 1024, 256, 1)]
+
+
+@pytest.mark.parametrize("accumulate", [0, 1])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", SPLITK_CASES)
+def test_conv2d_tail_split_k(B, H, W, Cin, Cout, k, accumulate):
+    from tinyfaces_b200 import _lib, ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(3 + B + H + Cin + k)
+    x = _tf32(torch.randn(B, Cin, H, W, generator=gen))
+    w = _tf32(torch.randn(Cout, Cin, k, k, generator=gen) / (Cin * k * k) ** 0.5)
+    ref = torch.nn.functional.conv2d(x, w, padding=k // 2)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(d)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, k * k, Cin).contiguous().to(d)
+    y0 = torch.full((B, H, W, Cout), 0.5 if accumulate else 7.0, dtype=torch.float32, device=d)   # 7.0 must be overwritten
+    outs = {}
+    try:
+        for split in (2, 0):                              # tf_debug_set(3, 2) disables the split: same numbers either way
+            _lib.check(_lib.lib().tf_debug_set(3, split), "tf_debug_set")
+            _lib.check(_lib.lib().tf_debug_set(1, accumulate), "tf_debug_set")
+            outs[split] = ops.conv2d_nhwc(xn, wp, k, out=y0.clone()).cpu().permute(0, 3, 1, 2)
+    finally:
+        _lib.lib().tf_debug_set(3, 0)
+        _lib.lib().tf_debug_set(1, 0)
+    torch.cuda.synchronize()
+    assert ops.gemm_error_flag() == 0
+    if accumulate:
+        ref = ref + 0.5
+    scale = ref.abs().max().item()
+    for split, got in outs.items():
+        err = (got - ref).abs().max().item() / scale
+        assert err < 3e-5, "split flag %d: rel err %g" % (split, err)        # fp32 CPU reference: 1e-5 noise of its own
+
+
 STRIDED_CASES = [(1, 16, 16, 64, 64, 3), (2, 17, 23, 128, 128, 3), (1, 31, 40, 256, 256, 3), (2, 17, 23, 256, 512, 1),
                  (1, 30, 41, 512, 1024, 1)]
 

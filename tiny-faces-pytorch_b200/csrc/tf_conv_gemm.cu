@@ -44,7 +44,10 @@ struct GemmParams {
     int tiles_x, tiles_y, tw, th; // spatial tiling of one image (tw * th == 128)
     int taps, kblocks, nseg;      // K loop = nseg x taps x kblocks blocks of 32 channels
     int stride;                   // spatial mode: input coordinate = stride * output coordinate + tap offset (TMA elementStrides)
-    int m_tile_begin;             // this launch covers m-tiles [m_tile_begin, m_tile_begin + num_m_tiles)
+    // Tail-wave split-K: work units [0, main_tiles) are whole tiles; every later tile is cut into `ksplit` K slices
+    // (one unit each) whose partial sums meet in D through TMA reduce-add (the host zeroes those rows first).  Without
+    // it 300 tiles on 148 SMs cost 3 rounds for 2.03 rounds of work.
+    int main_tiles, ksplit;
     const float* scale;           // optional per-output-channel epilogue: v = v * scale[n] + shift[n]
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
     int relu, round_out;
@@ -77,6 +80,20 @@ __device__ __forceinline__ void store_row_swizzled(uint8_t* buf, int row, const 
     }
 }
 
+struct WorkUnit { int tile, k0, k1, split; };
+__device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u, int kiters) {
+    WorkUnit w;
+    if (u < p.main_tiles) { w.tile = u; w.k0 = 0; w.k1 = kiters; w.split = 0; }
+    else {
+        const int t = u - p.main_tiles, s = t % p.ksplit;
+        w.tile = p.main_tiles + t / p.ksplit;
+        w.k0 = (int)((long long)kiters * s / p.ksplit);
+        w.k1 = (int)((long long)kiters * (s + 1) / p.ksplit);
+        w.split = 1;
+    }
+    return w;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
@@ -106,15 +123,18 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int total_units = p.main_tiles + (total_tiles - p.main_tiles) * p.ksplit;
+    const int kiters = p.nseg * p.taps * p.kblocks;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------------------------------------ TMA producer
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int n0 = (tile % p.num_n_tiles) * BN;
-                const int mt = tile / p.num_n_tiles + p.m_tile_begin;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+                const WorkUnit wu = decode_unit(p, unit, kiters);
+                const int n0 = (wu.tile % p.num_n_tiles) * BN;
+                const int mt = wu.tile / p.num_n_tiles;
                 int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
                 if (p.spatial) {
                     img = mt / tiles_per_img;
@@ -122,36 +142,37 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                     y0 = (r / p.tiles_x) * p.th;
                     x0 = (r % p.tiles_x) * p.tw;
                 }
-                for (int seg = 0; seg < p.nseg; ++seg)
-                    for (int tap = 0; tap < p.taps; ++tap)
-                        for (int kb = 0; kb < p.kblocks; ++kb) {
-                            mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 1);
-                            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                            uint8_t* sb = sa + A_STAGE_BYTES;
-                            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                            if (p.spatial)
-                                tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
-                            else
-                                tma_load_2d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, m0);
-                            tma_load_2d(sb, &maps.b[seg], &full[stage], (tap * p.kblocks + kb) * BLOCK_K, n0);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                        }
+                // K index -> (segment, tap, 32-channel block), kb fastest
+                int kb = wu.k0 % p.kblocks, tap = (wu.k0 / p.kblocks) % p.taps, seg = wu.k0 / (p.kblocks * p.taps);
+                for (int k = wu.k0; k < wu.k1; ++k) {
+                    mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    if (p.spatial)
+                        tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
+                    else
+                        tma_load_2d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, m0);
+                    tma_load_2d(sb, &maps.b[seg], &full[stage], (tap * p.kblocks + kb) * BLOCK_K, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++kb == p.kblocks) { kb = 0; if (++tap == p.taps) { tap = 0; ++seg; } }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BN, MAJOR_K, MAJOR_K);
-            const int kiters = p.nseg * p.taps * p.kblocks;
             int stage = 0; uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+                const WorkUnit wu = decode_unit(p, unit, kiters);
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tempty[acc], acc_phase ^ 1, p.err_flag, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int k = 0; k < kiters; ++k) {
+                for (int k = wu.k0; k < wu.k1; ++k) {
                     mbar_wait(&full[stage], phase, p.err_flag, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -160,7 +181,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                     for (int j = 0; j < BLOCK_K / 8; ++j) {
                         const uint64_t ad = make_smem_desc(sa + j * 32, 16, 1024);
                         const uint64_t bd = make_smem_desc(sb + j * 32, 16, 1024);
-                        mma_tf32(d_tmem, ad, bd, idesc, (k | j) != 0);
+                        mma_tf32(d_tmem, ad, bd, idesc, (k != wu.k0) || j != 0);
                     }
                     tc_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -181,11 +202,12 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         float st_sum[BN / 32], st_sq[BN / 32];
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+            const WorkUnit wu = decode_unit(p, unit, kiters);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int n0 = (tile % p.num_n_tiles) * BN;
-            const int mt = tile / p.num_n_tiles + p.m_tile_begin;
+            const int n0 = (wu.tile % p.num_n_tiles) * BN;
+            const int mt = wu.tile / p.num_n_tiles;
             int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
             if (p.spatial) {
                 img = mt / tiles_per_img;
@@ -193,6 +215,8 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 y0 = (r / p.tiles_x) * p.th;
                 x0 = (r % p.tiles_x) * p.tw;
             }
+            const bool reduce_out = p.accumulate || wu.split;       // K slices meet in D through reduce-add
+            const bool do_stats = p.stats_partial && !wu.split;     // (the host reduces the split rows separately)
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -223,7 +247,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    if (p.accumulate) {
+                    if (reduce_out) {
                         if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
                         else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
                     } else {
@@ -232,7 +256,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                     }
                     tma_store_commit();
                 }
-                if (p.stats_partial) {
+                if (do_stats) {
                     // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged rows
                     // (a 3x3 tap can pull in-image data into an out-of-image output row, so those rows are masked)
                     float s0 = 0.f, s1 = 0.f;
@@ -318,7 +342,7 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = cluster_id; tile < pair_tiles; tile += num_clusters) {
                 const int n0 = (tile % p.num_n_tiles) * BN;
-                const int mt = 2 * (tile / p.num_n_tiles) + (int)rank + p.m_tile_begin;
+                const int mt = 2 * (tile / p.num_n_tiles) + (int)rank;
                 int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
                 if (p.spatial) {
                     img = mt / tiles_per_img;                 // an odd tail m-tile lands in image index B: fully OOB -> zeros
@@ -387,7 +411,7 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int n0 = (tile % p.num_n_tiles) * BN;
-            const int mt = 2 * (tile / p.num_n_tiles) + (int)rank + p.m_tile_begin;
+            const int mt = 2 * (tile / p.num_n_tiles) + (int)rank;
             int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
             if (p.spatial) {
                 img = mt / tiles_per_img;
@@ -395,7 +419,7 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 y0 = (r / p.tiles_x) * p.th;
                 x0 = (r % p.tiles_x) * p.tw;
             }
-            const bool real_tile = mt < p.num_m_tiles + p.m_tile_begin;     // the odd tail pair has one phantom half
+            const bool real_tile = mt < p.num_m_tiles;     // the odd tail pair has one phantom half
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 24);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -716,17 +740,14 @@ int ensure_device_state() {
 }
 
 template <int BN>
-int launch_gemm(const GemmMaps& maps, const GemmParams& p, cudaStream_t st) {
+int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
         TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    grid = grid / p.num_n_tiles * p.num_n_tiles;          // every CTA keeps one n-tile (see stats_partial)
-    conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+    conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -769,6 +790,7 @@ TF_API int tf_debug_set(int key, int value) {
 }
 
 #include "tf_conv_gemm.h"
+#include "tf_elementwise.h"
 namespace tfg {
 
 int debug_flag(int key) { return (key >= 0 && key < 8) ? g_debug[key] : 0; }
@@ -832,54 +854,56 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
             if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, bw, bh))) return rc;
         }
     }
-    // One launch covers m-tiles [m_begin, m_begin + m_count) with tile width bn; returns the number of
-    // statistics partial rows it writes.
-    const int total_m_tiles = p.num_m_tiles;
-    auto launch = [&](int bn, int m_begin, int m_count, float* stats_ptr, int* stats_rows) -> int {
-        GemmParams q = p;
-        q.num_m_tiles = m_count; q.m_tile_begin = m_begin; q.num_n_tiles = Cout / bn; q.stats_partial = stats_ptr;
+    const bool two_cta = BN == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || TWO_CTA_DEFAULT) && p.num_m_tiles >= 2;
+    for (int s = 0; s < p.nseg; ++s)
+        if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, two_cta ? 128 : BN))) return rc;
+    int stats_rows = 0;
+    if (two_cta) {
         // 2-CTA (cta_group::2) kernel for 256-wide tiles: each CTA of the pair stages half (128 rows) of the B tile
-        const bool two_cta = bn == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || TWO_CTA_DEFAULT) && q.num_m_tiles >= 2;
-        for (int s = 0; s < q.nseg; ++s)
-            if (int e = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, two_cta ? 128 : bn)) return e;
-        if (two_cta) return launch_gemm2(maps, q, stats_rows, st);
-        const int tiles = q.num_m_tiles * q.num_n_tiles;
-        const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / q.num_n_tiles * q.num_n_tiles;
-        if (stats_rows) *stats_rows = grid / q.num_n_tiles * 4;
-        if (bn == 256) return launch_gemm<256>(maps, q, st);
-        if (bn == 128) return launch_gemm<128>(maps, q, st);
-        return launch_gemm<64>(maps, q, st);
-    };
-    // Tail-wave split (EXPERIMENTAL, off unless tf_debug_set(3, 1)): when the last round over the SMs is mostly empty
-    // (e.g. 300 tiles on 148 SMs = 2.03 waves) the leftover m-tiles go to a second launch with narrower tiles.
-    // Measured on B200 for the layer-3 3x3 conv: 84.9 us with the split vs 77.9 us without -- the second launch's
-    // prologue and the smem-bound N=64 tiles cost more than the idle tail; kept for the 2-CTA / PDL follow-up.
-    int m_main = total_m_tiles, bn_tail = 0;
-    if (g_debug[3]) {
-        const long long tiles = (long long)total_m_tiles * (Cout / BN);
-        const long long full = tiles / g_num_sms;
-        if (full >= 1 && tiles % g_num_sms != 0) {
-            const int m_split = (int)((full * g_num_sms) / (Cout / BN));
-            const int tail_m = total_m_tiles - m_split;
-            const double pen[3] = {1.0, 1.45, 2.2};
-            const double base = (double)(full + 1) * BN * pen[BN == 256 ? 0 : (BN == 128 ? 1 : 2)];
-            double best_cost = base;
-            for (int cand = BN / 2; cand >= 64; cand >>= 1) {
-                if (Cout % cand) continue;
-                const long long tt = (long long)tail_m * (Cout / cand);
-                const double c = (double)full * BN * pen[BN == 256 ? 0 : (BN == 128 ? 1 : 2)] +
-                                 (double)((tt + g_num_sms - 1) / g_num_sms) * cand * pen[cand == 256 ? 0 : (cand == 128 ? 1 : 2)];
-                if (c < 0.93 * best_cost && m_split > 0) { best_cost = c; m_main = m_split; bn_tail = cand; }
-            }
+        p.main_tiles = p.num_m_tiles * p.num_n_tiles; p.ksplit = 1;
+        if ((rc = launch_gemm2(maps, p, &stats_rows, st))) return rc;
+        if (a.stats_blocks) *a.stats_blocks = stats_rows;
+        return TF_OK;
+    }
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / p.num_n_tiles * p.num_n_tiles;
+    stats_rows = grid / p.num_n_tiles * 4;
+    // ---- tail-wave split-K plan: the m-tiles that do not fill a whole round over the CTAs are cut along K.
+    //      Only for a plain epilogue (K slices cannot be scaled / clamped separately) and a K loop worth cutting.
+    p.main_tiles = tiles; p.ksplit = 1;
+    long long tail_pix0 = -1;                            // first output pixel of the split region (contiguous to the end)
+    const int kiters = p.nseg * p.taps * p.kblocks;
+    const bool plain = !a.scale && !a.shift && !a.relu && !a.round_out;
+    if (plain && g_debug[3] != 2 && kiters >= 16 && tiles > grid && tiles % grid != 0) {
+        const int full = tiles / grid;
+        int main_m = (int)((long long)full * grid / p.num_n_tiles);
+        if (p.spatial) main_m -= main_m % p.tiles_x;      // the split region starts at a tile-row boundary
+        const int tail_tiles = (p.num_m_tiles - main_m) * p.num_n_tiles;
+        int ks = grid / tail_tiles;
+        if (ks > kiters / 8) ks = kiters / 8;
+        // rounds: ceil(main / grid) whole tiles + one round of 1/ks tiles (+ ~0.2 of a tile for the extra epilogue / launches)
+        const int main_rounds = (main_m * p.num_n_tiles + grid - 1) / grid;
+        if (ks >= 2 && main_m > 0 && main_rounds + 1.0 / ks + 0.2 < 0.92 * (double)((tiles + grid - 1) / grid)) {     // worth >= 8 %
+            p.main_tiles = main_m * p.num_n_tiles; p.ksplit = ks;
+            if (p.spatial) {
+                const int tpi = p.tiles_x * p.tiles_y, img = main_m / tpi, ty = (main_m % tpi) / p.tiles_x;
+                tail_pix0 = ((long long)img * Ho + (long long)ty * p.th) * Wo;
+            } else tail_pix0 = (long long)main_m * BLOCK_M;
+            if (!p.accumulate)
+                TF_CHECK_CUDA(cudaMemsetAsync(a.y + tail_pix0 * Cout, 0, (size_t)(Mtot - tail_pix0) * Cout * sizeof(float), st));
         }
     }
-    int rows_main = 0, rows_tail = 0;
-    if ((rc = launch(BN, 0, m_main, a.stats_partial, &rows_main))) return rc;
-    if (bn_tail) {
-        float* sp = a.stats_partial ? a.stats_partial + (size_t)rows_main * 2 * Cout : nullptr;
-        if ((rc = launch(bn_tail, m_main, total_m_tiles - m_main, sp, &rows_tail))) return rc;
+    if (BN == 256) rc = launch_gemm<256>(maps, p, grid, st);
+    else if (BN == 128) rc = launch_gemm<128>(maps, p, grid, st);
+    else rc = launch_gemm<64>(maps, p, grid, st);
+    if (rc) return rc;
+    if (a.stats_partial && tail_pix0 >= 0) {
+        // BN statistics of the split rows (their epilogues only saw partial sums): appended partial rows
+        int nb = 0;
+        if ((rc = tfe::column_stats(a.y + tail_pix0 * Cout, Mtot - tail_pix0, Cout, a.stats_partial + (size_t)stats_rows * 2 * Cout, &nb, st))) return rc;
+        stats_rows += nb;
     }
-    if (a.stats_blocks) *a.stats_blocks = rows_main + rows_tail;
+    if (a.stats_blocks) *a.stats_blocks = stats_rows;
     return TF_OK;
 }
 

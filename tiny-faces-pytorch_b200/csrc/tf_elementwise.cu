@@ -567,6 +567,14 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
+int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st) {
+    TF_REQUIRE(C % 4 == 0 && C <= 1024 && M > 0, "column_stats: C=%d unsupported", C);
+    const int nb = reduce_blocks(M, C);
+    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    TF_LAUNCH_CHECK();
+    *nblk = nb;
+    return TF_OK;
+}
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st) {
     TF_REQUIRE(C % 4 == 0 && C <= 1024, "column_sum: C=%d unsupported", C);
     const int nb = reduce_blocks(M, C);

@@ -19,6 +19,8 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
 int bn_backward(const float* dout, const float* act, const unsigned int* mask /* either may gate dout */, const float* y, const float* save_mean, const float* save_rstd,
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
                 float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st);
+// per-channel (sum, sum^2) partials of y[M, C] -> partial[*nblk][2][C] (bn_finalize_train reduces them)
+int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st);
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st);
 int masked_add(const float* a, const float* act, const float* b, long long n, float* out, cudaStream_t st);
 int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,

@@ -15,13 +15,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tiny-faces-pytorch_b200"))
 sys.path.insert(0, ROOT)
 
+# keys: 3:2 = tail split-K off; 4:1 = 2-CTA GEMM; 5:1/2/3 = weight-gradient schedule 0/1/2; 6:1 = chain on the caller's stream
 DEFAULT = [
-    "legacy=5:1,6:1",          # wgrad forked before its dgrad, chain on the caller's stream (round-1 behaviour)
-    "prio_mode0=5:1",          # + high-priority chain stream
-    "prio_mode1=5:2",          # wgrad enqueued after its dgrad
-    "prio_mode2=5:3",          # deferred to the next block's bn3 backward (new default)
-    "noprio_mode2=5:3,6:1",
-    "prio_mode2_2cta=5:3,4:1",
+    "legacy=5:1,6:1,3:2",      # round-1 behaviour: wgrad forked before its dgrad, no priority stream, no split-K
+    "legacy_splitk=5:1,6:1",
+    "default=",
+    "default_2cta=4:1",
 ]
 
 
@@ -60,6 +59,12 @@ def run_case(spec, steps=8, warmup=3, B=8, H=960, W=1280):
         opt.zero_grad()
         loss.backward()
         ev[3].record()
+        if it == 0:                            # identical weights in every configuration: these must agree
+            named = dict(model.named_parameters())
+            first = dict(loss=float(loss), **{k: float(named[k].grad.double().abs().sum()) for k in
+                         ("model.conv1.weight", "model.layer1.0.conv2.weight", "model.layer2.3.conv1.weight",
+                          "model.layer3.0.downsample.0.weight", "model.layer3.11.conv2.weight",
+                          "model.layer3.22.conv3.weight", "model.layer3.22.bn3.weight", "score_res4.weight")})
         opt.step()
         ev[4].record()
         if it >= warmup:
@@ -79,7 +84,8 @@ def run_case(spec, steps=8, warmup=3, B=8, H=960, W=1280):
     t1.record()
     torch.cuda.synchronize()
     return dict(name=name, flags=flags, ms_per_step=t0.elapsed_time(t1) / steps, fwd_ms=phases[0], loss_ms=phases[1],
-                bwd_ms=phases[2], sgd_ms=phases[3], loss=float(loss), grad_abs_sum=gsum, flag=ops.gemm_error_flag())
+                bwd_ms=phases[2], sgd_ms=phases[3], loss=float(loss), grad_abs_sum=gsum, flag=ops.gemm_error_flag(),
+                first_step=first)
 
 
 if __name__ == "__main__":
@@ -99,4 +105,4 @@ if __name__ == "__main__":
                 rec = dict(name=spec, timeout=True)
             f.write(json.dumps(rec) + "\n")
             f.flush()
-            print(json.dumps(rec)[:600])
+            print(json.dumps(rec)[:1200])
