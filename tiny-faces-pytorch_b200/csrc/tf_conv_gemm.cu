@@ -217,6 +217,11 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
             const bool reduce_out = p.accumulate || wu.split;       // K slices meet in D through reduce-add
             const bool do_stats = p.stats_partial && !wu.split;     // (the host reduces the split rows separately)
+            uint32_t rowmask = 0xffffffffu;                         // bit l: row l of this warp is a pixel of the image
+            if (p.spatial && do_stats) {
+                const int rw = q * 32 + lane;
+                rowmask = __ballot_sync(0xffffffffu, x0 + rw % p.tw < p.img_w && y0 + rw / p.tw < p.img_h);
+            }
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -258,13 +263,12 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 }
                 if (do_stats) {
                     // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged rows
-                    // (a 3x3 tap can pull in-image data into an out-of-image output row, so those rows are masked)
+                    // (a 3x3 tap can pull in-image data into an out-of-image output row: rowmask drops those rows)
                     float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
+#pragma unroll
                     for (int l = 0; l < 32; ++l) {
-                        const int rw = q * 32 + l;
                         float v = *reinterpret_cast<const float*>(buf + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
-                        if (p.spatial && (x0 + rw % p.tw >= p.img_w || y0 + rw / p.tw >= p.img_h)) v = 0.f;
+                        if (!((rowmask >> l) & 1u)) v = 0.f;
                         s0 += v; s1 += v * v;
                     }
                     st_sum[chunk] += s0; st_sq[chunk] += s1;
@@ -420,6 +424,11 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 x0 = (r % p.tiles_x) * p.tw;
             }
             const bool real_tile = mt < p.num_m_tiles;     // the odd tail pair has one phantom half
+            uint32_t rowmask = 0xffffffffu;
+            if (p.spatial && p.stats_partial) {
+                const int rw = q * 32 + lane;
+                rowmask = __ballot_sync(0xffffffffu, x0 + rw % p.tw < p.img_w && y0 + rw / p.tw < p.img_h);
+            }
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 24);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -462,11 +471,10 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 }
                 if (p.stats_partial) {
                     float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
+#pragma unroll
                     for (int l = 0; l < 32; ++l) {
-                        const int rw = q * 32 + l;
                         float v = *reinterpret_cast<const float*>(buf + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
-                        if (p.spatial && (x0 + rw % p.tw >= p.img_w || y0 + rw / p.tw >= p.img_h)) v = 0.f;
+                        if (!((rowmask >> l) & 1u)) v = 0.f;
                         s0 += v; s1 += v * v;
                     }
                     st_sum[chunk] += s0; st_sq[chunk] += s1;
@@ -829,6 +837,11 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
     p.stats_partial = a.stats_partial; p.cout = Cout; p.img_w = Wo; p.img_h = Ho;
+    if (g_debug[7] && !p.stats_partial) {          // probe: time the BN-statistics epilogue without the model around it
+        static float* scratch = nullptr;
+        if (!scratch) TF_CHECK_CUDA(cudaMalloc(&scratch, (size_t)2 * 592 * 2 * 1024 * sizeof(float)));
+        p.stats_partial = scratch;
+    }
     p.err_flag = g_err_flag;
     p.num_n_tiles = Cout / BN;
     const float* as[3] = {a.x, a.x_lo, a.x};
@@ -897,10 +910,10 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     else if (BN == 128) rc = launch_gemm<128>(maps, p, grid, st);
     else rc = launch_gemm<64>(maps, p, grid, st);
     if (rc) return rc;
-    if (a.stats_partial && tail_pix0 >= 0) {
+    if (p.stats_partial && tail_pix0 >= 0) {
         // BN statistics of the split rows (their epilogues only saw partial sums): appended partial rows
         int nb = 0;
-        if ((rc = tfe::column_stats(a.y + tail_pix0 * Cout, Mtot - tail_pix0, Cout, a.stats_partial + (size_t)stats_rows * 2 * Cout, &nb, st))) return rc;
+        if ((rc = tfe::column_stats(a.y + tail_pix0 * Cout, Mtot - tail_pix0, Cout, p.stats_partial + (size_t)stats_rows * 2 * Cout, &nb, st))) return rc;
         stats_rows += nb;
     }
     if (a.stats_blocks) *a.stats_blocks = stats_rows;

@@ -59,6 +59,10 @@ __device__ __forceinline__ void store_act(float* out, float* out_lo, long long i
 //   mode 1: (sum g, sum g*xhat), g = dout (* [act > 0])       -- BN backward
 //   mode 2: (sum y, 0)                                        -- bias gradient
 // ------------------------------------------------------------------------------------------------
+// No shared memory on purpose: these kernels run next to side-stream weight-gradient GEMM CTAs that own all but ~1 KB of
+// an SM's shared memory -- a block with even a few KB of static smem would wait for those CTAs to retire instead of
+// overlapping them.  Thread t works on float4 channel group t / lanes of row lane t % lanes (lanes = 1024 / C rows per
+// block, a power of two <= 16, so the row lanes of one channel group sit in adjacent lanes of one warp).
 template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                                const float* __restrict__ act,
@@ -66,18 +70,17 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, long long M, int C,
                                                                float* __restrict__ partial) {
-    const int groups = C / 4;                       // float4 channel groups (<= 256)
-    const int lanes = EW_THREADS / groups;          // row lanes per block
-    const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+    const int groups = C / 4;                       // float4 channel groups (16 .. 256, a power of two)
+    const int lanes = EW_THREADS / groups;          // row lanes per block (1 .. 16)
+    const int g = threadIdx.x / lanes, rl = threadIdx.x % lanes;
     float4 s0 = make_float4(0, 0, 0, 0), s1 = s0;
     float4 mu = s0, rs = s0;
     if (MODE == 1) { mu = ld4(mean + g * 4); rs = ld4(rstd + g * 4); }
-    if (rl < lanes) {
+    {
         const long long step = (long long)gridDim.x * lanes;
         long long r = (long long)blockIdx.x * lanes + rl;
         if (MODE == 1 && mask) {
-            // 4 rows per iteration with every load issued up front: this kernel shares the SMs with side-stream GEMM
-            // CTAs (few resident warps), so the bytes in flight have to come from each thread
+            // 4 rows per iteration with every load issued up front: the bytes in flight have to come from each thread
             for (; r + 3 * step < M; r += 4 * step) {
                 float4 v[4], y[4]; unsigned int nib[4];
 #pragma unroll
@@ -112,56 +115,64 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
             }
         }
     }
-    __shared__ float4 sm0[EW_THREADS], sm1[EW_THREADS];
-    sm0[threadIdx.x] = s0; sm1[threadIdx.x] = s1;
-    __syncthreads();
+    for (int o = lanes >> 1; o > 0; o >>= 1) {       // row lanes of a group are adjacent lanes of the warp
+        s0.x += __shfl_xor_sync(0xffffffffu, s0.x, o); s0.y += __shfl_xor_sync(0xffffffffu, s0.y, o);
+        s0.z += __shfl_xor_sync(0xffffffffu, s0.z, o); s0.w += __shfl_xor_sync(0xffffffffu, s0.w, o);
+        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+        s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+    }
     if (rl == 0) {
-        for (int l = 1; l < lanes; ++l) {
-            float4 t0 = sm0[l * groups + g], t1 = sm1[l * groups + g];
-            s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
-            s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
-        }
         float* p = partial + (size_t)blockIdx.x * 2 * C;
         st4(p + g * 4, s0);
         st4(p + C + g * 4, s1);
     }
 }
 
-// sum the per-block partials of 32 channels with FIN_LANES lanes per channel (fp64), result valid for threadIdx.y == 0
-constexpr int FIN_LANES = 32;
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
-    __shared__ double sh[2][FIN_LANES][32];
-    s = 0; q = 0;
-    if (c < C)
-        for (int b = threadIdx.y; b < nblk; b += FIN_LANES) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
-    sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = q;
-    __syncthreads();
-    if (threadIdx.y == 0)
-        for (int l = 1; l < FIN_LANES; ++l) { s += sh[0][l][threadIdx.x]; q += sh[1][l][threadIdx.x]; }
+// Sum of the per-block partials, again without shared memory: a warp owns 4 channels (one float4 column of the
+// [nblk][2][C] partial table), its 32 lanes stride over the rows, fp64 butterfly at the end.  Result valid in lane 0:
+// s[j], q[j] for channel c4 + j.  Blocks are (32, FIN_WARPS): C / (4 * FIN_WARPS) blocks cover C channels.
+constexpr int FIN_WARPS = 8;
+__device__ __forceinline__ void reduce_partials4(const float* __restrict__ partial, int nblk, int C, int c4, double (&s)[4], double (&q)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s[j] = 0; q[j] = 0; }
+    if (c4 < C)
+        for (int b = threadIdx.x; b < nblk; b += 32) {
+            const float4 v = ld4(partial + (size_t)b * 2 * C + c4), w = ld4(partial + (size_t)b * 2 * C + C + c4);
+            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+            q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
+        }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s[j] += __shfl_xor_sync(0xffffffffu, s[j], o); q[j] += __shfl_xor_sync(0xffffffffu, q[j], o); }
 }
 // BN forward finalize (training): batch mean / biased var -> scale, shift, saved mean / rstd, running stats
-__global__ void __launch_bounds__(1024) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(32 * FIN_WARPS) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-    const int c = blockIdx.x * 32 + threadIdx.x;
-    double s, q;
-    reduce_partials(partial, nblk, C, c, s, q);
-    if (threadIdx.y != 0 || c >= C) return;
-    const double mean = s / (double)M;
-    double var = q / (double)M - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * rstd;
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mean * sc;
-    save_mean[c] = (float)mean;
-    save_rstd[c] = rstd;
-    if (run_mean) {
-        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
-        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
+    const int c4 = (blockIdx.x * FIN_WARPS + threadIdx.y) * 4;
+    double s[4], q[4];
+    reduce_partials4(partial, nblk, C, c4, s, q);
+    if (threadIdx.x != 0 || c4 >= C) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        const double mean = s[j] / (double)M;
+        double var = q[j] / (double)M - mean * mean;
+        if (var < 0) var = 0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float sc = gamma[c] * rstd;
+        scale[c] = sc;
+        shift[c] = beta[c] - (float)mean * sc;
+        save_mean[c] = (float)mean;
+        save_rstd[c] = rstd;
+        if (run_mean) {
+            const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+            run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
+        }
     }
 }
 // eval: scale / shift from the running statistics
@@ -187,27 +198,33 @@ __global__ void bn_eval_batched_kernel(const tfe::BnEvalJob* __restrict__ jobs, 
     j.shift[c] = j.beta[c] - j.run_mean[c] * sc;
 }
 // BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
-__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(32 * FIN_WARPS) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef /* [3][C]: gamma*rstd, mean(g), mean(g*xhat) */) {
-    const int c = blockIdx.x * 32 + threadIdx.x;
-    double s, q;
-    reduce_partials(partial, nblk, C, c, s, q);
-    if (threadIdx.y != 0 || c >= C) return;
-    if (dgamma) dgamma[c] = (float)q;
-    if (dbeta) dbeta[c] = (float)s;
-    coef[c] = gamma[c] * rstd[c];
-    coef[C + c] = (float)(s / (double)M);
-    coef[2 * C + c] = (float)(q / (double)M);
+    const int c4 = (blockIdx.x * FIN_WARPS + threadIdx.y) * 4;
+    double s[4], q[4];
+    reduce_partials4(partial, nblk, C, c4, s, q);
+    if (threadIdx.x != 0 || c4 >= C) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        if (dgamma) dgamma[c] = (float)q[j];
+        if (dbeta) dbeta[c] = (float)s[j];
+        coef[c] = gamma[c] * rstd[c];
+        coef[C + c] = (float)(s[j] / (double)M);
+        coef[2 * C + c] = (float)(q[j] / (double)M);
+    }
 }
-__global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
+__global__ void __launch_bounds__(32 * FIN_WARPS) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
                                        float* __restrict__ out) {
-    const int c = blockIdx.x * 32 + threadIdx.x;
-    double s, q;
-    reduce_partials(partial, nblk, C, c, s, q);
-    if (threadIdx.y != 0 || c >= Cout) return;
-    out[c] = (float)s;
+    const int c4 = (blockIdx.x * FIN_WARPS + threadIdx.y) * 4;
+    double s[4], q[4];
+    reduce_partials4(partial, nblk, C, c4, s, q);
+    if (threadIdx.x != 0) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (c4 + j < Cout) out[c4 + j] = (float)s[j];
 }
 
 // out = act( y*scale + shift (+ res | + res*rscale + rshift) ); optional 1-bit ReLU mask of the result
@@ -530,7 +547,7 @@ static int reduce_blocks(long long M, int C) {
 int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st) {
-    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
+    bn_finalize_train_kernel<<<(C + 4 * FIN_WARPS - 1) / (4 * FIN_WARPS), dim3(32, FIN_WARPS), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -557,10 +574,10 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
 int bn_backward(const float* dout, const float* act, const unsigned int* mask, const float* y, const float* save_mean, const float* save_rstd,
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
                 float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st) {
-    TF_REQUIRE(C % 4 == 0 && C <= 1024, "bn_backward: C=%d unsupported", C);
+    TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, partial);
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<(C + 4 * FIN_WARPS - 1) / (4 * FIN_WARPS), dim3(32, FIN_WARPS), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
                                                                 gmask_out, mode);
@@ -568,7 +585,7 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
     return TF_OK;
 }
 int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st) {
-    TF_REQUIRE(C % 4 == 0 && C <= 1024 && M > 0, "column_stats: C=%d unsupported", C);
+    TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0 && M > 0, "column_stats: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
     TF_LAUNCH_CHECK();
@@ -576,10 +593,10 @@ int column_stats(const float* y, long long M, int C, float* partial, int* nblk, 
     return TF_OK;
 }
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st) {
-    TF_REQUIRE(C % 4 == 0 && C <= 1024, "column_sum: C=%d unsupported", C);
+    TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "column_sum: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out);
+    colsum_finalize_kernel<<<(C + 4 * FIN_WARPS - 1) / (4 * FIN_WARPS), dim3(32, FIN_WARPS), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

@@ -148,7 +148,7 @@ struct Model {
     BnP bnp(const std::string& p, int C) { BnP b; b.gamma = add(p + ".weight"); b.beta = add(p + ".bias"); b.rm = add(p + ".running_mean"); b.rv = add(p + ".running_var"); b.C = C; return b; }
 
     explicit Model(int templates) : T(templates), Cn(5 * templates) {
-        Cp = (int)tf_align_up((size_t)Cn, 64);
+        Cp = 64; while (Cp < Cn) Cp *= 2;                        // padded head width (power of two: column reductions)
         stem = conv("model.conv1", 3, 64, 7, 2);
         stem_bn = bnp("model.bn1", 64);
         const int nblocks[3] = {3, 4, 23}, planes[3] = {64, 128, 256}, strides[3] = {1, 2, 2};

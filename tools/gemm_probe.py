@@ -23,12 +23,10 @@ CASES_R1B = [
     ("fprop+2cta", 2, 15, 20, 256, 256, 3), ("fprop+2cta", 1, 63, 63, 256, 256, 3), ("fprop+2cta", 3, 9, 16, 256, 512, 1),
 ]
 CASES = [
-    ("time+nosplit", 8, 60, 80, 1024, 256, 1), ("time", 8, 60, 80, 1024, 256, 1), ("time+2cta", 8, 60, 80, 1024, 256, 1),
-    ("time+nosplit", 8, 60, 80, 256, 256, 3), ("time", 8, 60, 80, 256, 256, 3), ("time+2cta", 8, 60, 80, 256, 256, 3),
-    ("time", 8, 60, 80, 256, 1024, 1), ("time+2cta", 8, 60, 80, 256, 1024, 1),
-    ("time+nosplit", 8, 120, 160, 128, 128, 3), ("time", 8, 120, 160, 128, 128, 3),
-    ("time+nosplit", 8, 240, 320, 64, 64, 3), ("time", 8, 240, 320, 64, 64, 3),
-    ("time", 8, 120, 160, 512, 128, 1), ("time", 8, 240, 320, 256, 64, 1),
+    ("time", 8, 60, 80, 1024, 256, 1), ("time+stats", 8, 60, 80, 1024, 256, 1),
+    ("time", 8, 60, 80, 256, 256, 3), ("time+stats", 8, 60, 80, 256, 256, 3), ("time+nosplit+stats", 8, 60, 80, 256, 256, 3),
+    ("time", 8, 60, 80, 256, 1024, 1), ("time+stats", 8, 60, 80, 256, 1024, 1), ("time+2cta+stats", 8, 60, 80, 256, 1024, 1),
+    ("time+stats", 8, 120, 160, 128, 512, 1), ("time+stats", 8, 240, 320, 64, 256, 1),
 ]
 CASES_OLD2 = [
     ("wgrad", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 128, 128, 1),
@@ -43,6 +41,9 @@ def run_case(kind, B, H, W, Cin, Cout, k):
     if kind.endswith("+plain"):
         _lib.lib().tf_debug_set(0, 1)
         kind = "wgrad"
+    if kind.endswith("+stats"):                   # force the BN-statistics epilogue
+        _lib.lib().tf_debug_set(7, 1)
+        kind = kind[:-6]
     if kind.endswith("+nosplit"):                 # tail-wave split-K off
         _lib.lib().tf_debug_set(3, 2)
         kind = kind[:-8]
