@@ -63,6 +63,8 @@ template <int BN> struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int WGRAD_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;   // epilogue overlays stage 0
+    static_assert(2 * EPI_BUF_BYTES <= STAGES * STAGE_BYTES, "wgrad epilogue buffers must fit in the operand ring");
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -72,11 +74,75 @@ __device__ __forceinline__ int tap_dy(int taps, int tap) { return taps == 9 ? ta
 
 __device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-__device__ __forceinline__ void store_row_swizzled(uint8_t* buf, int row, const uint32_t (&r)[32]) {
+// The staging buffers are reached through 32-bit shared-window addresses with explicit st.shared / ld.shared: a generic
+// pointer derived from the aligned dynamic-smem base makes the compiler emit generic LD/ST (seen in the round-1 SASS),
+// which are slower than LDS/STS and were the top long-scoreboard stall of the statistics epilogue.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void store_row_swizzled(uint32_t buf_s, int row, const uint32_t (&r)[32]) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        uint4 v = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-        *reinterpret_cast<uint4*>(buf + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+    for (int c = 0; c < 8; ++c)
+        sts128(buf_s + row * 128 + ((c ^ (row & 7)) << 4), r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+}
+
+// One 32-row x 32-column chunk of an accumulator tile, by one epilogue warp (lane = row): optional fused per-channel
+// scale / shift / ReLU / TF32 rounding (FUSED: the inference path), swizzled staging, TMA store or reduce-add of the
+// warp's box, optional per-column (sum, sum^2) of the staged values for the BN statistics.
+template <bool FUSED, bool SPATIAL>
+__device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const GemmParams& p, const CUtensorMap* dmap, uint8_t* buf,
+                                               int lane, int nb, bool reduce_out, bool do_stats, uint32_t rowmask,
+                                               int c1, int c2, int c3, float& ssum, float& ssq) {
+    if (FUSED) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]);
+            if (p.scale) v *= __ldg(p.scale + nb + j);
+            if (p.shift) v += __ldg(p.shift + nb + j);
+            if (p.relu) v = fmaxf(v, 0.f);
+            if (p.round_out) v = tf_round_tf32(v);
+            r[j] = __float_as_uint(v);
+        }
+    }
+    const uint32_t buf_s = smem_u32(buf);
+    if (lane == 0) tma_store_wait_read<1>();         // the store that last used this buffer has drained
+    __syncwarp();
+    store_row_swizzled(buf_s, lane, r);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        if (reduce_out) {
+            if (SPATIAL) tma_reduce_add_4d(dmap, buf, nb, c1, c2, c3);
+            else         tma_reduce_add_2d(dmap, buf, nb, c1);
+        } else {
+            if (SPATIAL) tma_store_4d(dmap, buf, nb, c1, c2, c3);
+            else         tma_store_2d(dmap, buf, nb, c1);
+        }
+        tma_store_commit();
+    }
+    if (do_stats) {
+        // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged rows, all issued before
+        // the first use; rowmask drops rows outside the image (a 3x3 tap can pull in-image data into such a row)
+        float v[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+            v[l] = lds32(buf_s + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
+        if (SPATIAL && rowmask != 0xffffffffu) {
+#pragma unroll
+            for (int l = 0; l < 32; ++l) if (!((rowmask >> l) & 1u)) v[l] = 0.f;
+        }
+        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; l += 2) {
+            s0 += v[l]; t0 = fmaf(v[l], v[l], t0);
+            s1 += v[l + 1]; t1 = fmaf(v[l + 1], v[l + 1], t1);
+        }
+        ssum += s0 + s1; ssq += t0 + t1;
     }
 }
 
@@ -94,7 +160,7 @@ __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u, int 
     return w;
 }
 
-template <int BN>
+template <int BN, bool FUSED, bool SPATIAL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -136,7 +202,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 const int n0 = (wu.tile % p.num_n_tiles) * BN;
                 const int mt = wu.tile / p.num_n_tiles;
                 int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
-                if (p.spatial) {
+                if (SPATIAL) {
                     img = mt / tiles_per_img;
                     const int r = mt % tiles_per_img;
                     y0 = (r / p.tiles_x) * p.th;
@@ -149,7 +215,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                    if (p.spatial)
+                    if (SPATIAL)
                         tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
                     else
                         tma_load_2d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, m0);
@@ -197,7 +263,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         uint8_t* wbuf = epi + q * 2 * 4096;
         int wx = 0, wy = 0;                     // position of the warp's 32 rows inside a spatial patch
-        if (p.spatial) { wy = (q * 32) / p.tw; wx = (q * 32) % p.tw; }
+        if (SPATIAL) { wy = (q * 32) / p.tw; wx = (q * 32) % p.tw; }
         int it = 0, ebuf = 0;
         float st_sum[BN / 32], st_sq[BN / 32];
 #pragma unroll
@@ -209,7 +275,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const int n0 = (wu.tile % p.num_n_tiles) * BN;
             const int mt = wu.tile / p.num_n_tiles;
             int m0 = mt * BLOCK_M, img = 0, x0 = 0, y0 = 0;
-            if (p.spatial) {
+            if (SPATIAL) {
                 img = mt / tiles_per_img;
                 const int r = mt % tiles_per_img;
                 y0 = (r / p.tiles_x) * p.th;
@@ -218,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             const bool reduce_out = p.accumulate || wu.split;       // K slices meet in D through reduce-add
             const bool do_stats = p.stats_partial && !wu.split;     // (the host reduces the split rows separately)
             uint32_t rowmask = 0xffffffffu;                         // bit l: row l of this warp is a pixel of the image
-            if (p.spatial && do_stats) {
+            if (SPATIAL && do_stats) {
                 const int rw = q * 32 + lane;
                 rowmask = __ballot_sync(0xffffffffu, x0 + rw % p.tw < p.img_w && y0 + rw / p.tw < p.img_h);
             }
@@ -233,46 +299,9 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 tmem_ld_wait();                                              // this chunk's registers are valid
                 if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, rr[(chunk + 1) & 1]);
                 else { tc_fence_before(); mbar_arrive(&tempty[acc]); }        // accumulator stage fully read
-                if (p.scale || p.shift || p.relu || p.round_out) {
-                    const int nb = n0 + chunk * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(r[j]);
-                        if (p.scale) v *= __ldg(p.scale + nb + j);
-                        if (p.shift) v += __ldg(p.shift + nb + j);
-                        if (p.relu) v = fmaxf(v, 0.f);
-                        if (p.round_out) v = tf_round_tf32(v);
-                        r[j] = __float_as_uint(v);
-                    }
-                }
                 uint8_t* buf = wbuf + ebuf * 4096;
-                if (lane == 0) tma_store_wait_read<1>();         // the store that last used this buffer has drained
-                __syncwarp();
-                store_row_swizzled(buf, lane, r);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    if (reduce_out) {
-                        if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
-                        else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
-                    } else {
-                        if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
-                        else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
-                    }
-                    tma_store_commit();
-                }
-                if (do_stats) {
-                    // column sums of this warp's 32 rows: lane = channel, conflict-free reads of the staged rows
-                    // (a 3x3 tap can pull in-image data into an out-of-image output row: rowmask drops those rows)
-                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                    for (int l = 0; l < 32; ++l) {
-                        float v = *reinterpret_cast<const float*>(buf + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
-                        if (!((rowmask >> l) & 1u)) v = 0.f;
-                        s0 += v; s1 += v * v;
-                    }
-                    st_sum[chunk] += s0; st_sq[chunk] += s1;
-                }
+                epilogue_chunk<FUSED, SPATIAL>(r, p, &maps.d, buf, lane, n0 + chunk * 32, reduce_out, do_stats, rowmask,
+                                               SPATIAL ? x0 + wx : m0 + q * 32, y0 + wy, img, st_sum[chunk], st_sq[chunk]);
                 ebuf ^= 1;
             }
         }
@@ -441,44 +470,11 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, rr[(chunk + 1) & 1]);
                 else { tc_fence_before(); mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[acc]), 0)); }
                 if (!real_tile) continue;
-                if (p.scale || p.shift || p.relu || p.round_out) {
-                    const int nb = n0 + chunk * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float v = __uint_as_float(r[j]);
-                        if (p.scale) v *= __ldg(p.scale + nb + j);
-                        if (p.shift) v += __ldg(p.shift + nb + j);
-                        if (p.relu) v = fmaxf(v, 0.f);
-                        if (p.round_out) v = tf_round_tf32(v);
-                        r[j] = __float_as_uint(v);
-                    }
-                }
                 uint8_t* buf = wbuf + ebuf * 4096;
-                if (lane == 0) tma_store_wait_read<1>();
-                __syncwarp();
-                store_row_swizzled(buf, lane, r);
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    if (p.accumulate) {
-                        if (p.spatial) tma_reduce_add_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
-                        else           tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
-                    } else {
-                        if (p.spatial) tma_store_4d(&maps.d, buf, n0 + chunk * 32, x0 + wx, y0 + wy, img);
-                        else           tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0 + q * 32);
-                    }
-                    tma_store_commit();
-                }
-                if (p.stats_partial) {
-                    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                    for (int l = 0; l < 32; ++l) {
-                        float v = *reinterpret_cast<const float*>(buf + l * 128 + (((lane >> 2) ^ (l & 7)) << 4) + ((lane & 3) << 2));
-                        if (!((rowmask >> l) & 1u)) v = 0.f;
-                        s0 += v; s1 += v * v;
-                    }
-                    st_sum[chunk] += s0; st_sq[chunk] += s1;
-                }
+                if (p.spatial) epilogue_chunk<true, true>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
+                                                          x0 + wx, y0 + wy, img, st_sum[chunk], st_sq[chunk]);
+                else           epilogue_chunk<true, false>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
+                                                           m0 + q * 32, 0, 0, st_sum[chunk], st_sq[chunk]);
                 ebuf ^= 1;
             }
         }
@@ -520,8 +516,11 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi = smem + STAGES * Cfg::STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(epi + 2 * EPI_BUF_BYTES);
+    // The epilogue staging buffers overlay the first operand stage: the epilogue only starts once every MMA (hence every
+    // operand read and every TMA load) has completed.  That keeps the CTA at 194 KB of shared memory, so ~30 KB stay free
+    // for the chain's elementwise blocks (1 KB reserved each) this kernel is meant to run next to.
+    uint8_t* epi = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
     uint64_t* empty = full + STAGES;
     uint64_t* tfull = empty + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
@@ -623,7 +622,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
                 if (store_thread) tma_store_wait_read<1>();
                 named_bar_sync_epi();
-                store_row_swizzled(buf, row, r);
+                store_row_swizzled(smem_u32(buf), row, r);
                 fence_proxy_async();
                 named_bar_sync_epi();
                 if (store_thread) {
@@ -747,17 +746,25 @@ int ensure_device_state() {
     return TF_OK;
 }
 
-template <int BN>
-int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
+template <int BN, bool FUSED, bool SPATIAL>
+int launch_gemm_variant(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, FUSED, SPATIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    conv_gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
+    conv_gemm_kernel<BN, FUSED, SPATIAL><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
     TF_LAUNCH_CHECK();
     return TF_OK;
+}
+// FUSED (per-channel scale / shift / ReLU / rounding in the epilogue) and SPATIAL (4-D patch tiles vs flat pixel rows)
+// are separate instantiations: the training path's plain epilogue stays small enough for the instruction cache
+template <int BN>
+int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
+    const bool fused = p.scale || p.shift || p.relu || p.round_out;
+    if (p.spatial) return fused ? launch_gemm_variant<BN, true, true>(maps, p, grid, st) : launch_gemm_variant<BN, false, true>(maps, p, grid, st);
+    return fused ? launch_gemm_variant<BN, true, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, false>(maps, p, grid, st);
 }
 int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cudaStream_t st) {
     static bool attr_set = false;
@@ -778,11 +785,11 @@ int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::WGRAD_SMEM_BYTES));
         attr_set = true;
     }
     const int grid = p.m_tiles * p.n_tiles * p.splits;
-    conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
+    conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, Cfg::WGRAD_SMEM_BYTES, st>>>(maps, p);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -887,7 +894,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     long long tail_pix0 = -1;                            // first output pixel of the split region (contiguous to the end)
     const int kiters = p.nseg * p.taps * p.kblocks;
     const bool plain = !a.scale && !a.shift && !a.relu && !a.round_out;
-    if (plain && g_debug[3] != 2 && kiters >= 16 && tiles > grid && tiles % grid != 0) {
+    if (plain && g_debug[3] != 2 && taps == 9 && kiters >= 16 && tiles > grid && tiles % grid != 0) {     // (measured: the two extra launches eat the gain of a K = 1024 1x1)
         const int full = tiles / grid;
         int main_m = (int)((long long)full * grid / p.num_n_tiles);
         if (p.spatial) main_m -= main_m % p.tiles_x;      // the split region starts at a tile-row boundary

@@ -128,51 +128,50 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
     }
 }
 
-// Sum of the per-block partials, again without shared memory: a warp owns 4 channels (one float4 column of the
-// [nblk][2][C] partial table), its 32 lanes stride over the rows, fp64 butterfly at the end.  Result valid in lane 0:
-// s[j], q[j] for channel c4 + j.  Blocks are (32, FIN_WARPS): C / (4 * FIN_WARPS) blocks cover C channels.
-constexpr int FIN_WARPS = 8;
-__device__ __forceinline__ void reduce_partials4(const float* __restrict__ partial, int nblk, int C, int c4, double (&s)[4], double (&q)[4]) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { s[j] = 0; q[j] = 0; }
-    if (c4 < C)
-        for (int b = threadIdx.x; b < nblk; b += 32) {
-            const float4 v = ld4(partial + (size_t)b * 2 * C + c4), w = ld4(partial + (size_t)b * 2 * C + C + c4);
-            s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-            q[0] += w.x; q[1] += w.y; q[2] += w.z; q[3] += w.w;
+// Sum of the per-block partials of 32 channels with FIN_LANES row lanes per channel (fp64), valid for threadIdx.y == 0.
+// 8 KB of static shared memory: small enough to sit next to a side-stream weight-gradient CTA (which leaves 32 KB).
+constexpr int FIN_LANES = 16;
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
+    __shared__ double sh[2][FIN_LANES][32];
+    s = 0; q = 0;
+    if (c < C) {
+        double s2 = 0, q2 = 0;
+        int b = threadIdx.y;
+        for (; b + FIN_LANES < nblk; b += 2 * FIN_LANES) {      // two independent rows per iteration
+            s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c];
+            s2 += partial[(size_t)(b + FIN_LANES) * 2 * C + c]; q2 += partial[(size_t)(b + FIN_LANES) * 2 * C + C + c];
         }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { s[j] += __shfl_xor_sync(0xffffffffu, s[j], o); q[j] += __shfl_xor_sync(0xffffffffu, q[j], o); }
+        if (b < nblk) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+        s += s2; q += q2;
+    }
+    sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.y == 0)
+        for (int l = 1; l < FIN_LANES; ++l) { s += sh[0][l][threadIdx.x]; q += sh[1][l][threadIdx.x]; }
 }
 // BN forward finalize (training): batch mean / biased var -> scale, shift, saved mean / rstd, running stats
-__global__ void __launch_bounds__(32 * FIN_WARPS) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(32 * FIN_LANES) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ save_mean, float* __restrict__ save_rstd) {
-    const int c4 = (blockIdx.x * FIN_WARPS + threadIdx.y) * 4;
-    double s[4], q[4];
-    reduce_partials4(partial, nblk, C, c4, s, q);
-    if (threadIdx.x != 0 || c4 >= C) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c4 + j;
-        const double mean = s[j] / (double)M;
-        double var = q[j] / (double)M - mean * mean;
-        if (var < 0) var = 0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float sc = gamma[c] * rstd;
-        scale[c] = sc;
-        shift[c] = beta[c] - (float)mean * sc;
-        save_mean[c] = (float)mean;
-        save_rstd[c] = rstd;
-        if (run_mean) {
-            const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
-            run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
-        }
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s, q;
+    reduce_partials(partial, nblk, C, c, s, q);
+    if (threadIdx.y != 0 || c >= C) return;
+    const double mean = s / (double)M;
+    double var = q / (double)M - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * rstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    save_mean[c] = (float)mean;
+    save_rstd[c] = rstd;
+    if (run_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unbiased;
     }
 }
 // eval: scale / shift from the running statistics
@@ -198,33 +197,27 @@ __global__ void bn_eval_batched_kernel(const tfe::BnEvalJob* __restrict__ jobs, 
     j.shift[c] = j.beta[c] - j.run_mean[c] * sc;
 }
 // BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
-__global__ void __launch_bounds__(32 * FIN_WARPS) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef /* [3][C]: gamma*rstd, mean(g), mean(g*xhat) */) {
-    const int c4 = (blockIdx.x * FIN_WARPS + threadIdx.y) * 4;
-    double s[4], q[4];
-    reduce_partials4(partial, nblk, C, c4, s, q);
-    if (threadIdx.x != 0 || c4 >= C) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c4 + j;
-        if (dgamma) dgamma[c] = (float)q[j];
-        if (dbeta) dbeta[c] = (float)s[j];
-        coef[c] = gamma[c] * rstd[c];
-        coef[C + c] = (float)(s[j] / (double)M);
-        coef[2 * C + c] = (float)(q[j] / (double)M);
-    }
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s, q;
+    reduce_partials(partial, nblk, C, c, s, q);
+    if (threadIdx.y != 0 || c >= C) return;
+    if (dgamma) dgamma[c] = (float)q;
+    if (dbeta) dbeta[c] = (float)s;
+    coef[c] = gamma[c] * rstd[c];
+    coef[C + c] = (float)(s / (double)M);
+    coef[2 * C + c] = (float)(q / (double)M);
 }
-__global__ void __launch_bounds__(32 * FIN_WARPS) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
+__global__ void __launch_bounds__(32 * FIN_LANES) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
                                        float* __restrict__ out) {
-    const int c4 = (blockIdx.x * FIN_WARPS + threadIdx.y) * 4;
-    double s[4], q[4];
-    reduce_partials4(partial, nblk, C, c4, s, q);
-    if (threadIdx.x != 0) return;
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (c4 + j < Cout) out[c4 + j] = (float)s[j];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s, q;
+    reduce_partials(partial, nblk, C, c, s, q);
+    if (threadIdx.y != 0 || c >= Cout) return;
+    out[c] = (float)s;
 }
 
 // out = act( y*scale + shift (+ res | + res*rscale + rshift) ); optional 1-bit ReLU mask of the result
@@ -547,7 +540,7 @@ static int reduce_blocks(long long M, int C) {
 int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st) {
-    bn_finalize_train_kernel<<<(C + 4 * FIN_WARPS - 1) / (4 * FIN_WARPS), dim3(32, FIN_WARPS), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
+    bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
                                                               run_var, scale, shift, save_mean, save_rstd);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -577,7 +570,7 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, partial);
-    bn_bwd_finalize_kernel<<<(C + 4 * FIN_WARPS - 1) / (4 * FIN_WARPS), dim3(32, FIN_WARPS), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
                                                                 gmask_out, mode);
@@ -596,7 +589,7 @@ int column_sum(const float* a, long long M, int C, int Cout, float* out, float* 
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "column_sum: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
-    colsum_finalize_kernel<<<(C + 4 * FIN_WARPS - 1) / (4 * FIN_WARPS), dim3(32, FIN_WARPS), 0, st>>>(partial, nb, C, Cout, out);
+    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

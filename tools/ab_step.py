@@ -31,6 +31,10 @@ def run_case(spec, steps=8, warmup=3, B=8, H=960, W=1280):
     from tinyfaces_b200.models.model import DetectionModel
     name, _, flags = spec.partition("=")
     for kv in filter(None, flags.split(",")):
+        if kv.startswith("env:"):                     # env:NAME:VALUE (read by the library at first use)
+            _, k, v = kv.split(":")
+            os.environ[k] = v
+            continue
         k, v = kv.split(":")
         _lib.check(_lib.lib().tf_debug_set(int(k), int(v)), "tf_debug_set")
     dev = torch.device("cuda:0")
