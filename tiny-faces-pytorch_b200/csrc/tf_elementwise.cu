@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                                                                const unsigned int* __restrict__ mask,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, long long M, int C,
-                                                               float* __restrict__ partial) {
+                                                               float* __restrict__ partial, int slots) {
     const int groups = C / 4;                       // float4 channel groups (16 .. 256, a power of two)
     const int lanes = EW_THREADS / groups;          // row lanes per block (1 .. 16)
     const int g = threadIdx.x / lanes, rl = threadIdx.x % lanes;
@@ -122,26 +122,42 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
         s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
     }
     if (rl == 0) {
-        float* p = partial + (size_t)blockIdx.x * 2 * C;
-        st4(p + g * 4, s0);
-        st4(p + C + g * 4, s1);
+        if (slots > 0) {
+            // BN backward: blocks accumulate into `slots` pre-zeroed rows (fire-and-forget fp32 reductions at L2), so
+            // the finalize kernel behind this one reads a handful of rows -- one L2 round trip -- instead of one row
+            // per block: with a weight-gradient GEMM streaming through HBM next to it that latency chain was ~35 us
+            float* p = partial + (size_t)(blockIdx.x % slots) * 2 * C + g * 4;
+            atomicAdd(p, s0.x); atomicAdd(p + 1, s0.y); atomicAdd(p + 2, s0.z); atomicAdd(p + 3, s0.w);
+            atomicAdd(p + C, s1.x); atomicAdd(p + C + 1, s1.y); atomicAdd(p + C + 2, s1.z); atomicAdd(p + C + 3, s1.w);
+        } else {
+            float* p = partial + (size_t)blockIdx.x * 2 * C;
+            st4(p + g * 4, s0);
+            st4(p + C + g * 4, s1);
+        }
     }
 }
 
 // Sum of the per-block partials of 32 channels with FIN_LANES row lanes per channel (fp64), valid for threadIdx.y == 0.
 // 8 KB of static shared memory: small enough to sit next to a side-stream weight-gradient CTA (which leaves 32 KB).
 constexpr int FIN_LANES = 16;
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
+template <bool CLEAN>
+__device__ __forceinline__ void reduce_partials(float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
     __shared__ double sh[2][FIN_LANES][32];
     s = 0; q = 0;
     if (c < C) {
         double s2 = 0, q2 = 0;
         int b = threadIdx.y;
         for (; b + FIN_LANES < nblk; b += 2 * FIN_LANES) {      // two independent rows per iteration
-            s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c];
-            s2 += partial[(size_t)(b + FIN_LANES) * 2 * C + c]; q2 += partial[(size_t)(b + FIN_LANES) * 2 * C + C + c];
+            float* r0 = partial + (size_t)b * 2 * C + c; float* r1 = partial + (size_t)(b + FIN_LANES) * 2 * C + c;
+            s += r0[0]; q += r0[C];
+            s2 += r1[0]; q2 += r1[C];
+            if (CLEAN) { r0[0] = 0.f; r0[C] = 0.f; r1[0] = 0.f; r1[C] = 0.f; }     // slot rows are left zeroed for the next user
         }
-        if (b < nblk) { s += partial[(size_t)b * 2 * C + c]; q += partial[(size_t)b * 2 * C + C + c]; }
+        if (b < nblk) {
+            float* r0 = partial + (size_t)b * 2 * C + c;
+            s += r0[0]; q += r0[C];
+            if (CLEAN) { r0[0] = 0.f; r0[C] = 0.f; }
+        }
         s += s2; q += q2;
     }
     sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = q;
@@ -150,14 +166,14 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
         for (int l = 1; l < FIN_LANES; ++l) { s += sh[0][l][threadIdx.x]; q += sh[1][l][threadIdx.x]; }
 }
 // BN forward finalize (training): batch mean / biased var -> scale, shift, saved mean / rstd, running stats
-__global__ void __launch_bounds__(32 * FIN_LANES) bn_finalize_train_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(32 * FIN_LANES) bn_finalize_train_kernel(float* __restrict__ partial, int nblk, int C, long long M,
                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                          float momentum, float* __restrict__ run_mean, float* __restrict__ run_var,
                                          float* __restrict__ scale, float* __restrict__ shift,
                                          float* __restrict__ save_mean, float* __restrict__ save_rstd) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s, q;
-    reduce_partials(partial, nblk, C, c, s, q);
+    reduce_partials<false>(partial, nblk, C, c, s, q);
     if (threadIdx.y != 0 || c >= C) return;
     const double mean = s / (double)M;
     double var = q / (double)M - mean * mean;
@@ -197,13 +213,13 @@ __global__ void bn_eval_batched_kernel(const tfe::BnEvalJob* __restrict__ jobs, 
     j.shift[c] = j.beta[c] - j.run_mean[c] * sc;
 }
 // BN backward finalize: dgamma, dbeta and the per-channel coefficients of the apply pass
-__global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, long long M,
+__global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(float* __restrict__ partial, int nblk, int C, long long M,
                                        const float* __restrict__ gamma, const float* __restrict__ rstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef /* [3][C]: gamma*rstd, mean(g), mean(g*xhat) */) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s, q;
-    reduce_partials(partial, nblk, C, c, s, q);
+    reduce_partials<true>(partial, nblk, C, c, s, q);
     if (threadIdx.y != 0 || c >= C) return;
     if (dgamma) dgamma[c] = (float)q;
     if (dbeta) dbeta[c] = (float)s;
@@ -211,11 +227,11 @@ __global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(const f
     coef[C + c] = (float)(s / (double)M);
     coef[2 * C + c] = (float)(q / (double)M);
 }
-__global__ void __launch_bounds__(32 * FIN_LANES) colsum_finalize_kernel(const float* __restrict__ partial, int nblk, int C, int Cout,
+__global__ void __launch_bounds__(32 * FIN_LANES) colsum_finalize_kernel(float* __restrict__ partial, int nblk, int C, int Cout,
                                        float* __restrict__ out) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s, q;
-    reduce_partials(partial, nblk, C, c, s, q);
+    reduce_partials<false>(partial, nblk, C, c, s, q);
     if (threadIdx.y != 0 || c >= Cout) return;
     out[c] = (float)s;
 }
@@ -531,13 +547,27 @@ __global__ void extract_upsample_diag_kernel(const float* __restrict__ w, int Cn
 
 namespace tfe {
 
+// The chain's elementwise kernels ask for the MAX-shared-memory carveout although they use (almost) none: an SM only
+// changes its L1 / shared split when it is idle, so a side-stream weight-gradient CTA (194 KB of shared memory) could
+// not join an SM that was running L1-preferring blocks until all of them had retired (seen as a ~55 us late start).
+template <typename K>
+static int prefer_shared_carveout(K kernel) {
+    TF_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    return TF_OK;
+}
+#define RC_CARVEOUT(kernel)                                                         \
+    do {                                                                            \
+        static bool done_ = false;                                                  \
+        if (!done_) { int rc_ = prefer_shared_carveout(kernel); if (rc_) return rc_; done_ = true; }  \
+    } while (0)
+
 static int reduce_blocks(long long M, int C) {
     const int lanes = EW_THREADS / (C / 4);
     long long b = (M + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
     return (int)std::min<long long>(std::max<long long>(b, 1), COLREDUCE_MAX_BLOCKS);
 }
 
-int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
+int bn_finalize_train(float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st) {
     bn_finalize_train_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nblk, C, M, gamma, beta, eps, momentum, run_mean,
@@ -566,11 +596,12 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
 }
 int bn_backward(const float* dout, const float* act, const unsigned int* mask, const float* y, const float* save_mean, const float* save_rstd,
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
-                float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st) {
+                float* gmask_out, int mode, float* slots /* [BN_BWD_SLOTS][2][C], zero on entry, left zeroed */, float* coef, cudaStream_t st) {
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
+    RC_CARVEOUT(colreduce_kernel<1>); RC_CARVEOUT(bn_bwd_finalize_kernel); RC_CARVEOUT(bn_bwd_apply_kernel);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, partial);
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, M, gamma, save_rstd, dgamma, dbeta, coef);
+    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(slots, nb < BN_BWD_SLOTS ? nb : BN_BWD_SLOTS, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
                                                                 gmask_out, mode);
@@ -580,20 +611,22 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
 int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st) {
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0 && M > 0, "column_stats: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0);
     TF_LAUNCH_CHECK();
     *nblk = nb;
     return TF_OK;
 }
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st) {
+    RC_CARVEOUT(colreduce_kernel<2>); RC_CARVEOUT(colsum_finalize_kernel);
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "column_sum: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial);
+    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0);
     colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
 int masked_add(const float* a, const float* act, const float* b, long long n, float* out, cudaStream_t st) {
+    RC_CARVEOUT(masked_add_kernel);
     masked_add_kernel<<<ew_blocks(n / 4, 2), EW_THREADS, 0, st>>>(a, act, b, n / 4, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -611,11 +644,13 @@ int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, floa
     return TF_OK;
 }
 int maxpool_bwd(const unsigned char* argmax, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st) {
+    RC_CARVEOUT(maxpool_bwd_kernel);
     maxpool_bwd_kernel<<<ew_blocks((long long)B * H * W * C / 4), EW_THREADS, 0, st>>>(argmax, dout, B, H, W, C, Ho, Wo, dx);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
 int zero_insert2(const float* xs, const float* xs_lo, int B, int H, int W, int C, float* out, float* out_lo, cudaStream_t st) {
+    RC_CARVEOUT(zero_insert2_kernel);
     const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
     zero_insert2_kernel<<<ew_blocks((long long)B * H * W * C / 4), EW_THREADS, 0, st>>>(xs, xs_lo, B, H, W, C, Ho, Wo, out, out_lo);
     TF_LAUNCH_CHECK();
@@ -633,6 +668,7 @@ int pack_weights_batched(const PackJob* jobs_device, int njobs, long long total,
     return TF_OK;
 }
 int unpack_wgrad(const float* dwp, int O, int I, int taps, int I_pad, float* dw, cudaStream_t st) {
+    RC_CARVEOUT(unpack_wgrad_kernel);
     unpack_wgrad_kernel<<<ew_blocks((long long)O * I * taps), EW_THREADS, 0, st>>>(dwp, O, I, taps, I_pad, dw);
     TF_LAUNCH_CHECK();
     return TF_OK;
@@ -645,6 +681,7 @@ int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, i
 }
 int head_combine_bwd(const float* dout_nchw, const float* up, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
                      float* ds3, float* ds4, cudaStream_t st) {
+    RC_CARVEOUT(head_combine_bwd_kernel);
     const long long n = (long long)B * (H3 * W3 + H4 * W4) * Cp;
     head_combine_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, st>>>(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4);
     TF_LAUNCH_CHECK();

@@ -3,10 +3,11 @@
 #include <cuda_runtime.h>
 
 namespace tfe {
+constexpr int BN_BWD_SLOTS = 32;             // accumulation rows of the BN-backward column reduction
 constexpr int COLREDUCE_MAX_BLOCKS = 592;     // partial buffers hold COLREDUCE_MAX_BLOCKS * 2 * C floats
 // `mode` of every activation producer: 0 = store as is, 1 = round to TF32 (fast mode operands),
 // 2 = store the (hi, lo) TF32 split into (out, out_lo) (3xTF32 parity mode)
-int bn_finalize_train(const float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
+int bn_finalize_train(float* partial, int nblk, long long M, int C, const float* gamma, const float* beta, float eps,
                       float momentum, float* run_mean, float* run_var, float* scale, float* shift, float* save_mean,
                       float* save_rstd, cudaStream_t st);
 int bn_scale_shift_eval(int C, const float* gamma, const float* beta, const float* run_mean, const float* run_var,
@@ -18,7 +19,7 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
              unsigned int* mask_out /* optional 1-bit ReLU mask, (M*C+31)/32 words */, cudaStream_t st);
 int bn_backward(const float* dout, const float* act, const unsigned int* mask /* either may gate dout */, const float* y, const float* save_mean, const float* save_rstd,
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
-                float* gmask_out, int mode, float* partial, float* coef, cudaStream_t st);
+                float* gmask_out, int mode, float* slots /* [BN_BWD_SLOTS][2][C] zeros, left zeroed */, float* coef, cudaStream_t st);
 // per-channel (sum, sum^2) partials of y[M, C] -> partial[*nblk][2][C] (bn_finalize_train reduces them)
 int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st);
 int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st);

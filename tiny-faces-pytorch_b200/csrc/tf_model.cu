@@ -69,7 +69,7 @@ struct Model {
     int H3 = 0, W3 = 0, H4 = 0, W4 = 0;
     const float* res3 = nullptr; const float* res3_lo = nullptr; const float* res4 = nullptr; const float* res4_lo = nullptr;
     float *w3p = nullptr, *w3p_lo = nullptr, *w4p = nullptr, *w4p_lo = nullptr, *b3p = nullptr, *b4p = nullptr, *up = nullptr, *offdiag = nullptr;
-    float* partial = nullptr; float* coef = nullptr; float* dwtmp = nullptr; size_t fwd_mark = 0;
+    float* partial = nullptr; float* bwd_slots = nullptr; float* coef = nullptr; float* dwtmp = nullptr; size_t fwd_mark = 0;
     float eps = 1e-5f, momentum = 0.1f;
     // weight-gradient GEMMs run on a side stream: they depend only on (x, dy) and nothing in the backward chain
     // depends on them, so their tensor-core time overlaps the HBM-bound BN-backward kernels of the main stream
@@ -341,6 +341,7 @@ struct Model {
         H2 = (H - 1) / 2 + 1; W2 = (W - 1) / 2 + 1;
         Hp = (H2 - 1) / 2 + 1; Wp = (W2 - 1) / 2 + 1;
         partial = ar.f((size_t)tfe::COLREDUCE_MAX_BLOCKS * 2 * 2 * 1024);   // main + tail-launch statistics rows
+        bwd_slots = ar.f((size_t)tfe::BN_BWD_SLOTS * 2 * 1024);
         coef = ar.f(3 * 1024);
         dwtmp = ar.f((size_t)1024 * 1024 + 4096);
         offdiag = ar.f(64);
@@ -471,7 +472,7 @@ struct Model {
         *dy = ar.f((size_t)M * C);
         *dy_lo = mode == 2 ? ar.f((size_t)M * C) : nullptr;
         if (!ar.dry) RC(tfe::bn_backward(dout, nullptr, mask, u.y, u.mean, u.rstd, P(u.bn.gamma), M, C, G(grads, u.bn.gamma), G(grads, u.bn.beta),
-                                         *dy, *dy_lo, gmask_out, mode, partial, coef, st));
+                                         *dy, *dy_lo, gmask_out, mode, bwd_slots, coef, st));
         return TF_OK;
     }
     // conv backward of unit u given dy at (Ho, Wo): weight gradient (always) and input gradient into dx
@@ -571,6 +572,7 @@ struct Model {
         const long long M3 = (long long)B * H3 * W3, M4 = (long long)B * H4 * W4;
         float* ds3 = ar.f((size_t)M3 * Cp); float* ds4 = ar.f((size_t)M4 * Cp);
         if (!ar.dry) {
+            TF_CHECK_CUDA(cudaMemsetAsync(bwd_slots, 0, (size_t)tfe::BN_BWD_SLOTS * 2 * 1024 * sizeof(float), st));   // every BN backward leaves it zeroed
             RC(tfe::head_combine_bwd(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4, st));
             if (G(grads, s3_b)) RC(tfe::column_sum(ds3, M3, Cp, Cn, G(grads, s3_b), partial, st));
             if (G(grads, s4_b)) RC(tfe::column_sum(ds4, M4, Cp, Cn, G(grads, s4_b), partial, st));
