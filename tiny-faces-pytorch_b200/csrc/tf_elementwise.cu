@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
         const bool live = t < n4;
         float4 v = make_float4(0, 0, 0, 0);
         if (live) {
-            const int c = (int)(i % C);
+            const int c = (int)(i & (long long)(C - 1));            // C is a power of two
             v = ld4(y + i);
             const float4 sc = ld4(scale + c), sh = ld4(shift + c);
             v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
                                                                   float* __restrict__ gmask_out, int mode) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
         const long long i = t * 4;
-        const int c = (int)(i % C);
+        const int c = (int)(i & (long long)(C - 1));            // C is a power of two
         float4 g = ld4(dout + i);
         if (mask) apply_mask(g, mask_nibble(mask, i));
         else if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
@@ -320,16 +320,29 @@ __global__ void __launch_bounds__(EW_THREADS) masked_add_kernel(const float* __r
 // ------------------------------------------------------------------------------------------------ stem
 // im2col for conv1 (7x7, stride 2, pad 3) straight from the caller's NCHW image:
 //   col[(b,oy,ox)][k], k = c*49 + kh*7 + kw (== OIHW flattening of conv1.weight), zero-padded to K_pad
+// One block = 64 consecutive output pixels of one output row: the 3 x 7 input rows they touch (133 columns) are staged
+// in shared memory with coalesced row reads, then the 64 x K_pad patch matrix goes out as whole 640-byte rows.
+constexpr int IM2COL_PIX = 64, IM2COL_TW = 136;
 __global__ void __launch_bounds__(EW_THREADS) stem_im2col_kernel(const float* __restrict__ x, int B, int H, int W, int Ho,
                                                                  int Wo, int K_pad, float* __restrict__ col,
                                                                  float* __restrict__ col_lo, int mode) {
+    __shared__ float t[21 * IM2COL_TW];
+    const int ox0 = blockIdx.x * IM2COL_PIX, oy = blockIdx.y, b = blockIdx.z;
+    const int ix0 = 2 * ox0 - 3;
+    for (int e = threadIdx.x; e < 21 * IM2COL_TW; e += EW_THREADS) {
+        const int rowi = e / IM2COL_TW, cx = e - rowi * IM2COL_TW;       // rowi = c * 7 + kh
+        const int c = rowi / 7, kh = rowi - c * 7;
+        const int iy = 2 * oy + kh - 3, ix = ix0 + cx;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + ((size_t)(b * 3 + c) * H + iy) * W + ix);
+        t[e] = v;
+    }
+    __syncthreads();
     const int kq = K_pad / 4;
-    const long long total = (long long)B * Ho * Wo * kq;
-    const long long plane = (long long)H * W;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int k0 = (int)(t % kq) * 4;
-        const long long pix = t / kq;
-        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+    const int npix = min(IM2COL_PIX, Wo - ox0);
+    const size_t row0 = ((size_t)b * Ho + oy) * Wo + ox0;
+    for (int e = threadIdx.x; e < npix * kq; e += EW_THREADS) {
+        const int pl = e / kq, k0 = (e - pl * kq) * 4;
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -337,69 +350,75 @@ __global__ void __launch_bounds__(EW_THREADS) stem_im2col_kernel(const float* __
             float val = 0.f;
             if (k < 147) {
                 const int c = k / 49, r = k - c * 49, kh = r / 7, kw = r - kh * 7;
-                const int iy = oy * 2 + kh - 3, ix = ox * 2 + kw - 3;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(x + ((long long)b * 3 + c) * plane + (long long)iy * W + ix);
+                val = t[(c * 7 + kh) * IM2COL_TW + 2 * pl + kw];
             }
             v[j] = val;
         }
-        store_act(col, col_lo, pix * K_pad + k0, make_float4(v[0], v[1], v[2], v[3]), mode);
+        store_act(col, col_lo, (long long)((row0 + pl) * K_pad + k0), make_float4(v[0], v[1], v[2], v[3]), mode);
     }
 }
 
-// max-pool 3x3 stride 2 pad 1, NHWC
+// max-pool 3x3 stride 2 pad 1, NHWC.  Blocks walk output rows (b, oy); threads cover (ox, 4-channel group): 32-bit index
+// arithmetic only (the first version spent most of its time in 64-bit divisions).
 __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const float* __restrict__ x, int B, int H, int W, int C,
                                                                  int Ho, int Wo, float* __restrict__ out,
                                                                  float* __restrict__ out_lo, int mode,
                                                                  unsigned char* __restrict__ argmax) {
-    const long long total = (long long)B * Ho * Wo * (C / 4);
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(t % (C / 4));
-        const long long pix = t / (C / 4);
-        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
-        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        int am[4] = {-1, -1, -1, -1};
-        for (int kh = 0; kh < 3; ++kh) {
-            const int iy = oy * 2 + kh - 1;
-            if (iy < 0 || iy >= H) continue;
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ix = ox * 2 + kw - 1;
-                if (ix < 0 || ix >= W) continue;
-                const float4 v4 = ld4(x + (((long long)b * H + iy) * W + ix) * C + cg * 4);
-                const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    const int cgs = C / 4, per_row = Wo * cgs;
+    for (int row = blockIdx.x; row < B * Ho; row += gridDim.x) {
+        const int b = row / Ho, oy = row - b * Ho;
+        const float* xb = x + (size_t)b * H * W * C;
+        for (int t = threadIdx.x; t < per_row; t += EW_THREADS) {
+            const int ox = t / cgs, cg = t - ox * cgs;
+            float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int am[4] = {-1, -1, -1, -1};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)     // first maximum in (kh, kw) scan order wins (ATen's CPU max_pool2d rule)
-                    if (v[j] > m[j] || am[j] < 0) { m[j] = v[j]; am[j] = kh * 3 + kw; }
+            for (int kh = 0; kh < 3; ++kh) {
+                const int iy = oy * 2 + kh - 1;
+                if (iy < 0 || iy >= H) continue;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int ix = ox * 2 + kw - 1;
+                    if (ix < 0 || ix >= W) continue;
+                    const float4 v4 = ld4(xb + ((size_t)iy * W + ix) * C + cg * 4);
+                    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)     // first maximum in (kh, kw) scan order wins (ATen's CPU max_pool2d rule)
+                        if (v[j] > m[j] || am[j] < 0) { m[j] = v[j]; am[j] = kh * 3 + kw; }
+                }
             }
+            const long long o = ((long long)row * Wo + ox) * C + cg * 4;
+            store_act(out, out_lo, o, make_float4(m[0], m[1], m[2], m[3]), mode);
+            if (argmax) *reinterpret_cast<uchar4*>(argmax + o) = make_uchar4(am[0], am[1], am[2], am[3]);
         }
-        store_act(out, out_lo, pix * C + cg * 4, make_float4(m[0], m[1], m[2], m[3]), mode);
-        if (argmax) *reinterpret_cast<uchar4*>(argmax + pix * C + cg * 4) = make_uchar4(am[0], am[1], am[2], am[3]);
     }
 }
 // backward as a gather over the saved window argmax: input pixel (iy, ix) collects dout of the (at most 4)
-// windows whose arg-max it is.  float4 over channels.
+// windows whose arg-max it is.  Blocks walk input rows (b, iy); float4 over channels.
 __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const unsigned char* __restrict__ argmax,
                                                                  const float* __restrict__ dout, int B, int H, int W, int C,
                                                                  int Ho, int Wo, float* __restrict__ dx) {
-    const long long total = (long long)B * H * W * (C / 4);
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(t % (C / 4));
-        const long long pix = t / (C / 4);
-        const int ix = (int)(pix % W), iy = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-        float4 acc = make_float4(0, 0, 0, 0);
+    const int cgs = C / 4, per_row = W * cgs;
+    for (int row = blockIdx.x; row < B * H; row += gridDim.x) {
+        const int b = row / H, iy = row - b * H;
         const int oy_lo = iy / 2, oy_hi = min(Ho - 1, (iy + 1) / 2);
-        const int ox_lo = ix / 2, ox_hi = min(Wo - 1, (ix + 1) / 2);
-        for (int oy = oy_lo; oy <= oy_hi; ++oy)
-            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                const int want = (iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1));
-                const long long o = (((long long)b * Ho + oy) * Wo + ox) * C + cg * 4;
-                const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + o);
-                const float4 g = ld4(dout + o);
-                if (am.x == want) acc.x += g.x;
-                if (am.y == want) acc.y += g.y;
-                if (am.z == want) acc.z += g.z;
-                if (am.w == want) acc.w += g.w;
-            }
-        st4(dx + pix * C + cg * 4, acc);
+        for (int t = threadIdx.x; t < per_row; t += EW_THREADS) {
+            const int ix = t / cgs, cg = t - ix * cgs;
+            const int ox_lo = ix / 2, ox_hi = min(Wo - 1, (ix + 1) / 2);
+            float4 acc = make_float4(0, 0, 0, 0);
+            for (int oy = oy_lo; oy <= oy_hi; ++oy)
+                for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                    const int want = (iy - (oy * 2 - 1)) * 3 + (ix - (ox * 2 - 1));
+                    const size_t o = (((size_t)b * Ho + oy) * Wo + ox) * C + cg * 4;
+                    const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + o);
+                    const float4 g = ld4(dout + o);
+                    if (am.x == want) acc.x += g.x;
+                    if (am.y == want) acc.y += g.y;
+                    if (am.z == want) acc.z += g.z;
+                    if (am.w == want) acc.w += g.w;
+                }
+            st4(dx + ((size_t)row * W + ix) * C + cg * 4, acc);
+        }
     }
 }
 
@@ -468,60 +487,82 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int O, int I,
 
 // ------------------------------------------------------------------------------------------------ heads
 // model.py:104-126: out[b,c,y,x] = s3[b,y,x,c] + sum_{i,j} s4[b,i,j,c] * up[c][y+1-2i][x+1-2j]   (NCHW result)
+// One block = 32 consecutive x of one (b, y): the values are computed channel-fastest (coalesced NHWC reads), transposed
+// through shared memory and written as 128-byte rows of the NCHW result.
+constexpr int HEAD_TX = 32, HEAD_CMAX = 256;
 __global__ void __launch_bounds__(EW_THREADS) head_combine_fwd_kernel(const float* __restrict__ s3, const float* __restrict__ s4,
                                                                       const float* __restrict__ up /*[Cn][16]*/, int B,
                                                                       int H3, int W3, int H4, int W4, int Cn, int Cp,
                                                                       float* __restrict__ out) {
-    const long long total = (long long)B * Cn * H3 * W3;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(t % W3), y = (int)((t / W3) % H3), c = (int)((t / ((long long)W3 * H3)) % Cn);
-        const int b = (int)(t / ((long long)W3 * H3 * Cn));
-        float v = s3[(((long long)b * H3 + y) * W3 + x) * Cp + c];
-        const int i0 = (y + 1) >> 1, j0 = (x + 1) >> 1;
+    extern __shared__ float tile[];                     // [Cp][HEAD_TX + 1]
+    const int x0 = blockIdx.x * HEAD_TX, y = blockIdx.y, b = blockIdx.z;
+    const int nx = min(HEAD_TX, W3 - x0);
+    const int i0 = (y + 1) >> 1;
+    for (int e = threadIdx.x; e < nx * Cp; e += EW_THREADS) {
+        const int xl = e / Cp, c = e - xl * Cp, x = x0 + xl;
+        float v = 0.f;
+        if (c < Cn) {
+            v = s3[(((size_t)b * H3 + y) * W3 + x) * Cp + c];
+            const int j0 = (x + 1) >> 1;
 #pragma unroll
-        for (int di = 0; di < 2; ++di) {
-            const int i = i0 - di, ky = y + 1 - 2 * i;
-            if (i < 0 || i >= H4) continue;
+            for (int di = 0; di < 2; ++di) {
+                const int i = i0 - di, ky = y + 1 - 2 * i;
+                if (i < 0 || i >= H4) continue;
 #pragma unroll
-            for (int dj = 0; dj < 2; ++dj) {
-                const int j = j0 - dj, kx = x + 1 - 2 * j;
-                if (j < 0 || j >= W4) continue;
-                v += s4[(((long long)b * H4 + i) * W4 + j) * Cp + c] * up[c * 16 + ky * 4 + kx];
-            }
-        }
-        out[t] = v;
-    }
-}
-// adjoint: ds3[b,y,x,c] = dout[b,c,y,x] (padded channels = 0); ds4[b,i,j,c] = sum_{y,x} dout[b,c,y,x] * up[c][y+1-2i][x+1-2j]
-__global__ void __launch_bounds__(EW_THREADS) head_combine_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ up,
-                                                                      int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
-                                                                      float* __restrict__ ds3, float* __restrict__ ds4) {
-    const long long n3 = (long long)B * H3 * W3 * Cp, n4 = (long long)B * H4 * W4 * Cp;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n3 + n4; t += (long long)gridDim.x * blockDim.x) {
-        if (t < n3) {
-            const int c = (int)(t % Cp);
-            const long long pix = t / Cp;
-            const int x = (int)(pix % W3), y = (int)((pix / W3) % H3), b = (int)(pix / ((long long)W3 * H3));
-            ds3[t] = c < Cn ? dout[(((long long)b * Cn + c) * H3 + y) * W3 + x] : 0.f;
-        } else {
-            const long long u = t - n3;
-            const int c = (int)(u % Cp);
-            const long long pix = u / Cp;
-            const int j = (int)(pix % W4), i = (int)((pix / W4) % H4), b = (int)(pix / ((long long)W4 * H4));
-            float v = 0.f;
-            if (c < Cn) {
-                for (int ky = 0; ky < 4; ++ky) {
-                    const int y = 2 * i - 1 + ky;
-                    if (y < 0 || y >= H3) continue;
-                    for (int kx = 0; kx < 4; ++kx) {
-                        const int x = 2 * j - 1 + kx;
-                        if (x < 0 || x >= W3) continue;
-                        v += dout[(((long long)b * Cn + c) * H3 + y) * W3 + x] * up[c * 16 + ky * 4 + kx];
-                    }
+                for (int dj = 0; dj < 2; ++dj) {
+                    const int j = j0 - dj, kx = x + 1 - 2 * j;
+                    if (j < 0 || j >= W4) continue;
+                    v += s4[(((size_t)b * H4 + i) * W4 + j) * Cp + c] * up[c * 16 + ky * 4 + kx];
                 }
             }
-            ds4[u] = v;
         }
+        tile[c * (HEAD_TX + 1) + xl] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < Cn * HEAD_TX; e += EW_THREADS) {
+        const int c = e / HEAD_TX, xl = e - c * HEAD_TX;
+        if (xl < nx) out[(((size_t)b * Cn + c) * H3 + y) * W3 + x0 + xl] = tile[c * (HEAD_TX + 1) + xl];
+    }
+}
+// adjoint, step 1: ds3[b,y,x,c] = dout[b,c,y,x] (padded channels = 0) -- an NCHW -> NHWC transpose through shared memory
+__global__ void __launch_bounds__(EW_THREADS) head_transpose_bwd_kernel(const float* __restrict__ dout, int B, int H3, int W3,
+                                                                        int Cn, int Cp, float* __restrict__ ds3) {
+    extern __shared__ float tile[];                     // [Cp][HEAD_TX + 1]
+    const int x0 = blockIdx.x * HEAD_TX, y = blockIdx.y, b = blockIdx.z;
+    const int nx = min(HEAD_TX, W3 - x0);
+    for (int e = threadIdx.x; e < Cp * HEAD_TX; e += EW_THREADS) {
+        const int c = e / HEAD_TX, xl = e - c * HEAD_TX;
+        tile[c * (HEAD_TX + 1) + xl] = (c < Cn && xl < nx) ? dout[(((size_t)b * Cn + c) * H3 + y) * W3 + x0 + xl] : 0.f;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nx * Cp; e += EW_THREADS) {
+        const int xl = e / Cp, c = e - xl * Cp;
+        ds3[(((size_t)b * H3 + y) * W3 + x0 + xl) * Cp + c] = tile[c * (HEAD_TX + 1) + xl];
+    }
+}
+// adjoint, step 2: ds4[b,i,j,c] = sum_{y,x} ds3[b,y,x,c] * up[c][y+1-2i][x+1-2j]   (channel-fastest on both sides)
+__global__ void __launch_bounds__(EW_THREADS) head_upsample_bwd_kernel(const float* __restrict__ ds3, const float* __restrict__ up,
+                                                                       int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
+                                                                       float* __restrict__ ds4) {
+    const int total = B * H4 * W4 * Cp;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
+        const int c = u % Cp, pix = u / Cp;
+        const int j = pix % W4, i = (pix / W4) % H4, b = pix / (W4 * H4);
+        float v = 0.f;
+        if (c < Cn) {
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const int y = 2 * i - 1 + ky;
+                if (y < 0 || y >= H3) continue;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    const int x = 2 * j - 1 + kx;
+                    if (x < 0 || x >= W3) continue;
+                    v += ds3[(((size_t)b * H3 + y) * W3 + x) * Cp + c] * up[c * 16 + ky * 4 + kx];
+                }
+            }
+        }
+        ds4[u] = v;
     }
 }
 // up[c][k] = w[c][c][k]  (the ConvTranspose2d weight must be diagonal, model.py:45-65); offdiag = max |off-diagonal|
@@ -589,6 +630,7 @@ int bn_scale_shift_eval_batched(const BnEvalJob* jobs_device, int njobs, int tot
 int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
              const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, unsigned int* mask_out,
              cudaStream_t st) {
+    TF_REQUIRE(C >= 4 && (C & (C - 1)) == 0, "bn_apply: C=%d must be a power of two", C);
     const long long n4 = M * C / 4;
     bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out);
     TF_LAUNCH_CHECK();
@@ -633,19 +675,20 @@ int masked_add(const float* a, const float* act, const float* b, long long n, fl
 }
 int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,
                 cudaStream_t st) {
-    stem_im2col_kernel<<<ew_blocks((long long)B * Ho * Wo * K_pad / 4), EW_THREADS, 0, st>>>(x_nchw, B, H, W, Ho, Wo, K_pad, col, col_lo, mode);
+    TF_REQUIRE(K_pad % 4 == 0 && K_pad >= 148 && Ho <= 65535 && B <= 65535, "stem_im2col: unsupported shape");
+    stem_im2col_kernel<<<dim3((Wo + IM2COL_PIX - 1) / IM2COL_PIX, Ho, B), EW_THREADS, 0, st>>>(x_nchw, B, H, W, Ho, Wo, K_pad, col, col_lo, mode);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
 int maxpool_fwd(const float* x, int B, int H, int W, int C, int Ho, int Wo, float* out, float* out_lo, int mode,
                 unsigned char* argmax, cudaStream_t st) {
-    maxpool_fwd_kernel<<<ew_blocks((long long)B * Ho * Wo * C / 4), EW_THREADS, 0, st>>>(x, B, H, W, C, Ho, Wo, out, out_lo, mode, argmax);
+    maxpool_fwd_kernel<<<std::min(B * Ho, 148 * 16), EW_THREADS, 0, st>>>(x, B, H, W, C, Ho, Wo, out, out_lo, mode, argmax);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
 int maxpool_bwd(const unsigned char* argmax, const float* dout, int B, int H, int W, int C, int Ho, int Wo, float* dx, cudaStream_t st) {
     RC_CARVEOUT(maxpool_bwd_kernel);
-    maxpool_bwd_kernel<<<ew_blocks((long long)B * H * W * C / 4), EW_THREADS, 0, st>>>(argmax, dout, B, H, W, C, Ho, Wo, dx);
+    maxpool_bwd_kernel<<<std::min(B * H, 148 * 16), EW_THREADS, 0, st>>>(argmax, dout, B, H, W, C, Ho, Wo, dx);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -675,15 +718,19 @@ int unpack_wgrad(const float* dwp, int O, int I, int taps, int I_pad, float* dw,
 }
 int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, int H3, int W3, int H4, int W4, int Cn,
                      int Cp, float* out_nchw, cudaStream_t st) {
-    head_combine_fwd_kernel<<<ew_blocks((long long)B * Cn * H3 * W3), EW_THREADS, 0, st>>>(s3, s4, up, B, H3, W3, H4, W4, Cn, Cp, out_nchw);
+    TF_REQUIRE(Cp <= HEAD_CMAX && H3 <= 65535 && B <= 65535, "head_combine_fwd: unsupported shape");
+    const size_t smem = (size_t)Cp * (HEAD_TX + 1) * sizeof(float);
+    head_combine_fwd_kernel<<<dim3((W3 + HEAD_TX - 1) / HEAD_TX, H3, B), EW_THREADS, smem, st>>>(s3, s4, up, B, H3, W3, H4, W4, Cn, Cp, out_nchw);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
 int head_combine_bwd(const float* dout_nchw, const float* up, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
                      float* ds3, float* ds4, cudaStream_t st) {
-    RC_CARVEOUT(head_combine_bwd_kernel);
-    const long long n = (long long)B * (H3 * W3 + H4 * W4) * Cp;
-    head_combine_bwd_kernel<<<ew_blocks(n), EW_THREADS, 0, st>>>(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4);
+    TF_REQUIRE(Cp <= HEAD_CMAX && H3 <= 65535 && B <= 65535, "head_combine_bwd: unsupported shape");
+    TF_REQUIRE((long long)B * H4 * W4 * Cp < (1ll << 31), "head_combine_bwd: tensor too large");
+    const size_t smem = (size_t)Cp * (HEAD_TX + 1) * sizeof(float);
+    head_transpose_bwd_kernel<<<dim3((W3 + HEAD_TX - 1) / HEAD_TX, H3, B), EW_THREADS, smem, st>>>(dout_nchw, B, H3, W3, Cn, Cp, ds3);
+    head_upsample_bwd_kernel<<<ew_blocks((long long)B * H4 * W4 * Cp), EW_THREADS, 0, st>>>(ds3, up, B, H3, W3, H4, W4, Cn, Cp, ds4);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
