@@ -176,7 +176,7 @@ def main():
     model = DetectionModel(pretrained_weights=None, num_templates=T).to(dev)
     model.train()
     crit = DetectionCriterion(T, sampler="device", seed=rank)
-    opt = torch.optim.SGD(model.learnable_parameters(1e-4), momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD(model.learnable_parameters(1e-4), momentum=0.9, weight_decay=5e-4, fused=True)
     B = B_PER_GPU
     H3, W3 = (H_IMG + 7) // 8, (W_IMG + 7) // 8
     img_h = synthetic.images(B, H_IMG, W_IMG, seed=rank).pin_memory()

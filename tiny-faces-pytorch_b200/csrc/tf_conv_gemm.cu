@@ -48,6 +48,10 @@ struct GemmParams {
     // (one unit each) whose partial sums meet in D through TMA reduce-add (the host zeroes those rows first).  Without
     // it 300 tiles on 148 SMs cost 3 rounds for 2.03 rounds of work.
     int main_tiles, ksplit;
+    // Residual epilogue (RES kernels, flat pixel rows only): D[row, n] = acc + (bit n of res_mask row ? res[row, n] : 0) --
+    // the masked upstream gradient of an identity shortcut joins the 1x1 dgrad here instead of being written out by the
+    // BN-backward pass and read-modify-written by a TMA reduce-add.
+    const float* res; const unsigned int* res_mask; long long m_rows;
     const float* scale;           // optional per-output-channel epilogue: v = v * scale[n] + shift[n]
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
     int relu, round_out;
@@ -160,7 +164,26 @@ __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u, int 
     return w;
 }
 
-template <int BN, bool FUSED, bool SPATIAL>
+__device__ __forceinline__ uint4 ldg_nc_v4(const float* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+// residual chunk of one row: 32 floats + their mask word (row stride = cout floats, masks are 1 bit per element)
+__device__ __forceinline__ void res_load(const GemmParams& p, bool valid, long long row, int nb, uint4 (&rs)[8], uint32_t& mw) {
+    if (valid) {
+        const float* src = p.res + row * p.cout + nb;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rs[c] = ldg_nc_v4(src + 4 * c);
+        mw = __ldg(p.res_mask + ((row * p.cout + nb) >> 5));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rs[c] = make_uint4(0, 0, 0, 0);
+        mw = 0;
+    }
+}
+
+template <int BN, bool FUSED, bool SPATIAL, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
@@ -288,6 +311,10 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 const int rw = q * 32 + lane;
                 rowmask = __ballot_sync(0xffffffffu, x0 + rw % p.tw < p.img_w && y0 + rw / p.tw < p.img_h);
             }
+            uint4 rs[2][8]; uint32_t mw[2];                         // RES: residual chunk prefetched one chunk ahead
+            const long long res_row = (long long)m0 + q * 32 + lane;
+            const bool res_valid = RES && res_row < p.m_rows;
+            if (RES) res_load(p, res_valid, res_row, n0, rs[0], mw[0]);   // in flight while the accumulators finish
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -299,6 +326,18 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 tmem_ld_wait();                                              // this chunk's registers are valid
                 if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, rr[(chunk + 1) & 1]);
                 else { tc_fence_before(); mbar_arrive(&tempty[acc]); }        // accumulator stage fully read
+                if (RES) {
+                    if (chunk + 1 < BN / 32) res_load(p, res_valid, res_row, n0 + (chunk + 1) * 32, rs[(chunk + 1) & 1], mw[(chunk + 1) & 1]);
+                    const uint32_t m = mw[chunk & 1];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 v = rs[chunk & 1][c];
+                        if (m & (1u << (4 * c)))     r[4 * c]     = __float_as_uint(__uint_as_float(r[4 * c])     + __uint_as_float(v.x));
+                        if (m & (2u << (4 * c)))     r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + __uint_as_float(v.y));
+                        if (m & (4u << (4 * c)))     r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + __uint_as_float(v.z));
+                        if (m & (8u << (4 * c)))     r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + __uint_as_float(v.w));
+                    }
+                }
                 uint8_t* buf = wbuf + ebuf * 4096;
                 epilogue_chunk<FUSED, SPATIAL>(r, p, &maps.d, buf, lane, n0 + chunk * 32, reduce_out, do_stats, rowmask,
                                                SPATIAL ? x0 + wx : m0 + q * 32, y0 + wy, img, st_sum[chunk], st_sq[chunk]);
@@ -746,25 +785,27 @@ int ensure_device_state() {
     return TF_OK;
 }
 
-template <int BN, bool FUSED, bool SPATIAL>
+template <int BN, bool FUSED, bool SPATIAL, bool RES>
 int launch_gemm_variant(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, FUSED, SPATIAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, FUSED, SPATIAL, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    conv_gemm_kernel<BN, FUSED, SPATIAL><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
+    conv_gemm_kernel<BN, FUSED, SPATIAL, RES><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
-// FUSED (per-channel scale / shift / ReLU / rounding in the epilogue) and SPATIAL (4-D patch tiles vs flat pixel rows)
-// are separate instantiations: the training path's plain epilogue stays small enough for the instruction cache
+// FUSED (per-channel scale / shift / ReLU / rounding in the epilogue), SPATIAL (4-D patch tiles vs flat pixel rows) and
+// RES (masked residual added in the epilogue) are separate instantiations: the training path's plain epilogue stays
+// small enough for the instruction cache
 template <int BN>
 int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
     const bool fused = p.scale || p.shift || p.relu || p.round_out;
-    if (p.spatial) return fused ? launch_gemm_variant<BN, true, true>(maps, p, grid, st) : launch_gemm_variant<BN, false, true>(maps, p, grid, st);
-    return fused ? launch_gemm_variant<BN, true, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, false>(maps, p, grid, st);
+    if (p.res) return launch_gemm_variant<BN, false, false, true>(maps, p, grid, st);
+    if (p.spatial) return fused ? launch_gemm_variant<BN, true, true, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, true, false>(maps, p, grid, st);
+    return fused ? launch_gemm_variant<BN, true, false, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, false, false>(maps, p, grid, st);
 }
 int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cudaStream_t st) {
     static bool attr_set = false;
@@ -794,12 +835,12 @@ int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
     return TF_OK;
 }
 
-int g_debug[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+int g_debug[16] = {0};
 
 }  // namespace
 
 TF_API int tf_debug_set(int key, int value) {
-    TF_REQUIRE(key >= 0 && key < 8, "tf_debug_set: bad key");
+    TF_REQUIRE(key >= 0 && key < 16, "tf_debug_set: bad key");
     g_debug[key] = value;
     return TF_OK;
 }
@@ -808,7 +849,7 @@ TF_API int tf_debug_set(int key, int value) {
 #include "tf_elementwise.h"
 namespace tfg {
 
-int debug_flag(int key) { return (key >= 0 && key < 8) ? g_debug[key] : 0; }
+int debug_flag(int key) { return (key >= 0 && key < 16) ? g_debug[key] : 0; }
 
 int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     TF_REQUIRE(a.x && a.w && a.y, "conv_fprop: null pointer");
@@ -843,6 +884,9 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     p.taps = taps; p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
+    p.res = a.res; p.res_mask = a.res_mask; p.m_rows = Mtot;
+    TF_REQUIRE(!a.res || (a.res_mask && !spatial && !a.scale && !a.shift && !a.relu && !a.round_out && !p.accumulate && !a.stats_partial),
+               "conv_fprop: the residual epilogue needs a plain, flat (1x1 stride-1), non-accumulating GEMM");
     p.stats_partial = a.stats_partial; p.cout = Cout; p.img_w = Wo; p.img_h = Ho;
     if (g_debug[7] && !p.stats_partial) {          // probe: time the BN-statistics epilogue without the model around it
         static float* scratch = nullptr;
@@ -874,7 +918,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
             if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, bw, bh))) return rc;
         }
     }
-    const bool two_cta = BN == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || TWO_CTA_DEFAULT) && p.num_m_tiles >= 2;
+    const bool two_cta = BN == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || TWO_CTA_DEFAULT) && p.num_m_tiles >= 2 && !a.res;
     for (int s = 0; s < p.nseg; ++s)
         if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, two_cta ? 128 : BN))) return rc;
     int stats_rows = 0;

@@ -11,6 +11,7 @@ struct ConvArgs {
     int stride;                            // 0/1 or 2 (strided TMA traversal); output is ceil(H/s) x ceil(W/s)
     const float* scale; const float* shift;// optional per-channel epilogue (shift alone = bias)
     int relu, round_out, accumulate;
+    const float* res; const unsigned int* res_mask;   // optional (flat 1x1 only): y = conv + (mask bit ? res : 0), 1 bit / element
     float* y;                              // NHWC output
     float* stats_partial;                  // optional: per-channel (sum, sum^2) partials of the raw output,
     int* stats_blocks;                     //   [*stats_blocks][2][Cout] (HOST out: number of partial rows written)

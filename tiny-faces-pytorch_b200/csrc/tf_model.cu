@@ -478,7 +478,7 @@ struct Model {
     // conv backward of unit u given dy at (Ho, Wo): weight gradient (always) and input gradient into dx
     // (dx_accumulate: add into dx instead of overwriting); dx == null skips the dgrad.
     int unit_conv_bwd(const Unit& u, const float* dy, const float* dy_lo, float* dx, int dx_accumulate, int dxH, int dxW,
-                      void* const* grads, cudaStream_t st) {
+                      void* const* grads, cudaStream_t st, const float* res = nullptr, const unsigned int* res_mask = nullptr) {
         const ConvP& c = u.c;
         const int taps = c.k * c.k;
         // ---- wgrad (a stride-2 conv reads x through the TMA traversal stride; dy stays at the output resolution)
@@ -519,6 +519,7 @@ struct Model {
                 }
             } else {
                 a.x = dy; a.x_lo = dy_lo; a.H = u.H; a.W = u.W; a.y = dx; a.accumulate = dx_accumulate;
+                if (res) { a.res = res; a.res_mask = res_mask; a.accumulate = 0; }     // dx = dgrad + masked upstream gradient
                 if (a.x_lo == nullptr) a.w_lo = nullptr;
                 if (!ar.dry) RC(tfg::conv_fprop(a, st));
             }
@@ -531,8 +532,11 @@ struct Model {
         const int C4 = s.u3.c.cout;
         float *dy3, *dy3_lo;
         const bool has_ds = s.has_ds;
-        // G = dout * [out > 0]: with an identity shortcut dx simply starts as G, otherwise G feeds the downsample BN
-        float* g = has_ds ? ar.f((size_t)Mo * C4) : dx;
+        // G = dout * [out > 0]: it feeds the downsample BN when there is one; with an identity shortcut it is never
+        // materialised -- the conv1 dgrad epilogue adds the masked dout itself (tf_debug_set(8, 1): old path, dx starts
+        // as G and the dgrad reduce-adds onto it)
+        const bool fuse_g = !has_ds && s.u1.c.k == 1 && s.u1.c.stride == 1 && !tfg::debug_flag(8);
+        float* g = has_ds ? ar.f((size_t)Mo * C4) : (fuse_g ? nullptr : dx);
         RC(unit_bn_bwd(s.u3, dout, s.omask, g, &dy3, &dy3_lo, grads, st));
         const long long M2o = (long long)s.B * s.u2.Ho * s.u2.Wo;
         float* da2 = ar.f((size_t)M2o * s.u2.c.cout);
@@ -549,7 +553,8 @@ struct Model {
             RC(unit_bn_bwd(s.ud, g, nullptr, nullptr, &dyd, &dyd_lo, grads, st));
             RC(unit_conv_bwd(s.ud, dyd, dyd_lo, dx, 0, s.H, s.W, grads, st));          // dx = downsample path
         }
-        RC(unit_conv_bwd(s.u1, dy1, dy1_lo, dx, 1, s.H, s.W, grads, st));              // dx += main path
+        if (fuse_g) RC(unit_conv_bwd(s.u1, dy1, dy1_lo, dx, 0, s.H, s.W, grads, st, dout, s.omask));   // dx = main path + G
+        else RC(unit_conv_bwd(s.u1, dy1, dy1_lo, dx, 1, s.H, s.W, grads, st));         // dx += main path
         return TF_OK;
     }
 
@@ -623,14 +628,12 @@ struct Model {
             max_used = std::max(max_used, ar.off - (scratch_mark + (size_t)r * region));
             dcur = dx;
         }
-        if (ar.dry) { bwd_region_bytes = tf_align_up(max_used, 1024); ar.peak = std::max(ar.peak, scratch_mark + 2 * bwd_region_bytes + 4096); }
-        else if (side) {
-            RC(wgrad_flush(st));
-            TF_CHECK_CUDA(cudaEventRecord(ev_region[0], side));
-            TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[0], 0));          // the stem scratch below overlays both regions
-            TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[1], 0));
-        }
-        ar.off = scratch_mark;
+        if (ar.dry) bwd_region_bytes = tf_align_up(max_used, 1024);
+        else if (side) RC(wgrad_flush(st));
+        // the stem's scratch lives BEHIND the two regions (1.3 GB more workspace at batch-8 960x1280): the chain does not
+        // have to wait for the layer-1 weight gradients still running on the side stream
+        ar.off = scratch_mark + 2 * bwd_region_bytes;
+        ar.peak = std::max(ar.peak, ar.off + 4096);
         // ---- stem
         const long long M2 = (long long)B * H2 * W2;
         float* da0 = ar.f((size_t)M2 * 64);

@@ -42,7 +42,7 @@ def run_case(spec, steps=8, warmup=3, B=8, H=960, W=1280):
     model = DetectionModel(pretrained_weights=None, num_templates=25).to(dev)
     model.train()
     crit = DetectionCriterion(25, sampler="device", seed=0)
-    opt = torch.optim.SGD(model.learnable_parameters(1e-4), momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD(model.learnable_parameters(1e-4), momentum=0.9, weight_decay=5e-4, fused=True)
     H3, W3 = (H + 7) // 8, (W + 7) // 8
     img = synthetic.images(B, H, W, seed=0).to(dev)
     cm, rm = synthetic.targets(B, H3, W3, 25, seed=0)

@@ -22,7 +22,7 @@ def main():
     model = DetectionModel(pretrained_weights=None, num_templates=25).to(dev)
     model.train()
     crit = DetectionCriterion(25, sampler="device", seed=0)
-    opt = torch.optim.SGD(model.learnable_parameters(1e-4), momentum=0.9, weight_decay=5e-4)
+    opt = torch.optim.SGD(model.learnable_parameters(1e-4), momentum=0.9, weight_decay=5e-4, fused=True)
     img = synthetic.images(B, H, W, seed=0).to(dev)
     cm, rm = synthetic.targets(B, (H + 7) // 8, (W + 7) // 8, 25, seed=0)
     cm, rm = cm.to(dev), rm.to(dev)
