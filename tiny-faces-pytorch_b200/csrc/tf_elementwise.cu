@@ -5,6 +5,7 @@
 // and its autograd backward.  All tensors are [pixels, C] with C % 4 == 0; accesses are float4.
 #include "tf_common.cuh"
 #include "tf_elementwise.h"
+#include "tf_conv_gemm.h"
 #include <algorithm>
 #include <cstdlib>
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                                                                const unsigned int* __restrict__ mask,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, long long M, int C,
-                                                               float* __restrict__ partial, int slots) {
+                                                               float* __restrict__ partial, int slots, int descending) {
     const int groups = C / 4;                       // float4 channel groups (16 .. 256, a power of two)
     const int lanes = EW_THREADS / groups;          // row lanes per block (1 .. 16)
     const int g = threadIdx.x / lanes, rl = threadIdx.x % lanes;
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                 float4 v[4], y[4]; unsigned int nib[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const long long i = (r + u * step) * C + g * 4;
+                    const long long row = descending ? M - 1 - (r + u * step) : r + u * step;
+                    const long long i = row * C + g * 4;
                     v[u] = ld4(a + i); y[u] = ld4(b + i); nib[u] = mask_nibble(mask, i);
                 }
 #pragma unroll
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
             }
         }
         for (; r < M; r += step) {
-            const long long i = r * C + g * 4;
+            const long long i = (descending ? M - 1 - r : r) * C + g * 4;
             float4 v = ld4(a + i);
             if (MODE == 0) {
                 s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
@@ -243,9 +245,14 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
                                                               const float* __restrict__ rscale,
                                                               const float* __restrict__ rshift, int relu, long long n4,
                                                               int C, float* __restrict__ out, float* __restrict__ out_lo,
-                                                              int mode, unsigned int* __restrict__ mask_out) {
+                                                              int mode, unsigned int* __restrict__ mask_out, int descending) {
+    // descending: walk the tensor from its end -- the GEMM that produced y wrote it front to back, so its tail is what
+    // is still in L2, and the consumer GEMM then starts at the front, which this pass wrote last
     const long long n4_up = (n4 + 31) & ~31ll;          // whole warps iterate together (the mask needs shuffles)
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4_up; t += (long long)gridDim.x * blockDim.x) {
+    const long long nchunks = (n4_up + blockDim.x - 1) / blockDim.x;
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const long long t = (descending ? nchunks - 1 - ch : ch) * blockDim.x + threadIdx.x;
+        if (t >= n4_up) continue;                       // (only whole warps drop out: n4_up and blockDim are multiples of 32)
         const long long i = t * 4;
         const bool live = t < n4;
         float4 v = make_float4(0, 0, 0, 0);
@@ -632,7 +639,8 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
              cudaStream_t st) {
     TF_REQUIRE(C >= 4 && (C & (C - 1)) == 0, "bn_apply: C=%d must be a power of two", C);
     const long long n4 = M * C / 4;
-    bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out);
+    bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out,
+                                                             tfg::debug_flag(9) & 1);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -642,7 +650,7 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
     RC_CARVEOUT(colreduce_kernel<1>); RC_CARVEOUT(bn_bwd_finalize_kernel); RC_CARVEOUT(bn_bwd_apply_kernel);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS);
+    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS, (tfg::debug_flag(9) >> 1) & 1);
     bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(slots, nb < BN_BWD_SLOTS ? nb : BN_BWD_SLOTS, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
@@ -653,7 +661,7 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
 int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st) {
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0 && M > 0, "column_stats: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0);
+    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0);
     TF_LAUNCH_CHECK();
     *nblk = nb;
     return TF_OK;
@@ -662,7 +670,7 @@ int column_sum(const float* a, long long M, int C, int Cout, float* out, float* 
     RC_CARVEOUT(colreduce_kernel<2>); RC_CARVEOUT(colsum_finalize_kernel);
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "column_sum: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0);
+    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0);
     colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out);
     TF_LAUNCH_CHECK();
     return TF_OK;
