@@ -140,27 +140,32 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
 }
 
 // Sum of the per-block partials of 32 channels with FIN_LANES row lanes per channel (fp64), valid for threadIdx.y == 0.
-// 8 KB of static shared memory: small enough to sit next to a side-stream weight-gradient CTA (which leaves 32 KB).
-constexpr int FIN_LANES = 16;
+// 16 KB of static shared memory: small enough to sit next to a side-stream weight-gradient CTA (which leaves 32 KB).
+constexpr int FIN_LANES = 32;
 template <bool CLEAN>
 __device__ __forceinline__ void reduce_partials(float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
     __shared__ double sh[2][FIN_LANES][32];
     s = 0; q = 0;
     if (c < C) {
-        double s2 = 0, q2 = 0;
+        // four independent rows per iteration: this is a latency chain through L2 (up to 592 rows / 32 lanes deep)
+        double sa[4] = {0, 0, 0, 0}, qa[4] = {0, 0, 0, 0};
         int b = threadIdx.y;
-        for (; b + FIN_LANES < nblk; b += 2 * FIN_LANES) {      // two independent rows per iteration
-            float* r0 = partial + (size_t)b * 2 * C + c; float* r1 = partial + (size_t)(b + FIN_LANES) * 2 * C + c;
-            s += r0[0]; q += r0[C];
-            s2 += r1[0]; q2 += r1[C];
-            if (CLEAN) { r0[0] = 0.f; r0[C] = 0.f; r1[0] = 0.f; r1[C] = 0.f; }     // slot rows are left zeroed for the next user
+        for (; b + 3 * FIN_LANES < nblk; b += 4 * FIN_LANES) {
+            float v[4], w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { float* r = partial + (size_t)(b + u * FIN_LANES) * 2 * C + c; v[u] = r[0]; w[u] = r[C]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                sa[u] += v[u]; qa[u] += w[u];
+                if (CLEAN) { float* r = partial + (size_t)(b + u * FIN_LANES) * 2 * C + c; r[0] = 0.f; r[C] = 0.f; }   // slot rows are left zeroed
+            }
         }
-        if (b < nblk) {
-            float* r0 = partial + (size_t)b * 2 * C + c;
-            s += r0[0]; q += r0[C];
-            if (CLEAN) { r0[0] = 0.f; r0[C] = 0.f; }
+        for (; b < nblk; b += FIN_LANES) {
+            float* r = partial + (size_t)b * 2 * C + c;
+            sa[0] += r[0]; qa[0] += r[C];
+            if (CLEAN) { r[0] = 0.f; r[C] = 0.f; }
         }
-        s += s2; q += q2;
+        s = (sa[0] + sa[1]) + (sa[2] + sa[3]); q = (qa[0] + qa[1]) + (qa[2] + qa[3]);
     }
     sh[0][threadIdx.y][threadIdx.x] = s; sh[1][threadIdx.y][threadIdx.x] = q;
     __syncthreads();

@@ -78,7 +78,7 @@ struct Model {
     // when a dgrad GEMM of the chain and a weight-gradient GEMM of the side stream are both ready, the block scheduler
     // hands the SMs to the chain first (both kernels need a whole SM's shared memory, so they cannot co-reside).
     cudaStream_t chain = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_region[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr, ev_region[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
     // wgrad_mode 0: weight gradient forked before its dgrad is enqueued; 1: forked before, enqueued after the dgrad;
     //            2: deferred -- a block's three weight gradients are enqueued when the NEXT block's bn3 backward
     //               (the longest HBM-bound stretch of the chain, ~6 passes over a 1024-channel tensor) starts
@@ -93,6 +93,7 @@ struct Model {
         TF_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_pack, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_region[i], cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_chain[i], cudaEventDisableTiming));
         int least = 0, greatest = 0;
@@ -102,7 +103,7 @@ struct Model {
     }
     ~Model() {
         if (side) {
-            cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join);
+            cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_pack);
             for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_region[i]); cudaEventDestroy(ev_chain[i]); }
         }
     }
@@ -337,6 +338,20 @@ struct Model {
         return TF_OK;
     }
 
+    bool pack_pending = false;
+    // every dgrad (transposed, tap-flipped) weight of the backward pass, one launch
+    int prepack_dgrad_weights(cudaStream_t st) {
+        jobs.clear(); jobs_total = 0;
+        for (const BlockP& bp : blocks) {
+            prepack_add(bp.c1, bp.c1.cin, bp.c1.cout, 1); prepack_add(bp.c2, bp.c2.cin, bp.c2.cout, 1);
+            prepack_add(bp.c3, bp.c3.cin, bp.c3.cout, 1);
+            if (bp.has_ds) prepack_add(bp.cd, bp.cd.cin, bp.cd.cout, 1);
+        }
+        ConvP t3; t3.w = s3_w; t3.cin = 512; t3.cout = Cn; t3.k = 1;
+        ConvP t4; t4.w = s4_w; t4.cin = 1024; t4.cout = Cn; t4.k = 1;
+        prepack_add(t3, 512, Cp, 1); prepack_add(t4, 1024, Cp, 1);
+        return prepack_flush(st);
+    }
     int forward(const float* x_nchw, float* out_nchw, cudaStream_t st) {
         H2 = (H - 1) / 2 + 1; W2 = (W - 1) / 2 + 1;
         Hp = (H2 - 1) / 2 + 1; Wp = (W2 - 1) / 2 + 1;
@@ -345,10 +360,19 @@ struct Model {
         coef = ar.f(3 * 1024);
         dwtmp = ar.f((size_t)1024 * 1024 + 4096);
         offdiag = ar.f(64);
-        {   // every fprop weight of this pass, one launch
+        {   // Weight re-layout, batched.  Training: only the stem's weight is packed on the caller's stream; every other
+            // fprop weight AND the transposed / tap-flipped dgrad weights of the backward are packed on the side stream
+            // while the stem (im2col, GEMM, BN, max-pool: ~1.4 ms of HBM-bound work) runs -- off the critical path.
             packed.clear(); jobs.clear(); jobs_total = 0;
+            if (!ar.dry && training) RC(ensure_side());
+            const bool aside = training && (ar.dry || side);
+            cudaStream_t ps = (aside && !ar.dry) ? side : st;
             ConvP c = stem; c.cin = 147; c.k = 1;
             prepack_add(c, 64, 160, 0);
+            if (aside) {
+                RC(prepack_flush(st));
+                if (!ar.dry) { TF_CHECK_CUDA(cudaEventRecord(ev_fork, st)); TF_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0)); }
+            }
             for (const BlockP& bp : blocks) {
                 prepack_add(bp.c1, bp.c1.cout, bp.c1.cin, 0); prepack_add(bp.c2, bp.c2.cout, bp.c2.cin, 0);
                 prepack_add(bp.c3, bp.c3.cout, bp.c3.cin, 0);
@@ -357,7 +381,12 @@ struct Model {
             ConvP h3; h3.w = s3_w; h3.cin = 512; h3.cout = Cn; h3.k = 1;
             ConvP h4; h4.w = s4_w; h4.cin = 1024; h4.cout = Cn; h4.k = 1;
             prepack_add(h3, Cp, 512, 0); prepack_add(h4, Cp, 1024, 0);
-            RC(prepack_flush(st));
+            RC(prepack_flush(ps));
+            if (training) {
+                RC(prepack_dgrad_weights(ps));
+                if (aside && !ar.dry) TF_CHECK_CUDA(cudaEventRecord(ev_pack, side));
+            }
+            pack_pending = aside && !ar.dry;
         }
         if (!training) RC(prepare_eval_all(st)); else eval_ss.clear();
         // ---- stem: im2col + GEMM (K = 147 padded to 160), BN, ReLU, max-pool
@@ -433,6 +462,7 @@ struct Model {
             for (int k = 0; k < 2; ++k) { pp[k] = ar.f(mx); pp_lo[k] = mode == 2 ? ar.f(mx) : nullptr; }
         }
         const size_t scratch_mark = ar.off;
+        if (pack_pending) { TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_pack, 0)); pack_pending = false; }   // packed weights are ready
         const float* cur = pool; const float* cur_lo = pool_lo;
         int ch = Hp, cw = Wp;
         for (size_t i = 0; i < blocks.size(); ++i) {
@@ -587,18 +617,6 @@ struct Model {
         Unit h3; h3.c.w = s3_w; h3.c.cin = 512; h3.c.cout = Cp; h3.c.k = 1; h3.x = res3; h3.x_lo = nullptr; h3.B = B; h3.H = H3; h3.W = W3; h3.Ho = H3; h3.Wo = W3;
         Unit h4 = h3; h4.c.w = s4_w; h4.c.cin = 1024; h4.x = res4; h4.H = H4; h4.W = W4; h4.Ho = H4; h4.Wo = W4;
         float* dres4 = ar.f((size_t)M4 * 1024);
-        {   // every dgrad (transposed, tap-flipped) weight of this pass, one launch
-            jobs.clear(); jobs_total = 0;
-            for (const BlockP& bp : blocks) {
-                prepack_add(bp.c1, bp.c1.cin, bp.c1.cout, 1); prepack_add(bp.c2, bp.c2.cin, bp.c2.cout, 1);
-                prepack_add(bp.c3, bp.c3.cin, bp.c3.cout, 1);
-                if (bp.has_ds) prepack_add(bp.cd, bp.cd.cin, bp.cd.cout, 1);
-            }
-            ConvP t3; t3.w = s3_w; t3.cin = 512; t3.cout = Cn; t3.k = 1;
-            ConvP t4; t4.w = s4_w; t4.cin = 1024; t4.cout = Cn; t4.k = 1;
-            prepack_add(t3, 512, Cp, 1); prepack_add(t4, 1024, Cp, 1);
-            RC(prepack_flush(st));
-        }
         // input gradients ping-pong between two buffers; one scratch region is reused by every other block
         size_t mx = 0;
         for (const BlockS& s : bs) mx = std::max(mx, (size_t)s.B * s.H * s.W * s.u1.c.cin);
