@@ -214,12 +214,13 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ms_total = timed(step_resident, args.steps, args.warmup)
-    sampler.stop_flag = True
     if args.profile_mode:
+        sampler.stop_flag = True
         if rank == 0:
             print(json.dumps(dict(profile_mode=True, ms_per_step=ms_total / args.steps)))
         return
     ms_e2e = timed(step_e2e, args.steps, 1)
+    sampler.stop_flag = True                     # clocks are sampled over both timed regions (resident + end-to-end)
     imgs = B * world * args.steps
     value = imgs / (ms_total / 1000.0)
     e2e_value = imgs / (ms_e2e / 1000.0)
@@ -239,47 +240,9 @@ def main():
     line["step_tflops"] = STEP_GFLOP_PER_IMG * value / 1000.0
     line["step_frac_of_tf32_sustained"] = line["step_tflops"] / (pk["tf32_sustained"] * world)
 
-    # ---- kernel launch census of one step (CUPTI via torch.profiler; not timed).  The step contains the gradient
-    #      all-reduce, so EVERY rank runs it; only rank 0 records.
-    prof = None
-    try:
-        if rank == 0:
-            from torch.profiler import ProfilerActivity, profile
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                step_resident()
-                torch.cuda.synchronize()
-        else:
-            step_resident()
-            torch.cuda.synchronize()
-    except Exception as ex:      # noqa: BLE001
-        line["profiler_error"] = str(ex)[:200]
+    # ---- isolated micro-benchmarks first (roofline kernel, NMS, pyramid inference): torch.profiler leaves CUPTI attached,
+    #      which slows the host round trips of the latency-bound NMS afterwards
     if rank == 0:
-        try:
-            if prof is None:
-                raise RuntimeError("no profile")
-            ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-            mine = [e for e in ev if any(s in e.name for s in ("conv_gemm_kernel", "conv_wgrad_kernel", "kernel<", "_kernel"))
-                    and "at::native" not in e.name and "nccl" not in e.name.lower()]
-            line["gpu_launches"] = len(mine)
-            line["gpu_launches_all"] = len(ev)
-            tot = sum(e.device_time for e in ev) or 1.0
-            gemm = sum(e.device_time for e in ev if "conv_gemm_kernel" in e.name or "conv_wgrad_kernel" in e.name)
-            line["gemm_share_of_step"] = gemm / tot
-            if args.breakdown:
-                agg = {}
-                for e in ev:
-                    a = agg.setdefault(e.name[:110], [0, 0.0])
-                    a[0] += 1
-                    a[1] += e.device_time
-                with open(args.breakdown, "w") as f:
-                    f.write("# one training step, batch-8 960x1280, torch.profiler (CUPTI) device times\n")
-                    f.write("%-112s %6s %10s %6s\n" % ("kernel", "calls", "total_us", "share"))
-                    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                        f.write("%-112s %6d %10.1f %5.1f%%\n" % (k, n, t, 100.0 * t / tot))
-        except Exception as ex:      # noqa: BLE001
-            line["gpu_launches"] = None
-            line["profiler_error"] = str(ex)[:200]
-
         # ---- roofline of the dominant kernel: layer3 3x3 256->256 at this config (8x60x80), isolated, CUDA events
         Bc, Hc, Wc, C = B, H3 // 2, W3 // 2, 256
         xc = torch.randn(Bc, Hc, Wc, C, device=dev)
@@ -338,6 +301,47 @@ def main():
                 del imodel
             except Exception as ex:  # noqa: BLE001
                 line["inference"] = dict(error=str(ex)[:300])
+
+    # ---- kernel launch census of one step (CUPTI via torch.profiler; not timed).  The step contains the gradient
+    #      all-reduce, so EVERY rank runs it; only rank 0 records.
+    prof = None
+    try:
+        if rank == 0:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step_resident()
+                torch.cuda.synchronize()
+        else:
+            step_resident()
+            torch.cuda.synchronize()
+    except Exception as ex:      # noqa: BLE001
+        line["profiler_error"] = str(ex)[:200]
+    if rank == 0:
+        try:
+            if prof is None:
+                raise RuntimeError("no profile")
+            ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+            mine = [e for e in ev if any(s in e.name for s in ("conv_gemm_kernel", "conv_wgrad_kernel", "kernel<", "_kernel"))
+                    and "at::native" not in e.name and "nccl" not in e.name.lower()]
+            line["gpu_launches"] = len(mine)
+            line["gpu_launches_all"] = len(ev)
+            tot = sum(e.device_time for e in ev) or 1.0
+            gemm = sum(e.device_time for e in ev if "conv_gemm_kernel" in e.name or "conv_wgrad_kernel" in e.name)
+            line["gemm_share_of_step"] = gemm / tot
+            if args.breakdown:
+                agg = {}
+                for e in ev:
+                    a = agg.setdefault(e.name[:110], [0, 0.0])
+                    a[0] += 1
+                    a[1] += e.device_time
+                with open(args.breakdown, "w") as f:
+                    f.write("# one training step, batch-8 960x1280, torch.profiler (CUPTI) device times\n")
+                    f.write("%-112s %6s %10s %6s\n" % ("kernel", "calls", "total_us", "share"))
+                    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                        f.write("%-112s %6d %10.1f %5.1f%%\n" % (k, n, t, 100.0 * t / tot))
+        except Exception as ex:      # noqa: BLE001
+            line["gpu_launches"] = None
+            line["profiler_error"] = str(ex)[:200]
 
         # ---- CPU baseline beside it (bounded sample)
         if world == 1 and not args.no_cpu_baseline:

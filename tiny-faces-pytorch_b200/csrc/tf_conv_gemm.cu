@@ -368,13 +368,13 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 // Barrier protocol: full[s] lives in the leader (count 1 = the leader producer's expect_tx of BOTH CTAs' bytes; both
 // producers' TMA complete_tx on it); empty[s] / tfull[a] exist in both CTAs and are signalled by multicast commits;
 // tempty[a] lives in the leader and collects the 256 epilogue threads of both CTAs.
-constexpr bool TWO_CTA_DEFAULT = false;     // flipped once the kernel is validated and faster on the GPU
 constexpr int G2_BN = 256;
 constexpr int G2_STAGES = 6;
 constexpr int G2_B_STAGE_BYTES = 128 * 128;                        // this CTA's half of the B tile
 constexpr int G2_STAGE_BYTES = A_STAGE_BYTES + G2_B_STAGE_BYTES;   // 32 KB
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 + 1024;
 
+template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     constexpr int BN = G2_BN;
@@ -510,9 +510,9 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 else { tc_fence_before(); mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[acc]), 0)); }
                 if (!real_tile) continue;
                 uint8_t* buf = wbuf + ebuf * 4096;
-                if (p.spatial) epilogue_chunk<true, true>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
+                if (p.spatial) epilogue_chunk<FUSED, true>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
                                                           x0 + wx, y0 + wy, img, st_sum[chunk], st_sq[chunk]);
-                else           epilogue_chunk<true, false>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
+                else           epilogue_chunk<FUSED, false>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
                                                            m0 + q * 32, 0, 0, st_sum[chunk], st_sq[chunk]);
                 ebuf ^= 1;
             }
@@ -807,19 +807,24 @@ int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_
     if (p.spatial) return fused ? launch_gemm_variant<BN, true, true, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, true, false>(maps, p, grid, st);
     return fused ? launch_gemm_variant<BN, true, false, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, false, false>(maps, p, grid, st);
 }
-int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cudaStream_t st) {
+template <bool FUSED>
+int launch_gemm2_variant(const GemmMaps& maps, const GemmParams& p, int clusters, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
         attr_set = true;
     }
+    conv_gemm2_kernel<FUSED><<<2 * clusters, GEMM_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
+    TF_LAUNCH_CHECK();
+    return TF_OK;
+}
+int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cudaStream_t st) {
     const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     int clusters = pair_tiles < g_num_sms / 2 ? pair_tiles : g_num_sms / 2;
     clusters = clusters / p.num_n_tiles * p.num_n_tiles;                 // every cluster keeps one n-tile
     if (stats_rows) *stats_rows = clusters / p.num_n_tiles * 2 * 4;
-    conv_gemm2_kernel<<<2 * clusters, GEMM_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
-    TF_LAUNCH_CHECK();
-    return TF_OK;
+    if (p.scale || p.shift || p.relu || p.round_out) return launch_gemm2_variant<true>(maps, p, clusters, st);
+    return launch_gemm2_variant<false>(maps, p, clusters, st);
 }
 template <int BN>
 int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
@@ -918,7 +923,11 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
             if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, bw, bh))) return rc;
         }
     }
-    const bool two_cta = BN == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || TWO_CTA_DEFAULT) && p.num_m_tiles >= 2 && !a.res;
+    // 2-CTA (cta_group::2, 256 x 256 tiles): measured on B200 at batch-8 960x1280 -- K = 1024 1x1 (N = 256): 48.1 vs 52.8 us
+    // (49.4 vs 53.1 with the statistics epilogue); K = 256 -> N = 1024: 52.4 vs 53.8 (noise); 3x3: 77 vs 69 (the one-CTA
+    // kernel has the tail split-K).  So: flat GEMMs with a long K loop and a single 256-wide n-tile.
+    const bool two_cta_auto = !spatial && Cout == 256 && Cin >= 512 && p.nseg == 1;
+    const bool two_cta = BN == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || two_cta_auto) && p.num_m_tiles >= 2 && !a.res;
     for (int s = 0; s < p.nseg; ++s)
         if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, two_cta ? 128 : BN))) return rc;
     int stats_rows = 0;

@@ -5,10 +5,13 @@
 //   2. sort-and-sweep along x: boxes are sorted by x1; box a only meets boxes whose x1 lies in [x1_a, x2_a], so
 //      the number of exact IoU tests is sum_a #{b : x1_a <= x1_b <= x2_a} instead of N^2/2
 //   3. every conflicting pair (IoU > thr, evaluated with the reference's operation order) becomes an edge
-//      earlier-rank -> later-rank, stored CSR by the later box (count pass, scan, fill pass)
+//      (earlier rank, later rank) appended to ONE unordered list by warp-aggregated atomics -- a single sweep; the
+//      first version ran the sweep twice (count pass, scan, CSR fill pass) and the IoU tests are the cost
 //   4. greedy resolution as a monotone fixed point: a box is KEPT once all its earlier conflicting boxes are
-//      REMOVED, REMOVED once any of them is KEPT.  Every round decides at least the first undecided box and in
-//      practice the dependency chains are short, so a few rounds settle all N boxes in parallel.
+//      REMOVED, REMOVED once any of them is KEPT.  One round = an edge pass (an edge whose earlier box is KEPT removes
+//      the later one; an edge whose earlier box is still undecided blocks it) + a node pass (undecided and not
+//      blocked -> KEPT).  Every round decides at least the first undecided box and in practice the dependency
+//      chains are short, so a few rounds settle all N boxes in parallel.
 //   5. order-preserving compaction of the kept ranks -> original indices, descending score.
 //
 // Greedy NMS is defined by exactly this recurrence (keep(j) <=> no kept i < j with IoU(i, j) > thr), so the
@@ -17,8 +20,8 @@
 #include "tf_common.cuh"
 #include "tf_nms_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
+#include <algorithm>
 
 using namespace tfnms;
 
@@ -51,20 +54,19 @@ __global__ void gather_x_kernel(const Box<T>* __restrict__ sb, const T* __restri
     xarea[i] = area[r];
 }
 // One WARP per box a (position p in x order): the 32 lanes test 32 consecutive x-successors per step, so dense
-// inputs (real detections overlap thousands of x-neighbours) stay parallel.
-// FILL == 0: count conflicts per later box; FILL == 1: write the earlier box of each conflict into the CSR rows.
-template <typename T, int FILL>
+// inputs (real detections overlap thousands of x-neighbours) stay parallel.  Conflicts go to the edge list as
+// (earlier rank, later rank); entries past the capacity are counted but not stored (the host then falls back).
+template <typename T>
 __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ xb, const T* __restrict__ xarea,
                                                     const int* __restrict__ xorder, int n, double thr,
-                                                    unsigned int* __restrict__ count, const unsigned int* __restrict__ offset,
-                                                    unsigned int* __restrict__ cursor, int* __restrict__ edges) {
+                                                    unsigned long long* __restrict__ nedges, int2* __restrict__ edges,
+                                                    unsigned long long cap) {
     const int p = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (p >= n) return;
     const int a = xorder[p];                       // rank (score order) of this box
     const Box<T> A = xb[p];
     const T aa = xarea[p];
-    unsigned int mine = 0;                         // conflicts whose later box is a (lane-private count)
     for (int base = p + 1; base < n; base += 32) {
         const int q = base + lane;
         bool live = false, hit = false;
@@ -77,44 +79,43 @@ __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ x
                 hit = a < b ? suppresses<T>(A, aa, Bx, xarea[q], thr, true) : suppresses<T>(Bx, xarea[q], A, aa, thr, true);
             }
         }
-        if (hit) {
-            if (b > a) {                           // the neighbour is the later box: its own row
-                if (FILL) edges[offset[b] + atomicAdd(&cursor[b], 1u)] = a;
-                else atomicAdd(&count[b], 1u);
-            } else {                               // a is the later box: aggregate in the warp
-                if (!FILL) ++mine;
-            }
-        }
-        if (FILL) {
-            const unsigned int m = __ballot_sync(0xffffffffu, hit && b < a);
-            if (m) {
-                unsigned int start = 0;
-                if (lane == 0) start = atomicAdd(&cursor[a], (unsigned int)__popc(m));
-                start = __shfl_sync(0xffffffffu, start, 0);
-                if (hit && b < a) edges[offset[a] + start + __popc(m & ((1u << lane) - 1u))] = b;
-            }
+        const unsigned int m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            unsigned long long start = 0;
+            if (lane == 0) start = atomicAdd(nedges, (unsigned long long)__popc(m));
+            start = __shfl_sync(0xffffffffu, start, 0);
+            const unsigned long long e = start + __popc(m & ((1u << lane) - 1u));
+            if (hit && e < cap) edges[e] = a < b ? make_int2(a, b) : make_int2(b, a);
         }
         if (!__any_sync(0xffffffffu, live)) break;
         if (!__shfl_sync(0xffffffffu, (int)live, 31) ) break;      // lane 31 past the x range: so is everything after
     }
-    if (!FILL) {
-        mine = (unsigned int)tf_warp_sum((int)mine);
-        if (lane == 0 && mine) atomicAdd(&count[a], mine);
+}
+// one relaxation round = edge pass + node pass; states only move UNDECIDED -> KEPT / REMOVED (both final), so racing /
+// stale reads only ever delay a decision to the next round
+__global__ void edge_pass_kernel(const int2* __restrict__ edges, unsigned long long nedges, volatile unsigned char* state,
+                                 unsigned char* __restrict__ blocked) {
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < nedges;
+         e += (unsigned long long)gridDim.x * blockDim.x) {
+        const int2 ed = edges[e];                  // x = earlier rank, y = later rank
+        if (state[ed.y] != UNDECIDED) continue;
+        const unsigned char si = state[ed.x];
+        if (si == KEPT) state[ed.y] = REMOVED;
+        else if (si == UNDECIDED) blocked[ed.y] = 1;
     }
 }
-// one relaxation round; states only move UNDECIDED -> KEPT / REMOVED, so racing reads are harmless
-__global__ void resolve_kernel(const unsigned int* __restrict__ offset, const int* __restrict__ edges, int n,
-                               volatile unsigned char* state, int* __restrict__ undecided) {
+__global__ void node_pass_kernel(volatile unsigned char* state, unsigned char* __restrict__ blocked, int n,
+                                 int* __restrict__ undecided) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n || state[j] != UNDECIDED) return;
-    bool all_removed = true;
-    for (unsigned int e = offset[j]; e < offset[j + 1]; ++e) {
-        const unsigned char s = state[edges[e]];
-        if (s == KEPT) { state[j] = REMOVED; return; }
-        if (s == UNDECIDED) all_removed = false;
+    bool still = false;
+    if (j < n && state[j] == UNDECIDED) {
+        if (!blocked[j]) state[j] = KEPT;          // every earlier conflicting box was REMOVED (or there is none)
+        else { blocked[j] = 0; still = true; }
     }
-    if (all_removed) state[j] = KEPT;
-    else if (undecided) atomicAdd(undecided, 1);
+    if (undecided) {
+        const unsigned int m = __ballot_sync(0xffffffffu, still);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(undecided, __popc(m));
+    }
 }
 __global__ void flags_kernel(const unsigned char* __restrict__ state, int n, unsigned char* __restrict__ flags) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,27 +130,25 @@ __global__ void widen_kernel(const int* __restrict__ sel, const int* __restrict_
 
 template <typename T>
 struct SweepPlan {
-    size_t sort_bytes = 0, scan_bytes = 0, select_bytes = 0, total = 0;
+    size_t sort_bytes = 0, select_bytes = 0, total = 0;
     size_t edge_cap = 0;
     explicit SweepPlan(int64_t n) {
         cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, (const T*)nullptr, (T*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n);
         size_t s2 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, s2, (const T*)nullptr, (T*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n);
         sort_bytes = sort_bytes > s2 ? sort_bytes : s2;
-        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr, (int)n + 1);
         cub::DeviceSelect::Flagged(nullptr, select_bytes, (const int*)nullptr, (const unsigned char*)nullptr, (int*)nullptr, (int*)nullptr, (int)n);
-        edge_cap = (size_t)n * 256 + (1u << 20);
-        if (edge_cap > 0xF0000000ull) edge_cap = 0xF0000000ull;
+        edge_cap = (size_t)n * 128 + (1u << 19);                         // (earlier, later) pairs
+        if (edge_cap > 0x70000000ull) edge_cap = 0x70000000ull;
         size_t a = 0;
         auto add = [&](size_t b) { a = tf_align_up(a, 256) + b; };
         add(4 * n); add(4 * n); add(sizeof(T) * n);                      // iota, order, sorted keys
-        add(sort_bytes); add(scan_bytes); add(select_bytes);
+        add(sort_bytes); add(select_bytes);
         add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas by rank
         add(sizeof(T) * n); add(sizeof(T) * n); add(4 * n);               // x keys, sorted x keys, x order
         add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas in x order
-        add(4 * (n + 1)); add(4 * (n + 1)); add(4 * n);                   // counts, offsets, cursors
-        add(4 * edge_cap);                                                // CSR edges
-        add(n); add(n); add(4 * n);                                       // state, flags, selected
+        add(8 * edge_cap);                                                // edge list
+        add(n); add(n); add(n); add(4 * n);                               // state, blocked, flags, selected
         add(256);
         total = a + 256;
     }
@@ -175,7 +174,6 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     int* order = ar.take<int>(n);
     T* keys = ar.take<T>(n);
     void* sort_tmp = ar.take<char>(plan.sort_bytes);
-    void* scan_tmp = ar.take<char>(plan.scan_bytes);
     void* select_tmp = ar.take<char>(plan.select_bytes);
     Box<T>* sb = ar.take<Box<T>>(n);
     T* area = ar.take<T>(n);
@@ -184,14 +182,13 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     int* xorder = ar.take<int>(n);
     Box<T>* xb = ar.take<Box<T>>(n);
     T* xarea = ar.take<T>(n);
-    unsigned int* count = ar.take<unsigned int>(n + 1);
-    unsigned int* offset = ar.take<unsigned int>(n + 1);
-    unsigned int* cursor = ar.take<unsigned int>(n);
-    int* edges = ar.take<int>(plan.edge_cap);
+    int2* edges = ar.take<int2>(plan.edge_cap);
     unsigned char* state = ar.take<unsigned char>(n);
+    unsigned char* blocked = ar.take<unsigned char>(n);
     unsigned char* flags = ar.take<unsigned char>(n);
     int* selected = ar.take<int>(n);
-    int* scalars = ar.take<int>(16);                       // [0] undecided, [1] selected count
+    int* scalars = ar.take<int>(16);                       // [0] undecided, [1] selected count, [2..3] edge counter (u64)
+    unsigned long long* nedges_dev = reinterpret_cast<unsigned long long*>(scalars + 2);
     const int nb = (n + 255) / 256;
 
     iota2_kernel<<<nb, 256, 0, st>>>(iota, n);
@@ -203,21 +200,22 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sb_bytes, (const T*)xkey, xsorted, (const int*)iota, xorder, n, 0,
                                                   (int)sizeof(T) * 8, st));
     gather_x_kernel<T><<<nb, 256, 0, st>>>(sb, area, xorder, n, xb, xarea);
-    TF_CHECK_CUDA(cudaMemsetAsync(count, 0, 4 * (size_t)(n + 1), st));
+    TF_CHECK_CUDA(cudaMemsetAsync(scalars, 0, 16 * sizeof(int), st));
+    TF_CHECK_CUDA(cudaMemsetAsync(state, 0, (size_t)n, st));
+    TF_CHECK_CUDA(cudaMemsetAsync(blocked, 0, (size_t)n, st));
     const int sweep_blocks = (int)(((long long)n * 32 + 255) / 256);
-    sweep_kernel<T, 0><<<sweep_blocks, 256, 0, st>>>(xb, xarea, xorder, n, thr, count, nullptr, nullptr, nullptr);
-    size_t sc_bytes = plan.scan_bytes;
-    TF_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, sc_bytes, count, offset, n + 1, st));
-    unsigned int total_edges = 0;
-    TF_CHECK_CUDA(cudaMemcpyAsync(&total_edges, offset + n, 4, cudaMemcpyDeviceToHost, st));
+    sweep_kernel<T><<<sweep_blocks, 256, 0, st>>>(xb, xarea, xorder, n, thr, nedges_dev, edges, (unsigned long long)plan.edge_cap);
+    unsigned long long total_edges = 0;
+    TF_CHECK_CUDA(cudaMemcpyAsync(&total_edges, nedges_dev, 8, cudaMemcpyDeviceToHost, st));
     TF_CHECK_CUDA(cudaStreamSynchronize(st));
-    if ((size_t)total_edges > plan.edge_cap) return 1;
-    TF_CHECK_CUDA(cudaMemsetAsync(cursor, 0, 4 * (size_t)n, st));
-    sweep_kernel<T, 1><<<sweep_blocks, 256, 0, st>>>(xb, xarea, xorder, n, thr, nullptr, offset, cursor, edges);
-    TF_CHECK_CUDA(cudaMemsetAsync(state, 0, n, st));
+    if (total_edges > (unsigned long long)plan.edge_cap) return 1;
+    const int eb = (int)std::min<unsigned long long>((total_edges + 255) / 256, 148ull * 16);
     for (int round = 0; round < n + 8;) {
         TF_CHECK_CUDA(cudaMemsetAsync(scalars, 0, 4, st));
-        for (int k = 0; k < 4; ++k, ++round) resolve_kernel<<<nb, 256, 0, st>>>(offset, edges, n, state, k == 3 ? scalars : nullptr);
+        for (int k = 0; k < 4; ++k, ++round) {
+            if (total_edges) edge_pass_kernel<<<eb, 256, 0, st>>>(edges, total_edges, state, blocked);
+            node_pass_kernel<<<nb, 256, 0, st>>>(state, blocked, n, k == 3 ? scalars : nullptr);
+        }
         int undecided = 0;
         TF_CHECK_CUDA(cudaMemcpyAsync(&undecided, scalars, 4, cudaMemcpyDeviceToHost, st));
         TF_CHECK_CUDA(cudaStreamSynchronize(st));

@@ -23,10 +23,11 @@ CASES_R1B = [
     ("fprop+2cta", 2, 15, 20, 256, 256, 3), ("fprop+2cta", 1, 63, 63, 256, 256, 3), ("fprop+2cta", 3, 9, 16, 256, 512, 1),
 ]
 CASES = [
-    ("time", 8, 60, 80, 1024, 256, 1), ("time+stats", 8, 60, 80, 1024, 256, 1),
-    ("time", 8, 60, 80, 256, 256, 3), ("time+stats", 8, 60, 80, 256, 256, 3), ("time+nosplit+stats", 8, 60, 80, 256, 256, 3),
-    ("time", 8, 60, 80, 256, 1024, 1), ("time+stats", 8, 60, 80, 256, 1024, 1), ("time+2cta+stats", 8, 60, 80, 256, 1024, 1),
-    ("time+stats", 8, 120, 160, 128, 512, 1), ("time+stats", 8, 240, 320, 64, 256, 1),
+    ("fprop+pf", 2, 15, 20, 1024, 256, 1), ("fprop+pf", 3, 33, 47, 512, 128, 1),
+    ("time", 8, 60, 80, 1024, 256, 1), ("time+pf", 8, 60, 80, 1024, 256, 1), ("time+2cta", 8, 60, 80, 1024, 256, 1),
+    ("time+2cta+stats", 8, 60, 80, 1024, 256, 1), ("time+2cta+stats", 8, 60, 80, 256, 1024, 1), ("time+stats", 8, 60, 80, 256, 1024, 1),
+    ("time", 8, 120, 160, 512, 128, 1), ("time+pf", 8, 120, 160, 512, 128, 1),
+    ("time", 8, 30, 40, 1024, 256, 1), ("time+pf", 8, 30, 40, 1024, 256, 1),
 ]
 CASES_OLD2 = [
     ("wgrad", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 32, 64, 1), ("wgrad+plain", 1, 8, 16, 128, 128, 1),
