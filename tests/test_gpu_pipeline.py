@@ -185,3 +185,34 @@ def test_train_loop_runs_and_updates():
     assert not torch.equal(m.model.layer3[5].conv2.weight.detach().cpu(), w0)
     assert torch.equal(m.score4_upsample.weight.detach().cpu(), up0)          # lr 0 group never moves
     assert int(m.model.bn1.num_batches_tracked) == 2
+
+
+def test_pipelined_loop_equals_step_by_step():
+    """trainer.train_pipelined (double-buffered H2D on a copy stream, loss read one step late) yields exactly the
+    losses of the plain copy-then-step loop: same batches, lr = 0 so that the weights stay put."""
+    from oracle import synth
+    from tinyfaces_b200 import synthetic
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    from tinyfaces_b200.models.model import DetectionModel
+    from tinyfaces_b200.trainer import train_pipelined, train_step
+    dev = torch.device("cuda:0")
+    sd = synth.synthetic_state_dict(seed=2, bn3_gamma=0.25)
+    cm, rm = synthetic.targets(2, 13, 16, seed=1, p_neg=0.7, p_pos=0.1)
+    batches = [(synthetic.images(2, 100, 128, seed=10 + i).pin_memory(), cm.clone().pin_memory(), rm.clone().pin_memory())
+               for i in range(5)]
+
+    def fresh():
+        m = DetectionModel(pretrained_weights=None, num_templates=25)
+        m.load_state_dict(sd)
+        m = m.to(dev)
+        m.train()
+        return m, DetectionCriterion(25, sampler="device", seed=7), torch.optim.SGD(m.learnable_parameters(0.0), momentum=0.9)
+
+    m, crit, opt = fresh()
+    plain = [float(train_step(m, crit, opt, x.to(dev), c.to(dev), r.to(dev))) for x, c, r in batches]
+    m, crit, opt = fresh()
+    piped = list(train_pipelined(m, crit, opt, iter(batches), dev))
+    assert len(piped) == len(plain) == 5
+    assert np.all(np.isfinite(plain))
+    assert piped == plain, (piped, plain)
+    assert len(set(plain)) > 1                          # different batches really went through

@@ -38,13 +38,94 @@ def train_step(model, loss_fn, optimizer, img, class_map, regression_map, group=
     return loss
 
 
+class InputPipeline:
+    """Double-buffered host->device staging of (img, class_map, regression_map) batches on a copy stream, so that the
+    H2D transfer of batch i+1 overlaps the compute of batch i (the reference copies synchronously in the step loop,
+    trainer.py:73-76).  Device slots are allocated once; ordering is by events, never by host synchronisation."""
+
+    def __init__(self, device, depth=2):
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.depth = depth
+        self.slots = [None] * depth
+        self.ready = [None] * depth          # recorded on the copy stream when a slot's copies are enqueued
+        self.free = [None] * depth           # recorded on the compute stream when a slot's batch has been consumed
+        self.head = self.tail = 0            # staged batches are slots [tail, head)
+
+    def stage(self, img, class_map, regression_map):
+        """Start the asynchronous copy of one host batch (pinned memory for true overlap) into the next slot."""
+        assert self.head - self.tail < self.depth, "InputPipeline: all slots are staged"
+        k = self.head % self.depth
+        host = (img, class_map, regression_map)
+        if self.slots[k] is None or any(d.shape != h.shape for d, h in zip(self.slots[k], host)):
+            self.slots[k] = tuple(torch.empty(h.shape, dtype=torch.float32, device=self.device) for h in host)
+            self.free[k] = None
+        with torch.cuda.stream(self.copy_stream):
+            if self.free[k] is not None:
+                self.copy_stream.wait_event(self.free[k])            # the step that used this slot has finished with it
+            else:
+                self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            for d, h in zip(self.slots[k], host):
+                d.copy_(h, non_blocking=True)                        # (also converts uint8 / float64 sources to float32)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        self.ready[k] = ev
+        self.head += 1
+
+    def next(self):
+        """Device tensors of the oldest staged batch; the current stream waits for its copies."""
+        assert self.head > self.tail, "InputPipeline: nothing staged"
+        k = self.tail % self.depth
+        torch.cuda.current_stream(self.device).wait_event(self.ready[k])
+        return self.slots[k]
+
+    def release(self):
+        """Call after the step that consumed next()'s tensors has been enqueued."""
+        k = self.tail % self.depth
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.free[k] = ev
+        self.tail += 1
+
+
+def train_pipelined(model, loss_fn, optimizer, batches, device, group=None):
+    """Step loop over an iterable of HOST batches with the copies and the loss read-back taken off the critical path:
+    batch i+1 is staged while batch i computes, and the loss of step i is read (from a pinned buffer) only after step
+    i+1 has been enqueued.  Yields one Python float per step, in order."""
+    pipe = InputPipeline(device)
+    host_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_ready = [None, None]
+    it = iter(batches)
+    nxt = next(it, None)
+    if nxt is not None:
+        pipe.stage(*nxt)
+    i = 0
+    pending = None                                   # index of the step whose loss has not been yielded yet
+    while nxt is not None:
+        x, c, r = pipe.next()
+        loss = train_step(model, loss_fn, optimizer, x, c, r, group)
+        pipe.release()
+        host_loss[i % 2].copy_(loss.detach(), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(pipe.device))
+        loss_ready[i % 2] = ev
+        nxt = next(it, None)
+        if nxt is not None:
+            pipe.stage(*nxt)                         # overlaps the step just enqueued
+        if pending is not None:
+            loss_ready[pending % 2].synchronize()
+            yield float(host_loss[pending % 2])
+        pending = i
+        i += 1
+    if pending is not None:
+        loss_ready[pending % 2].synchronize()
+        yield float(host_loss[pending % 2])
+
+
 def train(model, loss_fn, optimizer, dataloader, epoch, device):
-    """trainer.py:68-90."""
+    """trainer.py:68-90 (same signature, same per-iteration printout), on the pipelined loop."""
     model = model.to(device)
     model.train()
-    for idx, (img, class_map, regression_map) in enumerate(dataloader):
-        x = img.float().to(device)
-        class_map_var = class_map.float().to(device)
-        regression_map_var = regression_map.float().to(device)
-        train_step(model, loss_fn, optimizer, x, class_map_var, regression_map_var)
-        print_state(idx, epoch, len(dataloader), loss_fn.class_average.average, loss_fn.reg_average.average)
+    n = len(dataloader)
+    for idx, _ in enumerate(train_pipelined(model, loss_fn, optimizer, dataloader, device)):
+        print_state(idx, epoch, n, loss_fn.class_average.average, loss_fn.reg_average.average)
