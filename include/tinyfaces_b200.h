@@ -68,6 +68,12 @@ int tf_conv2d_nhwc_strided(const float* x, int B, int H, int W, int Cin, const f
                            int stride, const float* bias, float* y, void* stream);
 int tf_conv2d_wgrad_nhwc_strided(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
                                  int stride, float* dw_packed /* accumulated */, void* stream);
+/* input gradient of a stride-2 convolution (3x3 pad 1 or 1x1) as 4 parity-class GEMMs, no zero insertion (the dgrad
+ * autograd runs for the stride-2 Bottlenecks, torchvision resnet.py:134,197).  dy: [B, ceil(H/2), ceil(W/2), Cdy];
+ * w_packed: [Cdx][k*k (flipped taps)][Cdy]; dx: [B,H,W,Cdx], overwritten (3x3) or -- accumulate != 0 -- added into;
+ * a 1x1 touches the even pixels only, so the caller supplies the base values of dx (accumulate) or zeros. */
+int tf_conv2d_dgrad_s2_nhwc(const float* dy, int B, int H, int W, int Cdy, const float* w_packed, int Cdx, int ksize,
+                            int accumulate, float* dx, void* stream);
 
 /* ---- one image-pyramid level with the exact arithmetic of tinyfaces/evaluation.py:40-50 (to_pil_image, PIL bilinear
  * resize, ToTensor, Normalize).  img: float32 [3,H,W] in [0,1]; the int32 tables hold Pillow's fixed-point resampling

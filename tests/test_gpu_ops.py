@@ -349,6 +349,35 @@ def test_conv2d_stride2_fprop_and_wgrad_vs_torch_cpu(B, H, W, Cin, Cout, k):
     assert e < 2e-5 and ew < 2e-5, (e, ew)
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(1, 16, 16, 64, 64, 3), (2, 17, 23, 128, 128, 3), (1, 31, 40, 256, 256, 3),
+                                               (2, 18, 21, 256, 256, 3), (2, 17, 23, 256, 512, 1), (1, 30, 41, 512, 1024, 1)])
+def test_conv2d_stride2_dgrad_parity_classes(B, H, W, Cin, Cout, k):
+    """dx of a stride-2 conv from 4 parity-class GEMMs (no zero insertion) vs torch autograd; 1x1: accumulate form."""
+    from tinyfaces_b200 import ops
+    d = _dev()
+    gen = torch.Generator().manual_seed(5 + B + H + Cin + k)
+    x = torch.zeros(B, Cin, H, W, dtype=torch.float64, requires_grad=True)
+    w = _tf32(torch.randn(Cout, Cin, k, k, generator=gen) / (Cout * k * k) ** 0.5)
+    y = torch.nn.functional.conv2d(x, w.double(), stride=2, padding=k // 2)
+    dy = _tf32(torch.randn(y.shape, generator=gen))
+    y.backward(dy.double())
+    ref = x.grad.float()                                                     # [B, Cin, H, W]
+    # dgrad packing: wp[ci][t][co] = w[co][ci][flipped tap t]
+    wp = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Cin, k * k, Cout).contiguous().to(d)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(d)
+    if k == 3:
+        dx = ops.conv2d_dgrad_s2_nhwc(dyn, wp, k, H, W, out=torch.full((B, H, W, Cin), 7.0, device=d))   # 7.0 must be overwritten
+        base = 0.0
+    else:
+        dx = ops.conv2d_dgrad_s2_nhwc(dyn, wp, k, H, W, out=torch.full((B, H, W, Cin), 0.25, device=d), accumulate=True)
+        base = 0.25
+    torch.cuda.synchronize()
+    assert ops.gemm_error_flag() == 0
+    got = dx.cpu().permute(0, 3, 1, 2) - base
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 3e-5, "rel err %g" % err
+
+
 def test_conv2d_3xtf32_parity_mode():
     """hi/lo split operands through the 3-segment K loop recover fp32-level accuracy on arbitrary fp32 data."""
     from tinyfaces_b200 import ops

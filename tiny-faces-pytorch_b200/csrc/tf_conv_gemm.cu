@@ -43,6 +43,9 @@ struct GemmParams {
     int spatial;                  // 0: A/D are 2-D [pixels, C]; 1: 4-D (C, W, H, B) with spatial tiles
     int tiles_x, tiles_y, tw, th; // spatial tiling of one image (tw * th == 128)
     int taps, kblocks, nseg;      // K loop = nseg x taps x kblocks blocks of 32 channels
+    // tap t reads A at (x0 + tap_ox[t], y0 + tap_oy[t]) (x stride) and B at K block (tap_w[t] * kblocks + kb): the full 3x3
+    // stencil by default; the parity classes of a stride-2 dgrad use 1, 2 or 4 taps with 0 / +1 offsets
+    signed char tap_ox[9], tap_oy[9]; unsigned char tap_w[9];
     int stride;                   // spatial mode: input coordinate = stride * output coordinate + tap offset (TMA elementStrides)
     // Tail-wave split-K: work units [0, main_tiles) are whole tiles; every later tile is cut into `ksplit` K slices
     // (one unit each) whose partial sums meet in D through TMA reduce-add (the host zeroes those rows first).  Without
@@ -56,7 +59,7 @@ struct GemmParams {
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
     int relu, round_out;
     int accumulate;               // 1: D += result (TMA reduce-add) instead of D = result
-    float* stats_partial;         // optional BN statistics: [grid/num_n_tiles*4][2][Cout] per-channel (sum, sum^2) partials
+    float* stats_partial;         // optional BN statistics: [grid/num_n_tiles][2][Cout] per-channel (sum, sum^2) partials, one row per CTA
     int cout;                     //   of the raw accumulators (needs gridDim.x % num_n_tiles == 0: fixed n-tile per CTA)
     int img_w, img_h;             // spatial mode: rows of a patch that fall outside the image are not statistics
     int* err_flag;
@@ -150,6 +153,33 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const GemmPara
     }
 }
 
+// End of a CTA's epilogue: the four warps' per-column (sum, sum^2) partials are combined through the (by now idle) staging
+// buffers into ONE row of the partial table per CTA -- the finalize kernel behind the GEMM then reads 4x fewer rows.
+template <int BN>
+__device__ __forceinline__ void write_stats_row(uint8_t* epi, int q, int lane, const float (&st_sum)[BN / 32],
+                                                const float (&st_sq)[BN / 32], float* __restrict__ dst /* row: [2][cout] at n0 */,
+                                                int cout) {
+    if (lane == 0) tma_store_wait_read<0>();             // this warp's stores have left its staging buffers
+    __syncwarp();
+    const uint32_t red = smem_u32(epi);                  // warp w keeps [2][BN] floats at the start of ITS 8 KB staging area
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + q * 8192 + (c * 32 + lane) * 4), "f"(st_sum[c]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(red + q * 8192 + (BN + c * 32 + lane) * 4), "f"(st_sq[c]) : "memory");
+    }
+    named_bar_sync_epi();                                // the 128 epilogue threads
+    for (int col = q * 32 + lane; col < BN; col += 128) {
+        float s = 0.f, t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            s += lds32(red + w * 8192 + col * 4);
+            t += lds32(red + w * 8192 + (BN + col) * 4);
+        }
+        dst[col] = s;
+        dst[cout + col] = t;
+    }
+}
+
 struct WorkUnit { int tile, k0, k1, split; };
 __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u, int kiters) {
     WorkUnit w;
@@ -239,10 +269,10 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     if (SPATIAL)
-                        tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
+                        tma_load_4d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, p.stride * x0 + p.tap_ox[tap], p.stride * y0 + p.tap_oy[tap], img);
                     else
                         tma_load_2d(sa, &maps.a[seg], &full[stage], kb * BLOCK_K, m0);
-                    tma_load_2d(sb, &maps.b[seg], &full[stage], (tap * p.kblocks + kb) * BLOCK_K, n0);
+                    tma_load_2d(sb, &maps.b[seg], &full[stage], (p.tap_w[tap] * p.kblocks + kb) * BLOCK_K, n0);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     if (++kb == p.kblocks) { kb = 0; if (++tap == p.taps) { tap = 0; ++seg; } }
                 }
@@ -346,12 +376,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         }
         if (p.stats_partial) {
             const int n0 = (blockIdx.x % p.num_n_tiles) * BN;
-            float* dst = p.stats_partial + (size_t)((blockIdx.x / p.num_n_tiles) * 4 + q) * 2 * p.cout;
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                dst[n0 + c * 32 + lane] = st_sum[c];
-                dst[p.cout + n0 + c * 32 + lane] = st_sq[c];
-            }
+            write_stats_row<BN>(epi, q, lane, st_sum, st_sq, p.stats_partial + (size_t)(blockIdx.x / p.num_n_tiles) * 2 * p.cout + n0, p.cout);
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -431,10 +456,10 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                             const uint32_t lead_full = map_to_cta(smem_u32(&full[stage]), 0);
                             if (rank == 0) mbar_expect_tx(&full[stage], 2 * G2_STAGE_BYTES);
                             if (p.spatial)
-                                tma2_load_4d(sa, &maps.a[seg], lead_full, kb * BLOCK_K, p.stride * x0 + tap_dx(p.taps, tap), p.stride * y0 + tap_dy(p.taps, tap), img);
+                                tma2_load_4d(sa, &maps.a[seg], lead_full, kb * BLOCK_K, p.stride * x0 + p.tap_ox[tap], p.stride * y0 + p.tap_oy[tap], img);
                             else
                                 tma2_load_2d(sa, &maps.a[seg], lead_full, kb * BLOCK_K, m0);
-                            tma2_load_2d(sb, &maps.b[seg], lead_full, (tap * p.kblocks + kb) * BLOCK_K, n0 + (int)rank * 128);
+                            tma2_load_2d(sb, &maps.b[seg], lead_full, (p.tap_w[tap] * p.kblocks + kb) * BLOCK_K, n0 + (int)rank * 128);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         }
             }
@@ -518,14 +543,10 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
             }
         }
         if (p.stats_partial) {
-            // every cluster keeps one n-tile (num_clusters % num_n_tiles == 0): row = ((cluster / n_tiles) * 2 + rank) * 4 + q
+            // every cluster keeps one n-tile (num_clusters % num_n_tiles == 0): row = (cluster / n_tiles) * 2 + rank
             const int n0 = (cluster_id % p.num_n_tiles) * BN;
-            float* dst = p.stats_partial + (size_t)(((cluster_id / p.num_n_tiles) * 2 + (int)rank) * 4 + q) * 2 * p.cout;
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                dst[n0 + c * 32 + lane] = st_sum[c];
-                dst[p.cout + n0 + c * 32 + lane] = st_sq[c];
-            }
+            write_stats_row<BN>(epi, q, lane, st_sum, st_sq,
+                                p.stats_partial + (size_t)((cluster_id / p.num_n_tiles) * 2 + (int)rank) * 2 * p.cout + n0, p.cout);
         }
         if (lane == 0) tma_store_wait_all<0>();
     }
@@ -731,6 +752,25 @@ int encode_4d(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t 
     return TF_OK;
 }
 
+// 4-D view (C, Wq, Hq, B) of every second pixel in x and y of an NHWC tensor [B,H,W,C], starting at pixel (py, px)
+int encode_4d_lattice2(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, int py, int px,
+                       uint32_t bc, uint32_t bw, uint32_t bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { tf_set_error("cuTensorMapEncodeTiled entry point unavailable"); return TF_ERR_CUDA; }
+    const uint64_t Wq = (W - px + 1) / 2, Hq = (H - py + 1) / 2;
+    cuuint64_t dims[4] = {C, Wq, Hq, B};
+    cuuint64_t strides[3] = {2 * C * 4, 2 * W * C * 4, H * W * C * 4};
+    cuuint32_t box[4] = {bc, bw, bh, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    const char* base = reinterpret_cast<const char*>(ptr) + ((size_t)py * W + px) * C * 4;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<char*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { tf_set_error("cuTensorMapEncodeTiled(4d lattice C=%llu W=%llu H=%llu B=%llu) failed: %d",
+                                          (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, (int)r); return TF_ERR_CUDA; }
+    return TF_OK;
+}
+
 // MN-major operand views for wgrad: channels split as (32, C/32) with the group axis outermost in the box
 int encode_3d_grouped(CUtensorMap* m, const void* ptr, uint64_t C, uint64_t rows, uint32_t box_rows, uint32_t groups) {
     EncodeTiledFn enc = get_encode();
@@ -785,6 +825,15 @@ int ensure_device_state() {
     return TF_OK;
 }
 
+void default_taps(GemmParams& p, int taps) {
+    p.taps = taps;
+    for (int t = 0; t < 9; ++t) {
+        p.tap_ox[t] = (signed char)(taps == 9 ? t % 3 - 1 : 0);
+        p.tap_oy[t] = (signed char)(taps == 9 ? t / 3 - 1 : 0);
+        p.tap_w[t] = (unsigned char)t;
+    }
+}
+
 template <int BN, bool FUSED, bool SPATIAL, bool RES>
 int launch_gemm_variant(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
     using Cfg = GemmCfg<BN>;
@@ -822,7 +871,7 @@ int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cud
     const int pair_tiles = ((p.num_m_tiles + 1) / 2) * p.num_n_tiles;
     int clusters = pair_tiles < g_num_sms / 2 ? pair_tiles : g_num_sms / 2;
     clusters = clusters / p.num_n_tiles * p.num_n_tiles;                 // every cluster keeps one n-tile
-    if (stats_rows) *stats_rows = clusters / p.num_n_tiles * 2 * 4;
+    if (stats_rows) *stats_rows = clusters / p.num_n_tiles * 2;
     if (p.scale || p.shift || p.relu || p.round_out) return launch_gemm2_variant<true>(maps, p, clusters, st);
     return launch_gemm2_variant<false>(maps, p, clusters, st);
 }
@@ -886,7 +935,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         if (cost < best) { best = cost; BN = cand; }
     }
     if (g_debug[2]) BN = g_debug[2];
-    p.taps = taps; p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
+    default_taps(p, taps); p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
     p.res = a.res; p.res_mask = a.res_mask; p.m_rows = Mtot;
@@ -940,7 +989,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     }
     const int tiles = p.num_m_tiles * p.num_n_tiles;
     const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / p.num_n_tiles * p.num_n_tiles;
-    stats_rows = grid / p.num_n_tiles * 4;
+    stats_rows = grid / p.num_n_tiles;
     // ---- tail-wave split-K plan: the m-tiles that do not fill a whole round over the CTAs are cut along K.
     //      Only for a plain epilogue (K slices cannot be scaled / clamped separately) and a K loop worth cutting.
     p.main_tiles = tiles; p.ksplit = 1;
@@ -977,6 +1026,77 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         stats_rows += nb;
     }
     if (a.stats_blocks) *a.stats_blocks = stats_rows;
+    return TF_OK;
+}
+
+// Input gradient of a stride-2 convolution (3x3 pad 1, or 1x1) WITHOUT zero insertion: the input pixels fall into 4
+// parity classes (py, px); each class is a small stride-1 correlation over dy -- 1, 2, 2 and 4 of the 9 flipped taps (1 tap,
+// class (0,0) only, for a 1x1) -- written through a tensor map of that class's quarter lattice of dx.  9/4 tap
+// evaluations per dy pixel instead of the 9 per dx pixel (= 36) of "zero-insert, then stride-1 dgrad".
+//   a.x = dy [B, ceil(H/2), ceil(W/2), Cin]  (Cin = the convolution's Cout), a.w = packed dgrad weights [Cout][taps][Cin]
+//   a.y = dx [B, H, W, Cout]; a.H, a.W = the dx size; a.accumulate adds into dx (1x1: untouched pixels keep their value)
+int conv_dgrad_s2(const ConvArgs& a, cudaStream_t st) {
+    TF_REQUIRE(a.x && a.w && a.y && !a.scale && !a.shift && !a.relu && !a.round_out && !a.stats_partial && !a.res,
+               "conv_dgrad_s2: plain epilogue only");
+    TF_REQUIRE((a.x_lo == nullptr) == (a.w_lo == nullptr), "conv_dgrad_s2: x_lo and w_lo must be given together");
+    TF_REQUIRE(a.B > 0 && a.H > 1 && a.W > 1 && a.Cin % 32 == 0 && a.Cout % 64 == 0 && (a.ksize == 1 || a.ksize == 3),
+               "conv_dgrad_s2: unsupported shape B=%d H=%d W=%d Cin=%d Cout=%d k=%d", a.B, a.H, a.W, a.Cin, a.Cout, a.ksize);
+    int rc = ensure_device_state();
+    if (rc) return rc;
+    const int B = a.B, H = a.H, W = a.W, Cin = a.Cin, Cout = a.Cout;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2, taps = a.ksize * a.ksize;
+    const float* as[3] = {a.x, a.x_lo, a.x};
+    const float* bs[3] = {a.w, a.w, a.w_lo};
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            if (a.ksize == 1 && (py || px)) continue;               // a 1x1/s2 only ever read the even pixels
+            const int Hq = (H - py + 1) / 2, Wq = (W - px + 1) / 2;
+            if (Hq <= 0 || Wq <= 0) continue;
+            GemmMaps maps;
+            GemmParams p = {};
+            p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1; p.stride = 1; p.spatial = 1;
+            p.accumulate = a.accumulate; p.cout = Cout; p.img_w = Wq; p.img_h = Hq; p.err_flag = g_err_flag;
+            // taps of this class in the stride-1 numbering t = (dy'+1)*3 + (dx'+1): dy' = 0 for even rows (dy offset 0),
+            // dy' = -1 (offset 0) and +1 (offset +1) for odd rows; likewise in x
+            int nt = 0;
+            if (a.ksize == 1) { p.tap_ox[0] = 0; p.tap_oy[0] = 0; p.tap_w[0] = 0; nt = 1; }
+            else {
+                const int ny = py ? 2 : 1, nx = px ? 2 : 1;
+                for (int iy = 0; iy < ny; ++iy)
+                    for (int ix = 0; ix < nx; ++ix) {
+                        const int dyp = py ? (iy ? 1 : -1) : 0, dxp = px ? (ix ? 1 : -1) : 0;
+                        p.tap_oy[nt] = (signed char)(dyp == 1 ? 1 : 0);
+                        p.tap_ox[nt] = (signed char)(dxp == 1 ? 1 : 0);
+                        p.tap_w[nt] = (unsigned char)((dyp + 1) * 3 + (dxp + 1));
+                        ++nt;
+                    }
+            }
+            p.taps = nt;
+            pick_tile(Wq, Hq, BLOCK_M, &p.tw, &p.th);
+            p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + p.th - 1) / p.th;
+            p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+            int BN = 64; double best = 1e30;
+            for (int cand = 256; cand >= 64; cand >>= 1) {
+                if (Cout % cand) continue;
+                const long long tiles = (long long)p.num_m_tiles * (Cout / cand);
+                const double cost = (double)((tiles + g_num_sms - 1) / g_num_sms) * cand * (cand == 256 ? 1.0 : (cand == 128 ? 1.45 : 2.2));
+                if (cost < best) { best = cost; BN = cand; }
+            }
+            p.num_n_tiles = Cout / BN;
+            for (int s = 0; s < p.nseg; ++s) {
+                if ((rc = encode_4d(&maps.a[s], as[s], Cin, Wo, Ho, B, 32, p.tw, p.th))) return rc;
+                if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, BN))) return rc;
+            }
+            const int bw = p.tw < 32 ? p.tw : 32, bh = 32 / bw;
+            if ((rc = encode_4d_lattice2(&maps.d, a.y, Cout, W, H, B, py, px, 32, bw, bh))) return rc;
+            const int tiles = p.num_m_tiles * p.num_n_tiles;
+            const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / p.num_n_tiles * p.num_n_tiles;
+            p.main_tiles = tiles; p.ksplit = 1;
+            if (BN == 256) rc = launch_gemm<256>(maps, p, grid, st);
+            else if (BN == 128) rc = launch_gemm<128>(maps, p, grid, st);
+            else rc = launch_gemm<64>(maps, p, grid, st);
+            if (rc) return rc;
+        }
     return TF_OK;
 }
 
@@ -1074,6 +1194,13 @@ TF_API int tf_conv2d_wgrad_nhwc_strided(const float* x, const float* dy, int B, 
     tfg::WgradArgs a = {};
     a.x = x; a.dy = dy; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.stride = stride; a.dw = dw_packed;
     return tfg::conv_wgrad(a, (cudaStream_t)stream);
+}
+
+TF_API int tf_conv2d_dgrad_s2_nhwc(const float* dy, int B, int H, int W, int Cdy, const float* w_packed, int Cdx, int ksize,
+                                   int accumulate, float* dx, void* stream) {
+    tfg::ConvArgs a = {};
+    a.x = dy; a.B = B; a.H = H; a.W = W; a.Cin = Cdy; a.w = w_packed; a.Cout = Cdx; a.ksize = ksize; a.accumulate = accumulate; a.y = dx;
+    return tfg::conv_dgrad_s2(a, (cudaStream_t)stream);
 }
 
 // Reads (and clears) the device-side pipeline error flag set by a timed-out mbarrier wait.

@@ -17,6 +17,8 @@ struct ConvArgs {
     int* stats_blocks;                     //   [*stats_blocks][2][Cout] (HOST out: number of partial rows written)
 };
 int conv_fprop(const ConvArgs& a, cudaStream_t st);
+// input gradient of a stride-2 conv as 4 parity-class GEMMs (no zero insertion): x = dy at ceil(H/2) x ceil(W/2), y = dx at H x W
+int conv_dgrad_s2(const ConvArgs& a, cudaStream_t st);
 
 struct WgradArgs {
     const float* x; const float* x_lo;

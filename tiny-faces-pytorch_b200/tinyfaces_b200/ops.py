@@ -162,6 +162,18 @@ def conv2d_wgrad_nhwc_strided(x, dy, ksize, stride):
     return dw
 
 
+def conv2d_dgrad_s2_nhwc(dy, w_packed, ksize, H, W, out=None, accumulate=False):
+    """Input gradient of a stride-2 conv: dy [B, ceil(H/2), ceil(W/2), Cdy], w_packed [Cdx, k*k (flipped), Cdy] -> dx [B,H,W,Cdx]."""
+    require_cuda(dy, "dy")
+    B, Ho, Wo, Cdy = dy.shape
+    Cdx = w_packed.shape[0]
+    assert dy.is_contiguous() and w_packed.is_contiguous() and Ho == (H + 1) // 2 and Wo == (W + 1) // 2
+    dx = out if out is not None else torch.zeros((B, H, W, Cdx), dtype=torch.float32, device=dy.device)
+    check(lib().tf_conv2d_dgrad_s2_nhwc(ptr(dy), B, H, W, Cdy, ptr(w_packed), Cdx, ksize, int(bool(accumulate)), ptr(dx),
+                                        stream_ptr(dy.device)), "tf_conv2d_dgrad_s2_nhwc")
+    return dx
+
+
 def gemm_error_flag():
     v = ctypes.c_int(0)
     check(lib().tf_gemm_error_flag(ctypes.byref(v)), "tf_gemm_error_flag")
