@@ -70,6 +70,7 @@ template <int BN> struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int FUSED_SMEM_BYTES = SMEM_BYTES + 1024;   // + the CTA's per-channel shift vector (= the 227 KB maximum for BN = 256)
     static constexpr int WGRAD_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;   // epilogue overlays stage 0
     static_assert(2 * EPI_BUF_BYTES <= STAGES * STAGE_BYTES, "wgrad epilogue buffers must fit in the operand ring");
     static constexpr int TMEM_COLS = 2 * BN;
@@ -104,16 +105,32 @@ __device__ __forceinline__ void store_row_swizzled(uint32_t buf_s, int row, cons
 template <bool FUSED, bool SPATIAL>
 __device__ __forceinline__ void epilogue_chunk(uint32_t (&r)[32], const GemmParams& p, const CUtensorMap* dmap, uint8_t* buf,
                                                int lane, int nb, bool reduce_out, bool do_stats, uint32_t rowmask,
-                                               int c1, int c2, int c3, float& ssum, float& ssq) {
+                                               int c1, int c2, int c3, float& ssum, float& ssq, uint32_t shift_s = 0) {
     if (FUSED) {
+        // shift_s: this chunk's 32 per-channel shifts, staged in shared memory at kernel start (every lane needs all 32:
+        // 8 broadcast LDS.128 instead of 32 global loads); the per-channel scale is normally folded into the packed weights
+        if (p.scale) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]);
-            if (p.scale) v *= __ldg(p.scale + nb + j);
-            if (p.shift) v += __ldg(p.shift + nb + j);
-            if (p.relu) v = fmaxf(v, 0.f);
-            if (p.round_out) v = tf_round_tf32(v);
-            r[j] = __float_as_uint(v);
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * __ldg(p.scale + nb + j));
+        }
+        if (shift_s) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 sv;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(sv.x), "=f"(sv.y), "=f"(sv.z), "=f"(sv.w) : "r"(shift_s + c * 16));
+                r[4 * c] = __float_as_uint(__uint_as_float(r[4 * c]) + sv.x);
+                r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + sv.y);
+                r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + sv.z);
+                r[4 * c + 3] = __float_as_uint(__uint_as_float(r[4 * c + 3]) + sv.w);
+            }
+        }
+        if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+        }
+        if (p.round_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(tf_round_tf32(__uint_as_float(r[j])));
         }
     }
     const uint32_t buf_s = smem_u32(buf);
@@ -226,8 +243,11 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* shift_smem = reinterpret_cast<float*>(epi + 2 * EPI_BUF_BYTES + 1024);    // FUSED only (FUSED_SMEM_BYTES)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (FUSED && p.shift)                               // every CTA keeps one n-tile: its BN shifts, once
+        for (int i = threadIdx.x; i < BN; i += GEMM_THREADS) shift_smem[i] = __ldg(p.shift + (blockIdx.x % p.num_n_tiles) * BN + i);
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&maps.a[s]); prefetch_tmap(&maps.b[s]); }
         prefetch_tmap(&maps.d);
@@ -370,7 +390,8 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 }
                 uint8_t* buf = wbuf + ebuf * 4096;
                 epilogue_chunk<FUSED, SPATIAL>(r, p, &maps.d, buf, lane, n0 + chunk * 32, reduce_out, do_stats, rowmask,
-                                               SPATIAL ? x0 + wx : m0 + q * 32, y0 + wy, img, st_sum[chunk], st_sq[chunk]);
+                                               SPATIAL ? x0 + wx : m0 + q * 32, y0 + wy, img, st_sum[chunk], st_sq[chunk],
+                                               (FUSED && p.shift) ? smem_u32(shift_smem) + chunk * 128 : 0u);
                 ebuf ^= 1;
             }
         }
@@ -398,6 +419,7 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_B_STAGE_BYTES = 128 * 128;                        // this CTA's half of the B tile
 constexpr int G2_STAGE_BYTES = A_STAGE_BYTES + G2_B_STAGE_BYTES;   // 32 KB
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 + 1024;
+constexpr int G2_FUSED_SMEM_BYTES = G2_SMEM_BYTES + 1024;
 
 template <bool FUSED>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -412,9 +434,12 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     uint64_t* tfull = empty + STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* shift_smem = reinterpret_cast<float*>(epi + 2 * EPI_BUF_BYTES + 1024);    // FUSED only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();                 // 0 = leader (issues the MMAs)
+    if (FUSED && p.shift)
+        for (int i = threadIdx.x; i < BN; i += GEMM_THREADS) shift_smem[i] = __ldg(p.shift + ((blockIdx.x >> 1) % p.num_n_tiles) * BN + i);
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&maps.a[s]); prefetch_tmap(&maps.b[s]); }
         prefetch_tmap(&maps.d);
@@ -535,10 +560,11 @@ conv_gemm2_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 else { tc_fence_before(); mbar_arrive_cluster(map_to_cta(smem_u32(&tempty[acc]), 0)); }
                 if (!real_tile) continue;
                 uint8_t* buf = wbuf + ebuf * 4096;
+                const uint32_t shs = (FUSED && p.shift) ? smem_u32(shift_smem) + chunk * 128 : 0u;
                 if (p.spatial) epilogue_chunk<FUSED, true>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
-                                                          x0 + wx, y0 + wy, img, st_sum[chunk], st_sq[chunk]);
+                                                          x0 + wx, y0 + wy, img, st_sum[chunk], st_sq[chunk], shs);
                 else           epilogue_chunk<FUSED, false>(r, p, &maps.d, buf, lane, n0 + chunk * 32, p.accumulate != 0, p.stats_partial != nullptr, rowmask,
-                                                           m0 + q * 32, 0, 0, st_sum[chunk], st_sq[chunk]);
+                                                           m0 + q * 32, 0, 0, st_sum[chunk], st_sq[chunk], shs);
                 ebuf ^= 1;
             }
         }
@@ -839,10 +865,11 @@ int launch_gemm_variant(const GemmMaps& maps, const GemmParams& p, int grid, cud
     using Cfg = GemmCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, FUSED, SPATIAL, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, FUSED, SPATIAL, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           FUSED ? Cfg::FUSED_SMEM_BYTES : Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    conv_gemm_kernel<BN, FUSED, SPATIAL, RES><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
+    conv_gemm_kernel<BN, FUSED, SPATIAL, RES><<<grid, GEMM_THREADS, FUSED ? Cfg::FUSED_SMEM_BYTES : Cfg::SMEM_BYTES, st>>>(maps, p);   // grid % num_n_tiles == 0: one n-tile per CTA (stats_partial)
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -860,10 +887,10 @@ template <bool FUSED>
 int launch_gemm2_variant(const GemmMaps& maps, const GemmParams& p, int clusters, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED ? G2_FUSED_SMEM_BYTES : G2_SMEM_BYTES));
         attr_set = true;
     }
-    conv_gemm2_kernel<FUSED><<<2 * clusters, GEMM_THREADS, G2_SMEM_BYTES, st>>>(maps, p);
+    conv_gemm2_kernel<FUSED><<<2 * clusters, GEMM_THREADS, FUSED ? G2_FUSED_SMEM_BYTES : G2_SMEM_BYTES, st>>>(maps, p);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

@@ -480,7 +480,7 @@ __global__ void pack_weights_batched_kernel(const tfe::PackJob* __restrict__ job
         const long long u = t - j.begin;
         const int i = (int)(u % j.I_pad), tp = (int)((u / j.I_pad) % j.taps), o = (int)(u / ((long long)j.I_pad * j.taps));
         float v = 0.f;
-        if (!j.transpose) { if (o < j.O_src && i < j.I_src) v = j.src[((long long)o * j.I_src + i) * j.taps + tp]; }
+        if (!j.transpose) { if (o < j.O_src && i < j.I_src) { v = j.src[((long long)o * j.I_src + i) * j.taps + tp]; if (j.oscale) v *= j.oscale[o]; } }
         else              { if (i < j.O_src && o < j.I_src) v = j.src[((long long)i * j.I_src + o) * j.taps + (j.taps - 1 - tp)]; }
         if (mode == 1) j.dst[u] = tf_round_tf32(v);
         else if (mode == 2) { const float h = hi_part(v); j.dst[u] = h; j.dst_lo[u] = v - h; }

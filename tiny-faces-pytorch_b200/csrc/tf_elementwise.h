@@ -34,6 +34,7 @@ int pack_weight(const float* w, int O_src, int I_src, int taps, int transpose, i
                 float* dst_lo, int mode, cudaStream_t st);
 struct PackJob {                              // one weight tensor of a batched packing launch
     const float* src; float* dst; float* dst_lo;
+    const float* oscale;                      // optional per-output-channel factor folded into the weights (eval-mode BN scale)
     int O_src, I_src, taps, transpose, O_pad, I_pad;
     long long begin;                          // first global element index of this job
 };

@@ -179,14 +179,21 @@ struct Model {
     std::map<std::pair<int, int>, std::pair<float*, float*>> packed;
     std::vector<tfe::PackJob> jobs;
     long long jobs_total = 0;
-    void prepack_add(const ConvP& c, int O_pad, int I_pad, int transpose) {
+    std::map<int, std::pair<float*, float*>> eval_ss;     // BN gamma index -> (scale, shift) of the eval-mode affine form
+    bool fold_scale = false;             // eval fast mode: the BN scale of a fused conv+BN(+ReLU) is folded into its packed weights
+    const float* eval_scale_of(const BnP& b) const {
+        if (!fold_scale) return nullptr;
+        auto it = eval_ss.find(b.gamma);
+        return it == eval_ss.end() ? nullptr : it->second.first;
+    }
+    void prepack_add(const ConvP& c, int O_pad, int I_pad, int transpose, const float* oscale = nullptr) {
         const int taps = c.k * c.k;
         const size_t n = (size_t)O_pad * taps * I_pad;
         float* wp = ar.f(n);
         float* wp_lo = mode == 2 ? ar.f(n) : nullptr;
         packed[{c.w, transpose}] = {wp, wp_lo};
         tfe::PackJob j;
-        j.src = ar.dry ? nullptr : P(c.w); j.dst = wp; j.dst_lo = wp_lo;
+        j.src = ar.dry ? nullptr : P(c.w); j.dst = wp; j.dst_lo = wp_lo; j.oscale = oscale;
         j.O_src = c.cout; j.I_src = c.cin; j.taps = taps; j.transpose = transpose; j.O_pad = O_pad; j.I_pad = I_pad;
         j.begin = jobs_total;
         jobs_total += (long long)n;
@@ -222,7 +229,7 @@ struct Model {
         RC(pack(c, c.cout, c.cin, 0, &u.wp, &u.wp_lo, st));
         tfg::ConvArgs a = {};
         a.B = B_; a.Cin = c.cin; a.Cout = c.cout; a.ksize = c.k; a.w = u.wp; a.w_lo = u.wp_lo;
-        if (fused) { a.scale = u.scale; a.shift = u.shift; a.relu = relu; a.round_out = 1; }
+        if (fused) { a.scale = fold_scale ? nullptr : u.scale; a.shift = u.shift; a.relu = relu; a.round_out = 1; }
         // stride 2 is a TMA traversal stride: the GEMM reads the full-resolution input directly
         u.x = x; u.x_lo = x_lo; u.H = H_; u.W = W_;
         a.x = u.x; a.x_lo = u.x_lo; a.H = u.H; a.W = u.W; a.stride = c.stride;
@@ -250,7 +257,6 @@ struct Model {
         return TF_OK;
     }
     // eval-mode scale/shift of every BN are computed by ONE launch at the start of the forward (prepare_eval_all)
-    std::map<int, std::pair<float*, float*>> eval_ss;
     int prepare_eval_all(cudaStream_t st) {
         eval_ss.clear();
         std::vector<tfe::BnEvalJob> ej;
@@ -364,19 +370,22 @@ struct Model {
             // fprop weight AND the transposed / tap-flipped dgrad weights of the backward are packed on the side stream
             // while the stem (im2col, GEMM, BN, max-pool: ~1.4 ms of HBM-bound work) runs -- off the critical path.
             packed.clear(); jobs.clear(); jobs_total = 0;
+            fold_scale = !training && mode == 1;
+            if (!training) RC(prepare_eval_all(st)); else eval_ss.clear();     // (scale, shift) of every BN: the packing below folds the scales
             if (!ar.dry && training) RC(ensure_side());
             const bool aside = training && (ar.dry || side);
             cudaStream_t ps = (aside && !ar.dry) ? side : st;
             ConvP c = stem; c.cin = 147; c.k = 1;
-            prepack_add(c, 64, 160, 0);
+            prepack_add(c, 64, 160, 0, eval_scale_of(stem_bn));
             if (aside) {
                 RC(prepack_flush(st));
                 if (!ar.dry) { TF_CHECK_CUDA(cudaEventRecord(ev_fork, st)); TF_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0)); }
             }
             for (const BlockP& bp : blocks) {
-                prepack_add(bp.c1, bp.c1.cout, bp.c1.cin, 0); prepack_add(bp.c2, bp.c2.cout, bp.c2.cin, 0);
-                prepack_add(bp.c3, bp.c3.cout, bp.c3.cin, 0);
-                if (bp.has_ds) prepack_add(bp.cd, bp.cd.cout, bp.cd.cin, 0);
+                prepack_add(bp.c1, bp.c1.cout, bp.c1.cin, 0, eval_scale_of(bp.b1));
+                prepack_add(bp.c2, bp.c2.cout, bp.c2.cin, 0, eval_scale_of(bp.b2));
+                prepack_add(bp.c3, bp.c3.cout, bp.c3.cin, 0);                      // conv3's BN is applied with the residual, not fused
+                if (bp.has_ds) prepack_add(bp.cd, bp.cd.cout, bp.cd.cin, 0, eval_scale_of(bp.bd));
             }
             ConvP h3; h3.w = s3_w; h3.cin = 512; h3.cout = Cn; h3.k = 1;
             ConvP h4; h4.w = s4_w; h4.cin = 1024; h4.cout = Cn; h4.k = 1;
@@ -388,7 +397,6 @@ struct Model {
             }
             pack_pending = aside && !ar.dry;
         }
-        if (!training) RC(prepare_eval_all(st)); else eval_ss.clear();
         // ---- stem: im2col + GEMM (K = 147 padded to 160), BN, ReLU, max-pool
         const long long M2 = (long long)B * H2 * W2;
         col = ar.f((size_t)M2 * 160);
@@ -407,7 +415,7 @@ struct Model {
         float* a0; float* a0_lo = nullptr;
         if (!training && mode == 1) {
             RC(bn_prepare_eval(u, st));
-            a.scale = u.scale; a.shift = u.shift; a.relu = 1; a.round_out = 0;
+            a.scale = fold_scale ? nullptr : u.scale; a.shift = u.shift; a.relu = 1; a.round_out = 0;
             a0 = ar.f((size_t)M2 * 64);
             a.y = a0; u.y = a0;
             if (!ar.dry) RC(tfg::conv_fprop(a, st));
