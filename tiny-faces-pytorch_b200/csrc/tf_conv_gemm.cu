@@ -36,6 +36,7 @@ struct GemmMaps {
     CUtensorMap a[MAX_SEG];
     CUtensorMap b[MAX_SEG];
     CUtensorMap d;
+    CUtensorMap res;              // RES kernels: the residual tensor, same geometry as d (32 x 32 boxes, SWIZZLE_128B)
 };
 
 struct GemmParams {
@@ -51,9 +52,10 @@ struct GemmParams {
     // (one unit each) whose partial sums meet in D through TMA reduce-add (the host zeroes those rows first).  Without
     // it 300 tiles on 148 SMs cost 3 rounds for 2.03 rounds of work.
     int main_tiles, ksplit;
-    // Residual epilogue (RES kernels, flat pixel rows only): D[row, n] = acc + (bit n of res_mask row ? res[row, n] : 0) --
-    // the masked upstream gradient of an identity shortcut joins the 1x1 dgrad here instead of being written out by the
-    // BN-backward pass and read-modify-written by a TMA reduce-add.
+    // Residual epilogue (RES kernels, flat pixel rows only): D[row, n] = f(acc + res[row, n]) -- res_mask (optional, 1 bit
+    // per element) gates the residual.  Each epilogue warp TMA-loads the 32 x 32 residual box of the chunk two chunks
+    // ahead into a private swizzled buffer (these kernels give one or two operand stages to those buffers).  Used by the
+    // inference path (conv3 + folded BN + shortcut + ReLU in one kernel, no separate BN-apply pass).
     const float* res; const unsigned int* res_mask; long long m_rows;
     const float* scale;           // optional per-output-channel epilogue: v = v * scale[n] + shift[n]
     const float* shift;           //   (shift alone = bias), then optional ReLU and TF32 rounding
@@ -70,6 +72,7 @@ template <int BN> struct GemmCfg {
     static constexpr int B_STAGE_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
+    static constexpr int RES_DROP = (32768 + STAGE_BYTES - 1) / STAGE_BYTES;   // operand stages given to the residual buffers (4 warps x 2 x 4 KB)
     static constexpr int FUSED_SMEM_BYTES = SMEM_BYTES + 1024;   // + the CTA's per-channel shift vector (= the 227 KB maximum for BN = 256)
     static constexpr int WGRAD_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;   // epilogue overlays stage 0
     static_assert(2 * EPI_BUF_BYTES <= STAGES * STAGE_BYTES, "wgrad epilogue buffers must fit in the operand ring");
@@ -211,38 +214,21 @@ __device__ __forceinline__ WorkUnit decode_unit(const GemmParams& p, int u, int 
     return w;
 }
 
-__device__ __forceinline__ uint4 ldg_nc_v4(const float* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-    return v;
-}
-// residual chunk of one row: 32 floats + their mask word (row stride = cout floats, masks are 1 bit per element)
-__device__ __forceinline__ void res_load(const GemmParams& p, bool valid, long long row, int nb, uint4 (&rs)[8], uint32_t& mw) {
-    if (valid) {
-        const float* src = p.res + row * p.cout + nb;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) rs[c] = ldg_nc_v4(src + 4 * c);
-        mw = __ldg(p.res_mask + ((row * p.cout + nb) >> 5));
-    } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) rs[c] = make_uint4(0, 0, 0, 0);
-        mw = 0;
-    }
-}
-
 template <int BN, bool FUSED, bool SPATIAL, bool RES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+    constexpr int STAGES = RES ? Cfg::STAGES - Cfg::RES_DROP : Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi = smem + STAGES * Cfg::STAGE_BYTES;
+    uint8_t* epi = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint8_t* resbuf = smem + STAGES * Cfg::STAGE_BYTES;             // RES: 4 warps x 2 x 4 KB in the dropped stage(s)
     uint64_t* full = reinterpret_cast<uint64_t*>(epi + 2 * EPI_BUF_BYTES);
-    uint64_t* empty = full + STAGES;
-    uint64_t* tfull = empty + STAGES;
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tfull = empty + Cfg::STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rbar = tempty + 4;                                    // RES: [4 warps][2 buffers]
     float* shift_smem = reinterpret_cast<float*>(epi + 2 * EPI_BUF_BYTES + 1024);    // FUSED only (FUSED_SMEM_BYTES)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,6 +239,7 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         prefetch_tmap(&maps.d);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+        if (RES) { prefetch_tmap(&maps.res); for (int i = 0; i < 8; ++i) mbar_init(&rbar[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -341,6 +328,15 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
         float st_sum[BN / 32], st_sq[BN / 32];
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+        uint32_t rphase[2] = {0, 0};
+        if (RES && lane == 0 && (int)blockIdx.x < total_units) {    // residual boxes of the first unit's chunks 0 and 1
+            const WorkUnit fw = decode_unit(p, blockIdx.x, kiters);
+            const int fn0 = (fw.tile % p.num_n_tiles) * BN, fm0 = (fw.tile / p.num_n_tiles) * BLOCK_M;
+            for (int c = 0; c < 2 && c < BN / 32; ++c) {
+                mbar_expect_tx(&rbar[q * 2 + c], 4096);
+                tma_load_2d(resbuf + (q * 2 + c) * 4096, &maps.res, &rbar[q * 2 + c], fn0 + c * 32, fm0 + q * 32);
+            }
+        }
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
             const WorkUnit wu = decode_unit(p, unit, kiters);
             const int acc = it & 1;
@@ -361,10 +357,15 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 const int rw = q * 32 + lane;
                 rowmask = __ballot_sync(0xffffffffu, x0 + rw % p.tw < p.img_w && y0 + rw / p.tw < p.img_h);
             }
-            uint4 rs[2][8]; uint32_t mw[2];                         // RES: residual chunk prefetched one chunk ahead
+            // RES: the residual boxes of chunks 0 and 1 of this unit were requested at the end of the previous unit (or
+            // before the loop); chunk c's buffer is refilled with chunk c+2 (next unit's 0 / 1 at the end) right after use
             const long long res_row = (long long)m0 + q * 32 + lane;
             const bool res_valid = RES && res_row < p.m_rows;
-            if (RES) res_load(p, res_valid, res_row, n0, rs[0], mw[0]);   // in flight while the accumulators finish
+            int nn0 = 0, nm0 = 0; bool has_next = false;            // first chunk coordinates of this CTA's next unit
+            if (RES && unit + (int)gridDim.x < total_units) {
+                const WorkUnit nw = decode_unit(p, unit + gridDim.x, kiters);
+                nn0 = (nw.tile % p.num_n_tiles) * BN; nm0 = (nw.tile / p.num_n_tiles) * BLOCK_M; has_next = true;
+            }
             mbar_wait(&tfull[acc], acc_phase, p.err_flag, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
@@ -377,11 +378,32 @@ conv_gemm_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
                 if (chunk + 1 < BN / 32) tmem_ld_32x32(taddr + (chunk + 1) * 32, rr[(chunk + 1) & 1]);
                 else { tc_fence_before(); mbar_arrive(&tempty[acc]); }        // accumulator stage fully read
                 if (RES) {
-                    if (chunk + 1 < BN / 32) res_load(p, res_valid, res_row, n0 + (chunk + 1) * 32, rs[(chunk + 1) & 1], mw[(chunk + 1) & 1]);
-                    const uint32_t m = mw[chunk & 1];
+                    constexpr int NCH = BN / 32;
+                    const int slot = chunk & 1;
+                    uint32_t m = 0xffffffffu;
+                    if (p.res_mask) m = res_valid ? __ldg(p.res_mask + ((res_row * p.cout + n0 + chunk * 32) >> 5)) : 0u;
+                    mbar_wait(&rbar[q * 2 + slot], rphase[slot], p.err_flag, 5);
+                    rphase[slot] ^= 1;
+                    const uint32_t rb = smem_u32(resbuf + (q * 2 + slot) * 4096) + lane * 128;
+                    uint4 rs[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(rs[c].x), "=r"(rs[c].y), "=r"(rs[c].z), "=r"(rs[c].w)
+                                     : "r"(rb + ((c ^ (lane & 7)) << 4)) : "memory");
+                    fence_proxy_async();                                     // generic reads before the async-proxy refill
+                    __syncwarp();                                            // every lane has read the buffer: refill it
+                    if (lane == 0) {
+                        if (chunk + 2 < NCH) {
+                            mbar_expect_tx(&rbar[q * 2 + slot], 4096);
+                            tma_load_2d(resbuf + (q * 2 + slot) * 4096, &maps.res, &rbar[q * 2 + slot], n0 + (chunk + 2) * 32, m0 + q * 32);
+                        } else if (has_next && chunk + 2 - NCH < NCH) {
+                            mbar_expect_tx(&rbar[q * 2 + slot], 4096);
+                            tma_load_2d(resbuf + (q * 2 + slot) * 4096, &maps.res, &rbar[q * 2 + slot], nn0 + (chunk + 2 - NCH) * 32, nm0 + q * 32);
+                        }
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const uint4 v = rs[chunk & 1][c];
+                        const uint4 v = rs[c];
                         if (m & (1u << (4 * c)))     r[4 * c]     = __float_as_uint(__uint_as_float(r[4 * c])     + __uint_as_float(v.x));
                         if (m & (2u << (4 * c)))     r[4 * c + 1] = __float_as_uint(__uint_as_float(r[4 * c + 1]) + __uint_as_float(v.y));
                         if (m & (4u << (4 * c)))     r[4 * c + 2] = __float_as_uint(__uint_as_float(r[4 * c + 2]) + __uint_as_float(v.z));
@@ -879,7 +901,7 @@ int launch_gemm_variant(const GemmMaps& maps, const GemmParams& p, int grid, cud
 template <int BN>
 int launch_gemm(const GemmMaps& maps, const GemmParams& p, int grid, cudaStream_t st) {
     const bool fused = p.scale || p.shift || p.relu || p.round_out;
-    if (p.res) return launch_gemm_variant<BN, false, false, true>(maps, p, grid, st);
+    if (p.res) return fused ? launch_gemm_variant<BN, true, false, true>(maps, p, grid, st) : launch_gemm_variant<BN, false, false, true>(maps, p, grid, st);
     if (p.spatial) return fused ? launch_gemm_variant<BN, true, true, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, true, false>(maps, p, grid, st);
     return fused ? launch_gemm_variant<BN, true, false, false>(maps, p, grid, st) : launch_gemm_variant<BN, false, false, false>(maps, p, grid, st);
 }
@@ -966,8 +988,8 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
     p.res = a.res; p.res_mask = a.res_mask; p.m_rows = Mtot;
-    TF_REQUIRE(!a.res || (a.res_mask && !spatial && !a.scale && !a.shift && !a.relu && !a.round_out && !p.accumulate && !a.stats_partial),
-               "conv_fprop: the residual epilogue needs a plain, flat (1x1 stride-1), non-accumulating GEMM");
+    TF_REQUIRE(!a.res || (!spatial && !p.accumulate && !a.stats_partial && !a.x_lo),
+               "conv_fprop: the residual epilogue needs a flat (1x1 stride-1), non-accumulating, single-pass GEMM without statistics");
     p.stats_partial = a.stats_partial; p.cout = Cout; p.img_w = Wo; p.img_h = Ho;
     if (g_debug[7] && !p.stats_partial) {          // probe: time the BN-statistics epilogue without the model around it
         static float* scratch = nullptr;
@@ -987,6 +1009,7 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
         for (int s = 0; s < p.nseg; ++s)
             if ((rc = encode_2d(&maps.a[s], as[s], Cin, M, Cin, 32, BLOCK_M))) return rc;
         if ((rc = encode_2d(&maps.d, a.y, Cout, M, Cout, 32, 32))) return rc;          // one store box per epilogue warp
+        if (a.res && (rc = encode_2d(&maps.res, a.res, Cout, M, Cout, 32, 32))) return rc;
     } else {
         p.spatial = 1;
         pick_tile(Wo, Ho, BLOCK_M, &p.tw, &p.th);

@@ -221,7 +221,7 @@ struct Model {
     }
     // conv (+ stride handling) producing the raw output u.y at (Ho, Wo); fused != 0: eval epilogue scale/shift(/relu)
     int run_conv(Unit& u, const float* x, const float* x_lo, int B_, int H_, int W_, int fused, int relu, float* fused_out,
-                 cudaStream_t st, int* stats_blocks = nullptr) {
+                 cudaStream_t st, int* stats_blocks = nullptr, const float* res = nullptr) {
         const ConvP& c = u.c;
         u.B = B_;
         const int Ho = c.stride == 2 ? (H_ + 1) / 2 : H_, Wo = c.stride == 2 ? (W_ + 1) / 2 : W_;
@@ -229,7 +229,7 @@ struct Model {
         RC(pack(c, c.cout, c.cin, 0, &u.wp, &u.wp_lo, st));
         tfg::ConvArgs a = {};
         a.B = B_; a.Cin = c.cin; a.Cout = c.cout; a.ksize = c.k; a.w = u.wp; a.w_lo = u.wp_lo;
-        if (fused) { a.scale = fold_scale ? nullptr : u.scale; a.shift = u.shift; a.relu = relu; a.round_out = 1; }
+        if (fused) { a.scale = fold_scale ? nullptr : u.scale; a.shift = u.shift; a.relu = relu; a.round_out = 1; a.res = res; }
         // stride 2 is a TMA traversal stride: the GEMM reads the full-resolution input directly
         u.x = x; u.x_lo = x_lo; u.H = H_; u.W = W_;
         a.x = u.x; a.x_lo = u.x_lo; a.H = u.H; a.W = u.W; a.stride = c.stride;
@@ -317,6 +317,20 @@ struct Model {
         s.Ho = Ho; s.Wo = Wo;
         const long long Mo = (long long)B_ * Ho * Wo;
         const int C4 = bp.c3.cout;
+        if (!training && mode == 1 && !tfg::debug_flag(12)) {
+            // inference fast path: conv3 + folded BN + shortcut + ReLU in ONE kernel (residual epilogue), no BN-apply pass
+            const float* res = x;
+            if (bp.has_ds) {
+                RC(bn_prepare_eval(s.ud, st));
+                RC(run_conv(s.ud, x, x_lo, B_, H_, W_, 1, 0, nullptr, st));            // BN folded into the epilogue
+                res = s.ud.y;
+            }
+            RC(bn_prepare_eval(s.u3, st));
+            s.out = out_pre ? out_pre : ar.f((size_t)Mo * C4);
+            s.out_lo = nullptr; s.omask = nullptr;
+            RC(run_conv(s.u3, s.u2.a, s.u2.a_lo, B_, Ho, Wo, 1, 1, s.out, st, nullptr, res));
+            return TF_OK;
+        }
         if (!training) RC(bn_prepare_eval(s.u3, st));
         RC(conv_with_stats(s.u3, s.u2.a, s.u2.a_lo, B_, Ho, Wo, st));
         const float* res = x; const float* rscale = nullptr; const float* rshift = nullptr;
@@ -384,7 +398,7 @@ struct Model {
             for (const BlockP& bp : blocks) {
                 prepack_add(bp.c1, bp.c1.cout, bp.c1.cin, 0, eval_scale_of(bp.b1));
                 prepack_add(bp.c2, bp.c2.cout, bp.c2.cin, 0, eval_scale_of(bp.b2));
-                prepack_add(bp.c3, bp.c3.cout, bp.c3.cin, 0);                      // conv3's BN is applied with the residual, not fused
+                prepack_add(bp.c3, bp.c3.cout, bp.c3.cin, 0, tfg::debug_flag(12) ? nullptr : eval_scale_of(bp.b3));   // (flag 12: conv3's BN in a separate pass)
                 if (bp.has_ds) prepack_add(bp.cd, bp.cd.cout, bp.cd.cin, 0, eval_scale_of(bp.bd));
             }
             ConvP h3; h3.w = s3_w; h3.cin = 512; h3.cout = Cn; h3.k = 1;
