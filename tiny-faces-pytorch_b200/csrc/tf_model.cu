@@ -591,11 +591,10 @@ struct Model {
         const int C4 = s.u3.c.cout;
         float *dy3, *dy3_lo;
         const bool has_ds = s.has_ds;
-        // G = dout * [out > 0]: with an identity shortcut dx simply starts as G (written by the BN-backward pass) and the
-        // conv1 dgrad reduce-adds onto it; otherwise G feeds the downsample BN.  tf_debug_set(8, 1) switches to the
-        // residual epilogue instead (the dgrad adds the masked dout itself, G is never materialised): correct, but measured
-        // 4x slower on B200 -- per-lane row loads in the epilogue (250 us vs 65 us for the layer-3 GEMM) -- so it is off.
-        const bool fuse_g = !has_ds && s.u1.c.k == 1 && s.u1.c.stride == 1 && tfg::debug_flag(8) == 1;
+        // G = dout * [out > 0]: it feeds the downsample BN when there is one; with an identity shortcut it is never
+        // materialised -- the conv1 dgrad's residual epilogue adds the masked dout itself (TMA-loaded boxes; -0.5 ms/step
+        // against "dx starts as G, written by the BN-backward pass, and the dgrad reduce-adds onto it" = tf_debug_set(8, 2))
+        const bool fuse_g = !has_ds && s.u1.c.k == 1 && s.u1.c.stride == 1 && mode == 1 && tfg::debug_flag(8) != 2;
         float* g = has_ds ? ar.f((size_t)Mo * C4) : (fuse_g ? nullptr : dx);
         RC(unit_bn_bwd(s.u3, dout, s.omask, g, &dy3, &dy3_lo, grads, st));
         const long long M2o = (long long)s.B * s.u2.Ho * s.u2.Wo;

@@ -60,9 +60,11 @@ def nms(boxes, scores, iou_threshold):
     return keep[: int(count.item())].to(src)
 
 
-def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True):
+def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True, sync=True):
     """Device-side replacement of evaluation.py:61-71 for one pyramid level.
-    output: [B,5T,H,W] CUDA tensor.  Returns (boxes f64 [N,4], scores f64 [N]) on the device."""
+    output: [B,5T,H,W] CUDA tensor.  Returns (boxes f64 [N,4], scores f64 [N]) on the device; with sync=False the
+    capacity-sized buffers and the device-side count are returned instead (boxes, scores, count) so that the caller can
+    read all counts with ONE host synchronisation after every level has been enqueued."""
     B, C, H, W = output.shape
     T = templates.shape[0]
     if bug_compat and W < 25:
@@ -73,6 +75,8 @@ def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True):
     out = output.contiguous()
     boxes, scores, _, count = ops.decode_device(out, out[:, T:], None, strides, strides, B, H, W, T, templates,
                                                 prob_thresh, inv if bug_compat else 0, 0 if bug_compat else inv, rf, scale)
+    if not sync:
+        return boxes, scores, count
     n = int(count.item())
     return boxes[:n], scores[:n]
 
@@ -85,14 +89,16 @@ def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, 
     model.eval()
     templates = np.asarray(templates, dtype=np.float64)
     pyr = _Pyramid(img, img_transforms, device, gpu_pyramid)
-    all_boxes, all_scores = [], []
+    levels = []
     for scale in [2 ** x for x in scales]:                          # evaluation.py:37,44
         x = pyr.level(scale)
         with torch.no_grad():
             output = model(x)
-        b, s = decode_level(output, templates, prob_thresh, rf, scale)
-        all_boxes.append(b)
-        all_scores.append(s)
+        levels.append(decode_level(output, templates, prob_thresh, rf, scale, sync=False))
+    # one host synchronisation for all levels: the host has enqueued every level before it waits for any candidate count
+    counts = torch.cat([c for _b, _s, c in levels]).cpu().tolist() if levels else []
+    all_boxes = [b[:n] for (b, _s, _c), n in zip(levels, counts)]
+    all_scores = [s[:n] for (_b, s, _c), n in zip(levels, counts)]
     boxes = torch.cat(all_boxes) if all_boxes else torch.zeros((0, 4), dtype=torch.float64, device=device)
     scores = torch.cat(all_scores) if all_scores else torch.zeros(0, dtype=torch.float64, device=device)
     keep, count = ops.nms_device(boxes, scores, nms_thresh)         # evaluation.py:84

@@ -30,6 +30,7 @@ class _Executor:
         self.names = [lib().tf_model_param_name(h, i).decode() for i in range(n)]
         self.workspace = None
         self._sizes = {}
+        self._out_shapes = {}
 
     def __del__(self):
         try:
@@ -51,32 +52,46 @@ class _Executor:
         return self.workspace
 
 
+def _run_forward(module, x):
+    """tf_model_forward on the module's current parameters (no autograd bookkeeping)."""
+    ex = module._executor
+    _lib.require_cuda(x, "x")
+    if x.dtype != torch.float32:
+        raise RuntimeError("DetectionModel expects float32 input")
+    x = x.contiguous()
+    B, _, H, W = x.shape
+    mode = PRECISION[module.precision]
+    training = bool(module.training)
+    ws = ex.ensure_workspace(x.device, B, H, W, training, mode)
+    table = module._tables()[0]
+    cached = module.__dict__.get("_ptr_table")
+    if cached is None or cached[0] is not table or cached[1] != x.device:
+        for t in table:
+            if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("DetectionModel parameters must be contiguous float32 tensors on the input's device")
+        # the ctypes pointer table of the ~570 parameters / buffers costs ~0.3 ms to build: once per parameter set
+        # (optimizers update parameters in place, so the addresses are stable; _apply() drops the cache)
+        ptrs = (ctypes.c_void_p * len(table))(*[t.data_ptr() for t in table])
+        cached = module.__dict__["_ptr_table"] = (table, x.device, ptrs)
+    ptrs = cached[2]
+    key = (H, W)
+    shp = ex._out_shapes.get(key)
+    if shp is None:
+        h3, w3 = ctypes.c_int(), ctypes.c_int()
+        check(lib().tf_model_output_shape(ex.handle, H, W, ctypes.byref(h3), ctypes.byref(w3)), "tf_model_output_shape")
+        shp = ex._out_shapes[key] = (h3.value, w3.value)
+    out = torch.empty((B, 5 * module.num_templates, shp[0], shp[1]), dtype=torch.float32, device=x.device)
+    check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, float(module.bn_momentum), out.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
+    if training:
+        torch._foreach_add_(module._bn_counters(), 1)        # num_batches_tracked of all 94 BN layers, one launch
+    return out
+
+
 class _TrunkFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, module, *tensors):
-        ex = module._executor
-        _lib.require_cuda(x, "x")
-        if x.dtype != torch.float32:
-            raise RuntimeError("DetectionModel expects float32 input")
-        x = x.contiguous()
-        B, _, H, W = x.shape
-        mode = PRECISION[module.precision]
-        training = bool(module.training)
-        ws = ex.ensure_workspace(x.device, B, H, W, training, mode)
-        table = module._tables()[0]
-        if module.__dict__.get("_checked_for") != (x.device, id(table)):
-            for t in table:
-                if t.device != x.device or t.dtype != torch.float32 or not t.is_contiguous():
-                    raise RuntimeError("DetectionModel parameters must be contiguous float32 tensors on the input's device")
-            module.__dict__["_checked_for"] = (x.device, id(table))
-        ptrs = (ctypes.c_void_p * len(table))(*[t.data_ptr() for t in table])
-        h3, w3 = ctypes.c_int(), ctypes.c_int()
-        check(lib().tf_model_output_shape(ex.handle, H, W, ctypes.byref(h3), ctypes.byref(w3)), "tf_model_output_shape")
-        out = torch.empty((B, 5 * module.num_templates, h3.value, w3.value), dtype=torch.float32, device=x.device)
-        check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, float(module.bn_momentum), out.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
-        if training:
-            torch._foreach_add_(module._bn_counters(), 1)        # num_batches_tracked of all 94 BN layers, one launch
+        out = _run_forward(module, x)
         ctx.module = module
         return out
 
@@ -153,6 +168,7 @@ class DetectionModel(nn.Module):
         # .to() / .cuda() / .float() may replace parameter storage: drop the cached tensor tables
         self.__dict__.pop("_cache", None)
         self.__dict__.pop("_bn_cnt", None)
+        self.__dict__.pop("_ptr_table", None)
         return super()._apply(fn, *args, **kwargs)
 
     def _bn_counters(self):
@@ -195,7 +211,10 @@ class DetectionModel(nn.Module):
         return t
 
     def forward(self, x):
-        out = _TrunkFunction.apply(x, self, *self._tables()[1])
+        if torch.is_grad_enabled():
+            out = _TrunkFunction.apply(x, self, *self._tables()[1])
+        else:
+            out = _run_forward(self, x)      # torch.no_grad(): skip autograd.Function.apply over ~300 parameter tensors
         if not self._checked_upsample:
             v = ctypes.c_float()
             check(lib().tf_model_upsample_offdiag(self._executor.handle, ctypes.byref(v), stream_ptr(x.device)),
