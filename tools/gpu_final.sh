@@ -16,7 +16,4 @@ tail -2 gpurun_out/ncu_launches_$TAG.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel --launch-skip 40 --launch-count 3 \
     -f -o gpurun_out/prof_gemm_$TAG python bench.py --profile-mode --steps 1 --warmup 0 > gpurun_out/ncu_gemm_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_gemm_$TAG.log
-timeout 600 ncu --set full --clock-control none -k regex:conv_wgrad_kernel --launch-skip 10 --launch-count 3 \
-    -f -o gpurun_out/prof_wgrad_$TAG python bench.py --profile-mode --steps 1 --warmup 0 > gpurun_out/ncu_wgrad_$TAG.log 2>&1
-tail -2 gpurun_out/ncu_wgrad_$TAG.log
 ls -la gpurun_out/*.ncu-rep
