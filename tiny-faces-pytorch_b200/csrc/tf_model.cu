@@ -9,8 +9,8 @@
 //
 // Precision modes: 1 = "fast": GEMM operands rounded to TF32 by their producers, one tensor-core product;
 //                  2 = "parity": operands kept as exact (hi, lo) TF32 splits, three products (3xTF32).
-// Stride-2 convolutions: 1x1/s2 = subsample then GEMM; 3x3/s2 = stride-1 conv then subsample (forward) and
-// zero-insert then stride-1 dgrad/wgrad (backward).
+// Stride-2 convolutions: fprop / wgrad read the full-resolution input through a TMA traversal stride; the dgrad runs as
+// 4 parity-class GEMMs over dY (tfg::conv_dgrad_s2), no zero insertion.
 #include "tf_common.cuh"
 #include "tf_conv_gemm.h"
 #include "tf_elementwise.h"
