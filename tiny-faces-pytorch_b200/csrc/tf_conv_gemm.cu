@@ -939,12 +939,14 @@ int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
 }
 
 int g_debug[16] = {0};
+int g_debug_epoch = 0;              // bumped by every tf_debug_set: cached workspace plans made under other switches are stale
 
 }  // namespace
 
 TF_API int tf_debug_set(int key, int value) {
     TF_REQUIRE(key >= 0 && key < 16, "tf_debug_set: bad key");
     g_debug[key] = value;
+    ++g_debug_epoch;
     return TF_OK;
 }
 
@@ -953,6 +955,7 @@ TF_API int tf_debug_set(int key, int value) {
 namespace tfg {
 
 int debug_flag(int key) { return (key >= 0 && key < 16) ? g_debug[key] : 0; }
+int debug_epoch() { return g_debug_epoch; }
 
 int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     TF_REQUIRE(a.x && a.w && a.y, "conv_fprop: null pointer");

@@ -28,5 +28,6 @@ struct WgradArgs {
     float* dw;                             // packed [Cout][k*k][Cin], accumulated into
 };
 int conv_wgrad(const WgradArgs& a, cudaStream_t st);
-int debug_flag(int key);                  // tf_debug_set(key, value) experiment switches (0 = default behaviour)
+int debug_flag(int key);
+int debug_epoch();                         // changes whenever a switch is set (invalidates cached plans)                  // tf_debug_set(key, value) experiment switches (0 = default behaviour)
 }  // namespace tfg

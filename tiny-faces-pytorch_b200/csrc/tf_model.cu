@@ -86,7 +86,7 @@ struct Model {
     struct PendingWgrad { tfg::WgradArgs w; size_t dw_elems; int O, I, taps, I_pad; float* gw; };
     std::vector<PendingWgrad> pending;
     size_t bwd_region_bytes = 0;
-    int plan_B = 0, plan_H = 0, plan_W = 0, plan_training = -1, plan_mode = 0; size_t plan_need = 0;   // cached dry run
+    int plan_B = 0, plan_H = 0, plan_W = 0, plan_training = -1, plan_mode = 0, plan_epoch = -1; size_t plan_need = 0;   // cached dry run
     bool side_enabled = true;
     int ensure_side() {
         if (!side_enabled || side) return TF_OK;
@@ -772,11 +772,13 @@ TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, c
     TF_REQUIRE(B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_forward: bad shape/mode");
     Model* m = reinterpret_cast<Model*>(handle);
     size_t need;
-    if (m->plan_B == B && m->plan_H == H && m->plan_W == W && m->plan_training == training && m->plan_mode == mode) {
+    if (m->plan_B == B && m->plan_H == H && m->plan_W == W && m->plan_training == training && m->plan_mode == mode &&
+        m->plan_epoch == tfg::debug_epoch()) {
         need = m->plan_need;                     // same shape as the last call: the dry-run plan is still valid
     } else {
         RC(tf_model_workspace_bytes(handle, B, H, W, training, mode, &need));
         m->plan_B = B; m->plan_H = H; m->plan_W = W; m->plan_training = training; m->plan_mode = mode; m->plan_need = need;
+        m->plan_epoch = tfg::debug_epoch();
     }
     m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode;
     if (workspace_bytes < need) { tf_set_error("tf_model_forward: workspace %zu < required %zu", workspace_bytes, need); return TF_ERR_WORKSPACE; }
