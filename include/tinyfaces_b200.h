@@ -75,6 +75,14 @@ int tf_conv2d_wgrad_nhwc_strided(const float* x, const float* dy, int B, int H, 
 int tf_conv2d_dgrad_s2_nhwc(const float* dy, int B, int H, int W, int Cdy, const float* w_packed, int Cdx, int ksize,
                             int accumulate, float* dx, void* stream);
 
+/* host-only views of the GEMM launch planning (no CUDA calls; used by the CPU tests):
+ * tf_conv_plan -> out16 = {spatial, tw, th, tiles_x, tiles_y, m_tiles, bn, n_tiles, grid, two_cta, main_tiles, ksplit,
+ *                          kiters, tail_pix0 & 0x7fffffff (or -1), tail_pix0 >> 31 (or -1), 0};
+ * tf_dgrad_s2_taps -> number of taps (0..4) of parity class (py, px) and their (weight tap, dY x offset, dY y offset). */
+int tf_conv_plan(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int nseg, int plain, int has_res,
+                 int num_sms, int* out16_host);
+int tf_dgrad_s2_taps(int ksize, int py, int px, int* tap_w_host, int* tap_ox_host, int* tap_oy_host);
+
 /* ---- one image-pyramid level with the exact arithmetic of tinyfaces/evaluation.py:40-50 (to_pil_image, PIL bilinear
  * resize, ToTensor, Normalize).  img: float32 [3,H,W] in [0,1]; the int32 tables hold Pillow's fixed-point resampling
  * coefficients (bounds [out,2], taps [out,ksize]; NULL when that axis keeps its size); out: float32 [3,Ho,Wo]. */

@@ -117,3 +117,90 @@ def test_pil_resize_tables_are_bit_exact():
         arr = r.randint(0, 256, (H, W, 3)).astype(np.uint8)
         ref = np.asarray(transforms.functional.resize(Image.fromarray(arr), size))
         assert np.array_equal(ref, emulate(arr, size)), (H, W, size)
+
+
+# ------------------------------------------------------------------------------------------- GEMM launch planning (host)
+def _plan(B, H, W, Cin, Cout, k, stride=1, nseg=1, plain=1, has_res=0, sms=148):
+    from tinyfaces_b200 import _lib
+    out = (ctypes.c_int * 16)()
+    assert _lib.lib().tf_conv_plan(B, H, W, Cin, Cout, k, stride, nseg, plain, has_res, sms, out) == 0
+    keys = ["spatial", "tw", "th", "tiles_x", "tiles_y", "m_tiles", "bn", "n_tiles", "grid", "two_cta", "main_tiles", "ksplit",
+            "kiters", "tail_lo", "tail_hi"]
+    d = dict(zip(keys, list(out)))
+    d["tail_pix0"] = -1 if d["tail_lo"] < 0 else (d["tail_hi"] << 31) | d["tail_lo"]
+    return d
+
+
+def test_conv_plan_known_answers_and_invariants():
+    """tf_conv_plan (pure host arithmetic): the bench's layer-3 shapes, and invariants over a sweep of shapes."""
+    p = _plan(8, 60, 80, 256, 256, 3)                     # layer-3 3x3 at batch-8 960x1280: 320 tiles on 148 SMs
+    assert (p["bn"], p["m_tiles"], p["grid"], p["two_cta"]) == (256, 320, 148, 0)
+    assert (p["main_tiles"], p["ksplit"], p["kiters"]) == (295, 5, 72)              # 25 tail tiles cut into 5 K slices
+    assert p["tail_pix0"] == (7 * 60 + 24) * 80           # image 7, tile row 3 (th = 8): the split rows are contiguous to the end
+    p = _plan(8, 60, 80, 1024, 256, 1)                    # layer-3 conv1: flat, K-heavy, one n-tile -> 2-CTA tiles
+    assert (p["spatial"], p["bn"], p["two_cta"], p["ksplit"]) == (0, 256, 1, 1)
+    p = _plan(8, 60, 80, 256, 1024, 1)                    # layer-3 conv3: 1200 tiles, no split (1x1), one-CTA kernel
+    assert (p["bn"], p["n_tiles"], p["grid"], p["two_cta"], p["ksplit"], p["main_tiles"]) == (256, 4, 148, 0, 1, 1200)
+    assert _plan(8, 60, 80, 256, 256, 3, plain=0)["ksplit"] == 1          # a fused epilogue cannot take K slices
+    assert _plan(8, 60, 80, 1024, 256, 1, has_res=1)["two_cta"] == 0      # the residual epilogue lives in the one-CTA kernel
+    r = np.random.RandomState(0)
+    for _ in range(300):
+        B, H, W = int(r.randint(1, 9)), int(r.randint(4, 200)), int(r.randint(4, 200))
+        Cin, Cout = int(r.choice([32, 64, 128, 256, 512, 1024])), int(r.choice([64, 128, 256, 512, 1024]))
+        k, stride, nseg = int(r.choice([1, 3])), int(r.choice([1, 2])), int(r.choice([1, 3]))
+        p = _plan(B, H, W, Cin, Cout, k, stride, nseg)
+        Ho, Wo = ((H + 1) // 2, (W + 1) // 2) if stride == 2 else (H, W)
+        tiles = p["m_tiles"] * p["n_tiles"]
+        assert p["bn"] in (64, 128, 256) and Cout % p["bn"] == 0 and p["n_tiles"] == Cout // p["bn"]
+        assert 0 < p["grid"] <= 148 and p["grid"] % p["n_tiles"] == 0                 # one n-tile per CTA (BN statistics rows)
+        assert p["kiters"] == nseg * k * k * Cin // 32
+        if p["spatial"]:
+            assert p["tw"] * p["th"] == 128 and p["tiles_x"] * p["tw"] >= Wo and p["tiles_y"] * p["th"] >= Ho
+            assert p["m_tiles"] == B * p["tiles_x"] * p["tiles_y"]
+        else:
+            assert p["m_tiles"] == (B * Ho * Wo + 127) // 128
+        if p["ksplit"] > 1:
+            assert k == 3 and not p["two_cta"] and 0 < p["main_tiles"] < tiles and p["main_tiles"] % p["n_tiles"] == 0
+            tail = tiles - p["main_tiles"]
+            assert tail * p["ksplit"] <= p["grid"] and p["ksplit"] * 8 <= p["kiters"]      # one round of K slices, >= 8 K steps each
+            main_m = p["main_tiles"] // p["n_tiles"]
+            assert main_m % p["tiles_x"] == 0                                            # split region starts at a tile-row boundary
+            img, ty = divmod(main_m, p["tiles_x"] * p["tiles_y"])[0], (main_m % (p["tiles_x"] * p["tiles_y"])) // p["tiles_x"]
+            assert p["tail_pix0"] == (img * Ho + ty * p["th"]) * Wo and 0 <= p["tail_pix0"] < B * Ho * Wo
+        else:
+            assert p["main_tiles"] == tiles and p["tail_pix0"] == -1
+
+
+def test_stride2_dgrad_parity_class_taps_reproduce_autograd():
+    """The tap tables of conv_dgrad_s2 (tf_dgrad_s2_taps), evaluated with numpy on the CPU, give the input gradient of a
+    stride-2 convolution: dx[2i+py, 2j+px] = sum_t dy[i+oy_t, j+ox_t] . Wflip[tap_t]  (no zero insertion)."""
+    import torch
+    from tinyfaces_b200 import _lib
+    lib = _lib.lib()
+    gen = torch.Generator().manual_seed(0)
+    for (k, H, W) in [(3, 9, 12), (3, 10, 7), (3, 8, 8), (1, 9, 12), (1, 6, 5)]:
+        Ci, Co, B = 5, 4, 2
+        x = torch.zeros(B, Ci, H, W, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(Co, Ci, k, k, generator=gen, dtype=torch.float64)
+        y = torch.nn.functional.conv2d(x, w, stride=2, padding=k // 2)
+        dy = torch.randn(y.shape, generator=gen, dtype=torch.float64)
+        y.backward(dy)
+        ref = x.grad.numpy()                                             # [B, Ci, H, W]
+        Ho, Wo = y.shape[2], y.shape[3]
+        wflip = w.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, k * k, Co).numpy()      # the packed dgrad layout [ci][flipped tap][co]
+        dyp = np.zeros((B, Co, Ho + 1, Wo + 1))
+        dyp[:, :, :Ho, :Wo] = dy.numpy()                                 # reads past the edge are zero (TMA out-of-bounds fill)
+        got = np.zeros_like(ref)
+        ntot = 0
+        for py in range(2):
+            for px in range(2):
+                tw_, ox, oy = (ctypes.c_int * 9)(), (ctypes.c_int * 9)(), (ctypes.c_int * 9)()
+                nt = lib.tf_dgrad_s2_taps(k, py, px, tw_, ox, oy)
+                ntot += nt
+                Hq, Wq = (H - py + 1) // 2, (W - px + 1) // 2
+                for t in range(nt):
+                    patch = dyp[:, :, oy[t]:oy[t] + Hq, ox[t]:ox[t] + Wq]                  # [B, Co, Hq, Wq]
+                    got[:, :, py::2, px::2] += np.einsum("bohw,io->bihw", patch, wflip[:, tw_[t], :])
+        assert ntot == (9 if k == 3 else 1)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
+    assert lib.tf_dgrad_s2_taps(2, 0, 0, tw_, ox, oy) == -1

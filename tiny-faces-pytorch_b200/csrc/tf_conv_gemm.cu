@@ -860,6 +860,89 @@ void pick_tile(int W, int H, int area, int* tw, int* th) {
     }
 }
 
+// ---- launch plan of one convolution GEMM: pure host arithmetic (no CUDA calls), exported as tf_conv_plan so that the
+//      CPU test-suite can check its invariants (tests/test_cabi_cpu.py)
+struct ConvPlan {
+    int spatial, tw, th, tiles_x, tiles_y, m_tiles;   // m-tiles: flat rows of 128 pixels or (tw x th) patches of one image
+    int bn, n_tiles, grid;                            // tile width, n-tiles, persistent CTAs (a multiple of n_tiles)
+    int two_cta;                                      // cta_group::2 kernel (256 x 256 tiles over CTA pairs)
+    int main_tiles, ksplit;                           // tail-wave split-K: tiles >= main_tiles are cut into ksplit K slices
+    long long tail_pix0;                              // first output pixel of the split region (-1: none); contiguous to the end
+    int kiters;
+};
+ConvPlan plan_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int nseg, bool plain, bool has_res,
+                   int num_sms, int force_bn, int two_cta_switch /*0 auto, 1 on, 2 off*/, bool allow_split) {
+    ConvPlan c = {};
+    const int taps = ksize * ksize;
+    const int Ho = stride == 2 ? (H + 1) / 2 : H, Wo = stride == 2 ? (W + 1) / 2 : W;
+    c.spatial = ksize == 3 || stride == 2;
+    const long long Mtot = (long long)B * Ho * Wo;
+    if (!c.spatial) { c.m_tiles = (int)((Mtot + BLOCK_M - 1) / BLOCK_M); c.tiles_x = c.tiles_y = 1; c.tw = 128; c.th = 1; }
+    else {
+        pick_tile(Wo, Ho, BLOCK_M, &c.tw, &c.th);
+        c.tiles_x = (Wo + c.tw - 1) / c.tw; c.tiles_y = (Ho + c.th - 1) / c.th;
+        c.m_tiles = B * c.tiles_x * c.tiles_y;
+    }
+    // tile width: fewest (rounds over the SMs) x (time per tile ~ BN); narrower tiles pay more smem bandwidth per MMA
+    c.bn = 64; double best = 1e30;
+    for (int cand = 256; cand >= 64; cand >>= 1) {
+        if (Cout % cand) continue;
+        const long long tiles = (long long)c.m_tiles * (Cout / cand);
+        const double rounds = (double)((tiles + num_sms - 1) / num_sms);
+        const double cost = rounds * cand * (cand == 256 ? 1.0 : (cand == 128 ? 1.45 : 2.2));   // measured: N=128 tiles are smem-bandwidth bound
+        if (cost < best) { best = cost; c.bn = cand; }
+    }
+    if (force_bn) c.bn = force_bn;
+    c.n_tiles = Cout / c.bn;
+    c.kiters = nseg * taps * (Cin / 32);
+    // 2-CTA (cta_group::2, 256 x 256 tiles): measured on B200 at batch-8 960x1280 -- K = 1024 1x1 (N = 256): 48.1 vs 52.8 us
+    // (49.4 vs 53.1 with the statistics epilogue); K = 256 -> N = 1024: 52.4 vs 53.8 (noise); 3x3: 77 vs 69 (the one-CTA
+    // kernel has the tail split-K).  So: flat GEMMs with a long K loop and a single 256-wide n-tile.
+    const bool two_cta_auto = !c.spatial && Cout == 256 && Cin >= 512 && nseg == 1;
+    c.two_cta = c.bn == 256 && two_cta_switch != 2 && (two_cta_switch == 1 || two_cta_auto) && c.m_tiles >= 2 && !has_res;
+    const int tiles = c.m_tiles * c.n_tiles;
+    c.grid = (tiles < num_sms ? tiles : num_sms) / c.n_tiles * c.n_tiles;
+    c.main_tiles = tiles; c.ksplit = 1; c.tail_pix0 = -1;
+    if (c.two_cta) return c;
+    // ---- tail-wave split-K: the m-tiles that do not fill a whole round over the CTAs are cut along K.  Only for a plain
+    //      epilogue (K slices cannot be scaled / clamped separately) and the 3x3 GEMMs (measured: for a K = 1024 1x1 the
+    //      two extra launches -- memset of the split rows, their BN statistics -- eat the 4 us).
+    if (plain && allow_split && taps == 9 && c.kiters >= 16 && c.grid > 0 && tiles > c.grid && tiles % c.grid != 0) {
+        const int full = tiles / c.grid;
+        int main_m = (int)((long long)full * c.grid / c.n_tiles);
+        if (c.spatial) main_m -= main_m % c.tiles_x;      // the split region starts at a tile-row boundary
+        const int tail_tiles = (c.m_tiles - main_m) * c.n_tiles;
+        int ks = tail_tiles > 0 ? c.grid / tail_tiles : 0;
+        if (ks > c.kiters / 8) ks = c.kiters / 8;
+        // rounds: ceil(main / grid) whole tiles + one round of 1/ks tiles (+ ~0.2 of a tile for the extra epilogue / launches)
+        const int main_rounds = (main_m * c.n_tiles + c.grid - 1) / c.grid;
+        if (ks >= 2 && main_m > 0 && main_rounds + 1.0 / ks + 0.2 < 0.92 * (double)((tiles + c.grid - 1) / c.grid)) {     // worth >= 8 %
+            c.main_tiles = main_m * c.n_tiles; c.ksplit = ks;
+            if (c.spatial) {
+                const int tpi = c.tiles_x * c.tiles_y, img = main_m / tpi, ty = (main_m % tpi) / c.tiles_x;
+                c.tail_pix0 = ((long long)img * Ho + (long long)ty * c.th) * Wo;
+            } else c.tail_pix0 = (long long)main_m * BLOCK_M;
+        }
+    }
+    return c;
+}
+// taps of parity class (py, px) of a stride-2 dgrad, in the stride-1 numbering t = (dy'+1)*3 + (dx'+1) of the flipped
+// packed weights: dy' = 0 for even rows (dY offset 0); dy' = -1 (offset 0) and +1 (offset +1) for odd rows; likewise in x
+int s2_class_taps(int ksize, int py, int px, int* tap_w, int* tap_ox, int* tap_oy) {
+    if (ksize == 1) { if (py || px) return 0; tap_w[0] = 0; tap_ox[0] = 0; tap_oy[0] = 0; return 1; }
+    int nt = 0;
+    const int ny = py ? 2 : 1, nx = px ? 2 : 1;
+    for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+            const int dyp = py ? (iy ? 1 : -1) : 0, dxp = px ? (ix ? 1 : -1) : 0;
+            tap_oy[nt] = dyp == 1 ? 1 : 0;
+            tap_ox[nt] = dxp == 1 ? 1 : 0;
+            tap_w[nt] = (dyp + 1) * 3 + (dxp + 1);
+            ++nt;
+        }
+    return nt;
+}
+
 int g_num_sms = 0;
 int* g_err_flag = nullptr;
 int ensure_device_state() {
@@ -972,21 +1055,12 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     GemmParams p = {};
     const int stride = a.stride == 2 ? 2 : 1;
     const int Ho = stride == 2 ? (H + 1) / 2 : H, Wo = stride == 2 ? (W + 1) / 2 : W;      // output size
-    const bool spatial = a.ksize == 3 || stride == 2;
     const long long Mtot = (long long)B * Ho * Wo;
-    int m_tiles;
-    if (!spatial) m_tiles = (int)((Mtot + BLOCK_M - 1) / BLOCK_M);
-    else { int tw, th; pick_tile(Wo, Ho, BLOCK_M, &tw, &th); m_tiles = B * ((Wo + tw - 1) / tw) * ((Ho + th - 1) / th); }
-    // tile width: fewest (rounds over the SMs) x (time per tile ~ BN); narrower tiles pay more smem bandwidth per MMA
-    int BN = 64; double best = 1e30;
-    for (int cand = 256; cand >= 64; cand >>= 1) {
-        if (Cout % cand) continue;
-        const long long tiles = (long long)m_tiles * (Cout / cand);
-        const double rounds = (double)((tiles + g_num_sms - 1) / g_num_sms);
-        const double cost = rounds * cand * (cand == 256 ? 1.0 : (cand == 128 ? 1.45 : 2.2));   // measured: N=128 tiles are smem-bandwidth bound
-        if (cost < best) { best = cost; BN = cand; }
-    }
-    if (g_debug[2]) BN = g_debug[2];
+    const bool plain = !a.scale && !a.shift && !a.relu && !a.round_out;
+    const ConvPlan cp = plan_conv(B, H, W, Cin, Cout, a.ksize, stride, a.x_lo ? 3 : 1, plain, a.res != nullptr, g_num_sms,
+                                  g_debug[2], g_debug[4], g_debug[3] != 2);
+    const bool spatial = cp.spatial != 0;
+    const int BN = cp.bn;
     default_taps(p, taps); p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1;
     p.scale = a.scale; p.shift = a.shift; p.relu = a.relu; p.round_out = a.round_out;
     p.accumulate = a.accumulate || g_debug[1];
@@ -1005,19 +1079,13 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
     const float* bs[3] = {a.w, a.w, a.w_lo};
     const long long M = Mtot;
     p.stride = stride;
+    p.spatial = cp.spatial; p.num_m_tiles = cp.m_tiles; p.tiles_x = cp.tiles_x; p.tiles_y = cp.tiles_y; p.tw = cp.tw; p.th = cp.th;
     if (!spatial) {
-        p.spatial = 0;
-        p.num_m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
-        p.tiles_x = p.tiles_y = 1; p.tw = 128; p.th = 1;
         for (int s = 0; s < p.nseg; ++s)
             if ((rc = encode_2d(&maps.a[s], as[s], Cin, M, Cin, 32, BLOCK_M))) return rc;
         if ((rc = encode_2d(&maps.d, a.y, Cout, M, Cout, 32, 32))) return rc;          // one store box per epilogue warp
         if (a.res && (rc = encode_2d(&maps.res, a.res, Cout, M, Cout, 32, 32))) return rc;
     } else {
-        p.spatial = 1;
-        pick_tile(Wo, Ho, BLOCK_M, &p.tw, &p.th);
-        p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th;
-        p.num_m_tiles = B * p.tiles_x * p.tiles_y;
         for (int s = 0; s < p.nseg; ++s)
             if ((rc = encode_4d(&maps.a[s], as[s], Cin, W, H, B, 32, p.tw, p.th, CU_TENSOR_MAP_SWIZZLE_128B, stride))) return rc;
         {   // per-warp store box: 32 consecutive tile rows = (bw x bh) pixels of the patch
@@ -1025,49 +1093,22 @@ int conv_fprop(const ConvArgs& a, cudaStream_t st) {
             if ((rc = encode_4d(&maps.d, a.y, Cout, Wo, Ho, B, 32, bw, bh))) return rc;
         }
     }
-    // 2-CTA (cta_group::2, 256 x 256 tiles): measured on B200 at batch-8 960x1280 -- K = 1024 1x1 (N = 256): 48.1 vs 52.8 us
-    // (49.4 vs 53.1 with the statistics epilogue); K = 256 -> N = 1024: 52.4 vs 53.8 (noise); 3x3: 77 vs 69 (the one-CTA
-    // kernel has the tail split-K).  So: flat GEMMs with a long K loop and a single 256-wide n-tile.
-    const bool two_cta_auto = !spatial && Cout == 256 && Cin >= 512 && p.nseg == 1;
-    const bool two_cta = BN == 256 && g_debug[4] != 2 && (g_debug[4] == 1 || two_cta_auto) && p.num_m_tiles >= 2 && !a.res;
+    const bool two_cta = cp.two_cta != 0;
     for (int s = 0; s < p.nseg; ++s)
         if ((rc = encode_2d(&maps.b[s], bs[s], (uint64_t)taps * Cin, Cout, (uint64_t)taps * Cin, 32, two_cta ? 128 : BN))) return rc;
     int stats_rows = 0;
+    p.main_tiles = cp.main_tiles; p.ksplit = cp.ksplit;
     if (two_cta) {
         // 2-CTA (cta_group::2) kernel for 256-wide tiles: each CTA of the pair stages half (128 rows) of the B tile
-        p.main_tiles = p.num_m_tiles * p.num_n_tiles; p.ksplit = 1;
         if ((rc = launch_gemm2(maps, p, &stats_rows, st))) return rc;
         if (a.stats_blocks) *a.stats_blocks = stats_rows;
         return TF_OK;
     }
-    const int tiles = p.num_m_tiles * p.num_n_tiles;
-    const int grid = (tiles < g_num_sms ? tiles : g_num_sms) / p.num_n_tiles * p.num_n_tiles;
+    const int grid = cp.grid;
     stats_rows = grid / p.num_n_tiles;
-    // ---- tail-wave split-K plan: the m-tiles that do not fill a whole round over the CTAs are cut along K.
-    //      Only for a plain epilogue (K slices cannot be scaled / clamped separately) and a K loop worth cutting.
-    p.main_tiles = tiles; p.ksplit = 1;
-    long long tail_pix0 = -1;                            // first output pixel of the split region (contiguous to the end)
-    const int kiters = p.nseg * p.taps * p.kblocks;
-    const bool plain = !a.scale && !a.shift && !a.relu && !a.round_out;
-    if (plain && g_debug[3] != 2 && taps == 9 && kiters >= 16 && tiles > grid && tiles % grid != 0) {     // (measured: the two extra launches eat the gain of a K = 1024 1x1)
-        const int full = tiles / grid;
-        int main_m = (int)((long long)full * grid / p.num_n_tiles);
-        if (p.spatial) main_m -= main_m % p.tiles_x;      // the split region starts at a tile-row boundary
-        const int tail_tiles = (p.num_m_tiles - main_m) * p.num_n_tiles;
-        int ks = grid / tail_tiles;
-        if (ks > kiters / 8) ks = kiters / 8;
-        // rounds: ceil(main / grid) whole tiles + one round of 1/ks tiles (+ ~0.2 of a tile for the extra epilogue / launches)
-        const int main_rounds = (main_m * p.num_n_tiles + grid - 1) / grid;
-        if (ks >= 2 && main_m > 0 && main_rounds + 1.0 / ks + 0.2 < 0.92 * (double)((tiles + grid - 1) / grid)) {     // worth >= 8 %
-            p.main_tiles = main_m * p.num_n_tiles; p.ksplit = ks;
-            if (p.spatial) {
-                const int tpi = p.tiles_x * p.tiles_y, img = main_m / tpi, ty = (main_m % tpi) / p.tiles_x;
-                tail_pix0 = ((long long)img * Ho + (long long)ty * p.th) * Wo;
-            } else tail_pix0 = (long long)main_m * BLOCK_M;
-            if (!p.accumulate)
-                TF_CHECK_CUDA(cudaMemsetAsync(a.y + tail_pix0 * Cout, 0, (size_t)(Mtot - tail_pix0) * Cout * sizeof(float), st));
-        }
-    }
+    const long long tail_pix0 = cp.tail_pix0;            // tail-wave split-K region (plan_conv), contiguous to the end
+    if (tail_pix0 >= 0 && !p.accumulate)
+        TF_CHECK_CUDA(cudaMemsetAsync(a.y + tail_pix0 * Cout, 0, (size_t)(Mtot - tail_pix0) * Cout * sizeof(float), st));
     if (BN == 256) rc = launch_gemm<256>(maps, p, grid, st);
     else if (BN == 128) rc = launch_gemm<128>(maps, p, grid, st);
     else rc = launch_gemm<64>(maps, p, grid, st);
@@ -1109,21 +1150,9 @@ int conv_dgrad_s2(const ConvArgs& a, cudaStream_t st) {
             GemmParams p = {};
             p.kblocks = Cin / 32; p.nseg = a.x_lo ? 3 : 1; p.stride = 1; p.spatial = 1;
             p.accumulate = a.accumulate; p.cout = Cout; p.img_w = Wq; p.img_h = Hq; p.err_flag = g_err_flag;
-            // taps of this class in the stride-1 numbering t = (dy'+1)*3 + (dx'+1): dy' = 0 for even rows (dy offset 0),
-            // dy' = -1 (offset 0) and +1 (offset +1) for odd rows; likewise in x
-            int nt = 0;
-            if (a.ksize == 1) { p.tap_ox[0] = 0; p.tap_oy[0] = 0; p.tap_w[0] = 0; nt = 1; }
-            else {
-                const int ny = py ? 2 : 1, nx = px ? 2 : 1;
-                for (int iy = 0; iy < ny; ++iy)
-                    for (int ix = 0; ix < nx; ++ix) {
-                        const int dyp = py ? (iy ? 1 : -1) : 0, dxp = px ? (ix ? 1 : -1) : 0;
-                        p.tap_oy[nt] = (signed char)(dyp == 1 ? 1 : 0);
-                        p.tap_ox[nt] = (signed char)(dxp == 1 ? 1 : 0);
-                        p.tap_w[nt] = (unsigned char)((dyp + 1) * 3 + (dxp + 1));
-                        ++nt;
-                    }
-            }
+            int tw_[9], tox[9], toy[9];
+            const int nt = s2_class_taps(a.ksize, py, px, tw_, tox, toy);
+            for (int t = 0; t < nt; ++t) { p.tap_w[t] = (unsigned char)tw_[t]; p.tap_ox[t] = (signed char)tox[t]; p.tap_oy[t] = (signed char)toy[t]; }
             p.taps = nt;
             pick_tile(Wq, Hq, BLOCK_M, &p.tw, &p.th);
             p.tiles_x = (Wq + p.tw - 1) / p.tw; p.tiles_y = (Hq + p.th - 1) / p.th;
@@ -1254,6 +1283,26 @@ TF_API int tf_conv2d_dgrad_s2_nhwc(const float* dy, int B, int H, int W, int Cdy
     tfg::ConvArgs a = {};
     a.x = dy; a.B = B; a.H = H; a.W = W; a.Cin = Cdy; a.w = w_packed; a.Cout = Cdx; a.ksize = ksize; a.accumulate = accumulate; a.y = dx;
     return tfg::conv_dgrad_s2(a, (cudaStream_t)stream);
+}
+
+// Host-only views of the launch planning, for the CPU test-suite (no CUDA calls):
+//   tf_conv_plan: out[16] = {spatial, tw, th, tiles_x, tiles_y, m_tiles, bn, n_tiles, grid, two_cta, main_tiles, ksplit,
+//                           kiters, tail_pix0 (low 31 bits), tail_pix0 >> 31, 0}
+TF_API int tf_conv_plan(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int nseg, int plain, int has_res,
+                        int num_sms, int* out16) {
+    TF_REQUIRE(out16 && B > 0 && H > 0 && W > 0 && Cin % 32 == 0 && Cout % 64 == 0 && (ksize == 1 || ksize == 3) && num_sms > 0,
+               "tf_conv_plan: bad args");
+    const ConvPlan c = plan_conv(B, H, W, Cin, Cout, ksize, stride == 2 ? 2 : 1, nseg, plain != 0, has_res != 0, num_sms, 0, 0, true);
+    const int v[16] = {c.spatial, c.tw, c.th, c.tiles_x, c.tiles_y, c.m_tiles, c.bn, c.n_tiles, c.grid, c.two_cta, c.main_tiles,
+                       c.ksplit, c.kiters, (int)(c.tail_pix0 < 0 ? -1 : (c.tail_pix0 & 0x7fffffff)),
+                       (int)(c.tail_pix0 < 0 ? -1 : (c.tail_pix0 >> 31)), 0};
+    for (int i = 0; i < 16; ++i) out16[i] = v[i];
+    return TF_OK;
+}
+//   tf_dgrad_s2_taps: the taps of parity class (py, px) of a stride-2 dgrad; returns the count (0..4), -1 on bad args
+TF_API int tf_dgrad_s2_taps(int ksize, int py, int px, int* tap_w, int* tap_ox, int* tap_oy) {
+    if (!(ksize == 1 || ksize == 3) || (py | px) & ~1 || !tap_w || !tap_ox || !tap_oy) return -1;
+    return s2_class_taps(ksize, py, px, tap_w, tap_ox, tap_oy);
 }
 
 // Reads (and clears) the device-side pipeline error flag set by a timed-out mbarrier wait.

@@ -46,6 +46,8 @@ _SIGS = {
     "tf_conv2d_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "tf_conv2d_nhwc_strided": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "tf_conv2d_wgrad_nhwc_strided": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "tf_conv_plan": (c_i32, [c_i32] * 11 + [ctypes.POINTER(c_i32)]),
+    "tf_dgrad_s2_taps": (c_i32, [c_i32, c_i32, c_i32, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "tf_conv2d_dgrad_s2_nhwc": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "tf_conv2d_wgrad_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
 }
