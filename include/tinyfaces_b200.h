@@ -20,7 +20,15 @@ extern "C" {
 
 const char* tf_last_error_string(void);
 int tf_version(void);
-int tf_debug_set(int key, int value);            /* test hooks only */
+/* Experiment switches (test / A-B hooks only; 0 = the default behaviour of every key):
+ *   0: wgrad plain store, no split-K   1: force accumulate in tf_conv2d_nhwc   2: force the GEMM tile width (64/128/256)
+ *   3: 2 = tail-wave split-K off       4: 1 = 2-CTA GEMM everywhere it fits, 2 = never
+ *   5: 1/2/3 = weight-gradient schedule (before its dgrad / after it / deferred to the next block [default])
+ *   6: 1 = backward chain on the caller's stream (no priority stream)      7: 1 = force the BN-statistics epilogue
+ *   8: 2 = materialise G and reduce-add (no residual epilogue in the conv1 dgrad)
+ *   9: bit 0 = bn_apply iterates descending, bit 1 = BN-backward column reduction ascending
+ *  11: 1 = stride-2 dgrad by zero insertion (old path)      12: 1 = inference conv3 without the fused shortcut epilogue */
+int tf_debug_set(int key, int value);
 int tf_gemm_error_flag(int* value_host);         /* HOST out: non-zero if a tcgen05 pipeline wait timed out */
 
 /* ---- greedy NMS: replaces torchvision.ops.nms as called at tinyfaces/evaluation.py:84 (float64 CPU tensors).
