@@ -27,7 +27,9 @@ int tf_version(void);
  *   6: 1 = backward chain on the caller's stream (no priority stream)      7: 1 = force the BN-statistics epilogue
  *   8: 2 = materialise G and reduce-add (no residual epilogue in the conv1 dgrad)
  *   9: bit 0 = bn_apply iterates descending, bit 1 = BN-backward column reduction ascending
- *  11: 1 = stride-2 dgrad by zero insertion (old path)      12: 1 = inference conv3 without the fused shortcut epilogue */
+ *  11: 1 = stride-2 dgrad by zero insertion (old path)      12: 1 = inference conv3 without the fused shortcut epilogue
+ *  13: 1 = tf_nms counts its IoU pair tests (tf_nms_sweep_stats)   14: 1/2/3 = tf_nms stops after sort / sweep / resolution
+ *      (stage timing; the result is then invalid) */
 int tf_debug_set(int key, int value);
 int tf_gemm_error_flag(int* value_host);         /* HOST out: non-zero if a tcgen05 pipeline wait timed out */
 
@@ -39,6 +41,16 @@ int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes_host);
 int tf_nms_set_algorithm(int algo);   /* test hook: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep + parallel resolution */
 int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int64_t* keep,
            int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+/* tf_nms with an explicit algorithm (0 auto, 1 blocked bit-matrix, 2 sort-and-sweep + parallel resolution).  Both entry
+ * points only ENQUEUE work on `stream` (no host synchronisation, graph-capturable).  The sort-and-sweep path keeps its
+ * conflict-edge list in the workspace (default capacity 128 edges per box; a larger workspace is used in full): if the
+ * list overflows, *num_keep is set to -1 on the device and the caller re-runs with algorithm 1, which is exact for
+ * every input.  Score order follows torch.sort (NaN first, -0.0 == +0.0, stable). */
+int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int algorithm,
+                int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+/* diagnostics of the last sort-and-sweep run on this workspace (SYNCHRONISES; not on the data path): out4_host =
+ * {conflict edges, IoU pair tests (counted under tf_debug_set(13, 1) only), resolution rounds, edge capacity} */
+int tf_nms_sweep_stats(int64_t n, int elem_bytes, void* workspace, size_t workspace_bytes, int64_t* out4_host, void* stream);
 
 /* ---- threshold + ordered compaction + anchor decode: replaces get_bboxes + regression_refinement
  * (tinyfaces/models/utils.py:4-100) and the sigmoid / D2H / transpose of tinyfaces/evaluation.py:61-71.
@@ -69,6 +81,10 @@ int tf_detloss_sample_device(float* labels /* [B,L] in place */, int B, int64_t 
  * w_packed: [Cout][k*k][Cin]; stride 1, "same" padding; x_lo/w_lo: optional low halves for the 3xTF32 mode. */
 int tf_conv2d_nhwc(const float* x, const float* x_lo, int B, int H, int W, int Cin, const float* w_packed,
                    const float* w_lo, int Cout, int ksize, const float* bias, float* y, void* stream);
+/* 1x1 stride-1 with the residual epilogue: y = conv(x, w) + (res_mask bit ? res : 0); res_mask NULL = unmasked.  (The
+ * backward's "dx = conv1 dgrad + [out > 0] * dout" and the inference conv3 + shortcut.) */
+int tf_conv2d_nhwc_res(const float* x, int B, int H, int W, int Cin, const float* w_packed, int Cout, const float* res,
+                       const uint32_t* res_mask, float* y, void* stream);
 int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
                          float* dw_packed /* accumulated */, void* stream);
 /* stride 1 or 2 (padding ksize/2): y / dy are [B, ceil(H/s), ceil(W/s), Cout]; the stride is a TMA traversal stride */
@@ -90,6 +106,35 @@ int tf_conv2d_dgrad_s2_nhwc(const float* dy, int B, int H, int W, int Cdy, const
 int tf_conv_plan(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int nseg, int plain, int has_res,
                  int num_sms, int* out16_host);
 int tf_dgrad_s2_taps(int ksize, int py, int px, int* tap_w_host, int* tap_ox_host, int* tap_oy_host);
+
+/* ---- the elementwise kernels between the GEMMs, one entry point each (NHWC fp32, tensors are [pixels, C] with C a power
+ * of two in [64, 1024]); the whole-model executor below launches exactly these kernels.
+ *   tf_bn_train_fwd / tf_bn_eval_fwd / tf_bn_bwd : nn.BatchNorm2d (+ shortcut add + ReLU) of torchvision resnet.py:143-163
+ *     and its autograd backward.  relu_mask: 1 bit per element ((M*C+31)/32 words), bit = [out > 0] (the ReLU derivative the
+ *     backward uses -- 0 at exactly 0, like ATen's threshold_backward).  round_tf32 != 0 rounds the result to TF32 (what the
+ *     executor's `fast` mode stores for the next GEMM); 0 keeps fp32.
+ *   tf_maxpool_fwd / _bwd : nn.MaxPool2d(3, 2, 1) (resnet.py:197-204); ties go to the first maximum in window scan order.
+ *   tf_head_upsample_add_fwd / _bwd : score_res3 + crop(score4_upsample(score_res4)) of tinyfaces/models/model.py:104-126
+ *     (ConvTranspose2d k4 s2 p1 with the frozen diagonal bilinear weight up_w [Cn,Cn,4,4]); s3/s4 NHWC with Cp >= Cn
+ *     channels per pixel, out / dout NCHW [B,Cn,H3,W3]. */
+int tf_bn_workspace_bytes(size_t* bytes_host);
+int tf_bn_train_fwd(const float* y, int64_t M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                    float* run_mean, float* run_var, const float* res, int relu, int round_tf32, float* out,
+                    uint32_t* relu_mask, float* save_mean, float* save_rstd, void* workspace, size_t workspace_bytes,
+                    void* stream);
+int tf_bn_eval_fwd(const float* y, int64_t M, int C, const float* gamma, const float* beta, const float* run_mean,
+                   const float* run_var, float eps, const float* res, int relu, int round_tf32, float* out, void* workspace,
+                   size_t workspace_bytes, void* stream);
+int tf_bn_bwd(const float* dout, const uint32_t* relu_mask, const float* y, const float* save_mean, const float* save_rstd,
+              const float* gamma, int64_t M, int C, float* dgamma, float* dbeta, float* dy, float* g_out, int round_tf32,
+              void* workspace, size_t workspace_bytes, void* stream);
+int tf_maxpool_fwd(const float* x, int B, int H, int W, int C, float* out, uint8_t* argmax, void* stream);
+int tf_maxpool_bwd(const uint8_t* argmax, const float* dout, int B, int H, int W, int C, float* dx, void* stream);
+int tf_head_workspace_bytes(int Cn, size_t* bytes_host);
+int tf_head_upsample_add_fwd(const float* s3, const float* s4, const float* up_w, int B, int H3, int W3, int H4, int W4,
+                             int Cn, int Cp, float* out_nchw, void* workspace, size_t workspace_bytes, void* stream);
+int tf_head_upsample_add_bwd(const float* dout_nchw, const float* up_w, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
+                             float* ds3, float* ds4, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- one image-pyramid level with the exact arithmetic of tinyfaces/evaluation.py:40-50 (to_pil_image, PIL bilinear
  * resize, ToTensor, Normalize).  img: float32 [3,H,W] in [0,1]; the int32 tables hold Pillow's fixed-point resampling

@@ -145,6 +145,22 @@ def golden_nms():
     b32, s32 = boxes.astype(np.float32), scores.astype(np.float32)
     keep = torchvision.ops.nms(torch.from_numpy(b32), torch.from_numpy(s32), 0.3).numpy()
     save("nms_case_f32.npz", boxes=b32, scores=s32, thr=np.float64(0.3), keep=keep)
+    # large edge case: NaN / +-0 / +-inf scores, heavy ties, a few NaN coordinates -- big enough for the sort-and-sweep path
+    boxes, scores = synth.synthetic_boxes(6000, seed=41, extent=500.0, dup_frac=0.05)
+    r = np.random.RandomState(42)
+    scores = np.round(scores, 2)
+    scores[r.randint(0, 6000, 300)] = np.nan
+    scores[r.randint(0, 6000, 300)] = 0.0
+    scores[r.randint(0, 6000, 300)] = -0.0
+    scores[r.randint(0, 6000, 50)] = np.inf
+    scores[r.randint(0, 6000, 50)] = -np.inf
+    scores[r.randint(0, 6000, 20)] = -np.nan
+    for c in range(4):
+        boxes[r.randint(0, 6000, 15), c] = np.nan
+    keep = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(scores), 0.3).numpy()
+    save("nms_edge.npz", boxes=boxes, scores=scores, thr=np.float64(0.3), keep=keep)
+    keep = torchvision.ops.nms(torch.from_numpy(boxes), torch.full((6000,), 0.25, dtype=torch.float64), 0.3).numpy()
+    save("nms_allequal.npz", boxes=boxes, scores=np.full(6000, 0.25), thr=np.float64(0.3), keep=keep)
     # known-answer semantics
     ka = []
     def run(b, s, t):
@@ -155,6 +171,18 @@ def golden_nms():
     run([[0, 0, 2, 2], [0, 0, 2, 1]], [0.9, 0.8], 0.4999)
     run([[1, 1, 1, 1], [1, 1, 1, 1]], [0.3, 0.7], 0.3)
     run([[0, 0, 4, 4], [1, 1, 3, 3], [5, 5, 6, 6], [0, 0, 4, 4.0001]], [0.1, 0.2, 0.3, 0.1], 0.2)
+    # score-order edge semantics: torch.sort puts NaN first (all NaNs tie), -0.0 == +0.0, ties stable
+    six = [[0, 0, 10, 10], [20, 20, 30, 30], [40, 40, 50, 50], [60, 60, 70, 70], [80, 80, 90, 90], [100, 100, 110, 110]]
+    nan = float("nan")
+    run(six, [0.0, -0.0, 0.0, -0.0, 0.5, nan], 0.3)
+    run(six, [-0.0, 0.0, nan, -1.0, -nan, float("inf")], 0.3)
+    run(six, [0.7] * 6, 0.3)
+    same = [[0, 0, 10, 10]] * 3
+    run(same, [0.5, nan, 0.9], 0.3)
+    run(same, [0.0, -0.0, -0.0], 0.3)
+    run(same, [-0.0, 0.0, -0.0], 0.3)
+    run(same + [[0, 0, 10, 10.5]], [nan, nan, 1e300, -1e300], 0.3)
+    run([[0, 0, 10, 10], [nan, 0, 10, 10], [0, 0, 10, 10], [0, 0, nan, 10]], [0.9, 0.8, 0.7, 0.6], 0.3)
     with open(os.path.join(OUT, "nms_known.json"), "w") as f:
         json.dump(dict(meta=json.loads(META), cases=ka), f, indent=1)
     print("wrote nms_known.json")
@@ -175,6 +203,73 @@ def golden_detections():
                                            nms_thresh=0.3, scales=scales, device=torch.device("cpu"))
         save("detections_case%d.npz" % i, img=img.numpy(), thresh=np.float64(thr),
              scales=np.array(scales, np.float64), dets=dets)
+
+
+def _fingerprint(t):
+    """Small witness of a seeded tensor that is regenerated (not stored) by the tests."""
+    f = t.reshape(-1)
+    return np.concatenate([f[:16].numpy().astype(np.float64), [float(f.double().sum()), float(f.double().abs().sum())]])
+
+
+SEL_BASELINE = ["model.conv1.weight", "model.bn1.weight", "model.layer1.0.conv2.weight", "model.layer2.0.downsample.0.weight",
+                "model.layer2.3.conv3.weight", "model.layer3.0.conv2.weight", "model.layer3.5.conv2.weight",
+                "model.layer3.11.conv1.weight", "model.layer3.22.conv3.weight", "model.layer3.22.bn3.weight",
+                "model.layer3.22.bn3.bias", "score_res3.weight", "score_res3.bias", "score_res4.weight", "score_res4.bias"]
+
+
+def _sub(a, step):
+    return np.ascontiguousarray(a[:, :, ::step, ::step])
+
+
+def golden_baseline():
+    """Goldens at the BASELINE.json shapes.  Inputs are regenerated from their seeds by the tests
+    (a fingerprint is stored); outputs are stored as strided samples + the norms of the full map.
+      cfg1: 1x3x500x500 -- eval forward (calibrated statistics) and train forward + gradients;
+      cfg2: 1x3x960x1280 train forward + selected gradients; 8x3x960x1280 train forward only (the real GEMM sizes:
+            tail split-K statistics, 2-CTA tiles; the CPU backward at batch 8 would need ~40 GB)."""
+    sd = synth.synthetic_state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1)
+
+    def train_case(name, B, H, W, seed, step, with_grads):
+        x = torch.randn(B, 3, H, W, generator=torch.Generator().manual_seed(seed))
+        m = ref_model(sd)
+        m.train()
+        kw = {}
+        if with_grads:
+            out = m(x)
+            cot = torch.randn(out.shape, generator=torch.Generator().manual_seed(seed + 1))
+            (out * cot).sum().backward()
+            for k, p in m.named_parameters():
+                if k in SEL_BASELINE:
+                    g = p.grad.numpy()
+                    kw["grad:" + k] = g if g.size < 100000 else g[:8]
+                    kw["gnorm:" + k] = np.float64(np.linalg.norm(g.astype(np.float64)))
+            kw["cot_fp"] = _fingerprint(cot)
+            out = out.detach()
+        else:
+            with torch.no_grad():
+                out = m(x)
+        rs = m.state_dict()
+        o = out.numpy()
+        save(name, x_fp=_fingerprint(x), shape=np.array([B, 3, H, W]), seed=np.int64(seed), step=np.int64(step),
+             out_sub=_sub(o, step), out_l2=np.float64(np.linalg.norm(o.astype(np.float64))), out_max=np.float64(np.abs(o).max()),
+             out_chan_sum=o.astype(np.float64).sum(axis=(0, 2, 3)),
+             run_mean_l3=rs["model.layer3.22.bn3.running_mean"].numpy(), run_var_l3=rs["model.layer3.22.bn3.running_var"].numpy(),
+             run_var_bn1=rs["model.bn1.running_var"].numpy(), **kw)
+
+    train_case("cfg1_train.npz", 1, 500, 500, 50, 2, True)
+    train_case("cfg2_b1_train.npz", 1, 960, 1280, 60, 4, True)
+    train_case("cfg2_b8_fwd.npz", 8, 960, 1280, 70, 8, False)
+    # cfg1 eval: BASELINE.json configs[0] (single 500x500 image, forward)
+    xc = torch.randn(2, 3, 96, 136, generator=torch.Generator().manual_seed(4))
+    sdc = synth.calibrate_running_stats(sd, xc)
+    m = ref_model(sdc)
+    m.eval()
+    x = torch.randn(1, 3, 500, 500, generator=torch.Generator().manual_seed(80))
+    with torch.no_grad():
+        o = m(x).numpy()
+    save("cfg1_eval.npz", x_fp=_fingerprint(x), shape=np.array([1, 3, 500, 500]), seed=np.int64(80), step=np.int64(2),
+         out_sub=_sub(o, 2), out_l2=np.float64(np.linalg.norm(o.astype(np.float64))), out_max=np.float64(np.abs(o).max()),
+         out_chan_sum=o.astype(np.float64).sum(axis=(0, 2, 3)))
 
 
 if __name__ == "__main__":

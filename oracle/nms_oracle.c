@@ -7,7 +7,8 @@
  * installed 0.26.0); its published algorithm is restated here and pinned against
  * the installed op by tests/golden/nms_*.npz (oracle/make_golden.py) and
  * tests/test_oracle_golden.py:
- *   - stable sort by score, descending (ties: lower index first)
+ *   - stable sort by score, descending (ties: lower index first), in torch.sort's order: every NaN is the
+ *     largest value and NaNs tie with each other; -0.0 == +0.0
  *   - area = (x2-x1)*(y2-y1)   (no +1)
  *   - suppress j iff inter / (area_i + area_j - inter) > thr   (strict; NaN never)
  *   - keep indices returned in descending-score order, int64
@@ -17,13 +18,18 @@
 #include <stdlib.h>
 #include <string.h>
 
+static int score_gt(double x, double y) {            /* torch.sort(descending=True): NaN > everything, NaN == NaN */
+    if (x != x) return y == y;
+    return x > y;
+}
+
 static void merge_sort_desc(const double *s, int64_t *idx, int64_t *tmp, int64_t n) {
     /* bottom-up stable merge sort on indices, descending by s[] */
     for (int64_t w = 1; w < n; w *= 2) {
         for (int64_t lo = 0; lo < n; lo += 2 * w) {
             int64_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
             int64_t a = lo, b = mid, o = lo;
-            while (a < mid && b < hi) tmp[o++] = (s[idx[b]] > s[idx[a]]) ? idx[b++] : idx[a++];
+            while (a < mid && b < hi) tmp[o++] = score_gt(s[idx[b]], s[idx[a]]) ? idx[b++] : idx[a++];
             while (a < mid) tmp[o++] = idx[a++];
             while (b < hi) tmp[o++] = idx[b++];
         }
@@ -54,13 +60,14 @@ int64_t tf_oracle_nms_f64(const double *boxes, const double *scores, int64_t n, 
         for (int64_t b = a + 1; b < n; ++b) {
             int64_t j = order[b];
             if (dead[j]) continue;
-            double xx1 = ix1 > boxes[4 * j] ? ix1 : boxes[4 * j];
-            double yy1 = iy1 > boxes[4 * j + 1] ? iy1 : boxes[4 * j + 1];
-            double xx2 = ix2 < boxes[4 * j + 2] ? ix2 : boxes[4 * j + 2];
-            double yy2 = iy2 < boxes[4 * j + 3] ? iy2 : boxes[4 * j + 3];
+            /* std::max(a, b) = (a < b) ? b : a; std::min(a, b) = (b < a) ? b : a -- NaN coordinates propagate like this */
+            double xx1 = ix1 < boxes[4 * j] ? boxes[4 * j] : ix1;
+            double yy1 = iy1 < boxes[4 * j + 1] ? boxes[4 * j + 1] : iy1;
+            double xx2 = boxes[4 * j + 2] < ix2 ? boxes[4 * j + 2] : ix2;
+            double yy2 = boxes[4 * j + 3] < iy2 ? boxes[4 * j + 3] : iy2;
             double w = xx2 - xx1, h = yy2 - yy1;
-            w = w > 0 ? w : 0;
-            h = h > 0 ? h : 0;
+            w = 0 < w ? w : 0;
+            h = 0 < h ? h : 0;
             double inter = w * h;
             double ovr = inter / (ia + area[j] - inter);
             if (ovr > thr) dead[j] = 1;

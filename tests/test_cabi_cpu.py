@@ -204,3 +204,14 @@ def test_stride2_dgrad_parity_class_taps_reproduce_autograd():
         assert ntot == (9 if k == 3 else 1)
         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12)
     assert lib.tf_dgrad_s2_taps(2, 0, 0, tw_, ox, oy) == -1
+
+
+def test_package_synthetic_weights_equal_the_test_side_recipe():
+    """bench.py scores its forward against tests/golden/cfg2_b8_fwd.npz using tinyfaces_b200.synthetic.state_dict (the
+    product may not import oracle/): the two generators must agree draw for draw."""
+    import torch
+    from oracle import synth
+    from tinyfaces_b200 import synthetic
+    a = synth.synthetic_state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1)
+    b = synthetic.state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1)
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)

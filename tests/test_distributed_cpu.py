@@ -36,6 +36,16 @@ def _worker(rank, world, port, out_dir):
         ok = ok and torch.equal(b, torch.cat([l[0] for l in levels])) and torch.equal(s, torch.cat([l[1] for l in levels]))
     else:
         ok = ok and b is None
+    # --- a rank that owns no level at all (more ranks than levels): it still takes part in both collectives
+    mine = {0: levels[0], 2: levels[2]} if rank == 0 else {}
+    b, s = gather_level_candidates(mine, 3, dst=0, device="cpu")
+    if rank == 0:
+        ok = ok and torch.equal(b, torch.cat([levels[0][0], levels[2][0]])) and s.shape[0] == 16
+    else:
+        ok = ok and b is None
+    b, s = gather_level_candidates({}, 2, dst=0)                 # nobody has candidates
+    if rank == 0:
+        ok = ok and b.shape == (0, 4) and s.shape == (0,)
     with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
         f.write("1" if ok else "0")
     dist.destroy_process_group()

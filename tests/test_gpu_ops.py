@@ -17,20 +17,21 @@ def _dev():
 
 
 def _nms(boxes, scores, thr, algo=0):
-    from tinyfaces_b200 import _lib, ops
+    from tinyfaces_b200 import ops
     d = _dev()
-    _lib.lib().tf_nms_set_algorithm(algo)          # 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep
-    try:
-        keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr)
-        return keep[: int(count.item())].cpu().numpy()
-    finally:
-        _lib.lib().tf_nms_set_algorithm(0)
+    # algo: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep (tf_nms_algo); no fallback here: an overflow must show up
+    keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr, algo)
+    k = int(count.item())
+    assert k >= 0, "sort-and-sweep edge list overflow"
+    return keep[:k].cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------- NMS
 @pytest.mark.parametrize("algo", [1, 2])
-@pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_case_f32"])
+@pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_case_f32", "nms_edge", "nms_allequal"])
 def test_nms_golden_bit_exact(name, algo):
+    """nms_edge / nms_allequal: NaN, +-0.0, +-inf scores, heavy ties, NaN coordinates (torch.sort order: NaN first, all NaNs
+    tie, -0.0 == +0.0, stable) -- keep indices from torchvision.ops.nms itself."""
     g = np.load(os.path.join(G, name + ".npz"))
     assert np.array_equal(_nms(g["boxes"], g["scores"], float(g["thr"]), algo), g["keep"])
 
@@ -58,6 +59,47 @@ def test_nms_vs_c_oracle(n, extent, thr, algo):
     boxes, scores = synth.synthetic_boxes(n, seed=n, extent=extent, dup_frac=0.02)
     scores = np.round(scores, 3)            # many exact score ties
     assert np.array_equal(_nms(boxes, scores, thr, algo), nms_oracle.nms(boxes, scores, thr))
+
+
+def test_nms_edge_semantics_float32_and_stream_order():
+    """float32 flavour of the score-order edge cases against torchvision's CPU op semantics restated in numpy, and the
+    stream-ordered contract: tf_nms only enqueues -- two calls on a side stream, results read after ONE synchronise."""
+    from tinyfaces_b200 import ops
+    g = np.load(os.path.join(G, "nms_edge.npz"))
+    d = _dev()
+    b = torch.from_numpy(g["boxes"]).to(d)
+    s = torch.from_numpy(g["scores"]).to(d)
+    side = torch.cuda.Stream(d)
+    side.wait_stream(torch.cuda.current_stream(d))
+    with torch.cuda.stream(side):
+        k1, c1 = ops.nms_device(b, s, 0.3, 2)
+        k2, c2 = ops.nms_device(b.clone(), torch.full_like(s, 0.25), 0.3, 2)       # same workspace, back to back: stream order
+    side.synchronize()
+    assert np.array_equal(k1[: int(c1.item())].cpu().numpy(), g["keep"])
+    g2 = np.load(os.path.join(G, "nms_allequal.npz"))
+    assert np.array_equal(k2[: int(c2.item())].cpu().numpy(), g2["keep"])
+    st = ops.nms_sweep_stats(b.shape[0], 8, d)
+    assert 0 < st["edges"] <= st["edge_capacity"] and st["rounds"] >= 1
+
+
+def test_nms_sweep_overflow_is_flagged_and_falls_back():
+    """A conflict list larger than the workspace's edge capacity: tf_nms_algo(2) reports -1 on the device, nms_keep re-runs
+    the bit-matrix algorithm -- same answer as the oracle."""
+    from oracle import nms_oracle
+    from tinyfaces_b200 import ops
+    n = 6000
+    r = np.random.RandomState(3)
+    c = r.rand(n, 2) * 6.0                                   # 6000 boxes of ~40 px in a 6 px square: ~n^2/2 conflicts
+    wh = 40 + r.rand(n, 2)
+    boxes = np.concatenate([c - wh / 2, c + wh / 2], axis=1)
+    scores = r.rand(n)
+    d = _dev()
+    b, s = torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d)
+    keep, count = ops.nms_device(b, s, 0.3, 2, exact_workspace=True)
+    assert int(count.item()) == -1
+    torch.cuda.synchronize()
+    k = ops.nms_keep(b, s, 0.3)             # (falls back by itself if the shared workspace is small enough to overflow too)
+    assert np.array_equal(k.cpu().numpy(), nms_oracle.nms(boxes, scores, 0.3))
 
 
 def test_nms_large_n_property():

@@ -88,7 +88,7 @@ def test_decode_known_answer():
     assert np.allclose(boxes[0], [-55.83823529, -114.94411765, 117.83823529, 112.94411765])
 
 
-@pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2"])
+@pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_edge", "nms_allequal"])
 def test_nms_oracle_c_and_numpy(name):
     g = np.load(os.path.join(G, name + ".npz"))
     k = nms_oracle.nms(g["boxes"], g["scores"], float(g["thr"]))
@@ -104,3 +104,21 @@ def test_nms_known_answers():
         k = nms_oracle.nms(np.array(c["boxes"], np.float64), np.array(c["scores"], np.float64), c["thr"])
         assert k.tolist() == c["keep"], c
     assert nms_oracle.nms(np.zeros((0, 4)), np.zeros(0), 0.3).shape == (0,)
+
+
+@pytest.mark.parametrize("name,training", [("cfg1_eval", False), ("cfg1_train", True)])
+def test_model_oracle_at_cfg1_shape(name, training):
+    """BASELINE configs[0] (1x3x500x500 forward on CPU): the oracle against the reference-generated golden samples."""
+    import torch
+    from oracle import model_oracle, synth
+    g = np.load(os.path.join(G, name + ".npz"))
+    B, C, H, W = (int(v) for v in g["shape"])
+    x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(int(g["seed"])))
+    sd = synth.synthetic_state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1)
+    if not training:
+        sd = synth.calibrate_running_stats(sd, torch.randn(2, 3, 96, 136, generator=torch.Generator().manual_seed(4)))
+    with torch.no_grad():
+        out = model_oracle.forward(sd, x, training=training).numpy()
+    step = int(g["step"])
+    assert np.abs(out[:, :, ::step, ::step] - g["out_sub"]).max() <= 1e-3 * float(g["out_max"])
+    assert abs(np.linalg.norm(out.astype(np.float64)) - float(g["out_l2"])) <= 1e-3 * float(g["out_l2"])

@@ -943,16 +943,30 @@ int s2_class_taps(int ksize, int py, int px, int* tap_w, int* tap_ox, int* tap_o
     return nt;
 }
 
-int g_num_sms = 0;
-int* g_err_flag = nullptr;
+// per-device state (a process may drive several GPUs; the SM count and the pipeline-error flag belong to the
+// device that is current when a GEMM is enqueued)
+constexpr int MAX_DEVICES = 64;
+int g_num_sms_dev[MAX_DEVICES] = {0};
+int* g_err_flag_dev[MAX_DEVICES] = {nullptr};
+thread_local int g_num_sms = 0;
+thread_local int* g_err_flag = nullptr;
+std::mutex g_dev_mutex;
 int ensure_device_state() {
-    if (g_num_sms == 0) {
-        int dev;
-        TF_CHECK_CUDA(cudaGetDevice(&dev));
-        TF_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-        TF_CHECK_CUDA(cudaMalloc(&g_err_flag, sizeof(int)));
-        TF_CHECK_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+    int dev = 0;
+    TF_CHECK_CUDA(cudaGetDevice(&dev));
+    TF_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device index %d out of range", dev);
+    if (g_num_sms_dev[dev] == 0) {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (g_num_sms_dev[dev] == 0) {
+            int sms = 0;
+            TF_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            TF_CHECK_CUDA(cudaMalloc(&g_err_flag_dev[dev], sizeof(int)));
+            TF_CHECK_CUDA(cudaMemset(g_err_flag_dev[dev], 0, sizeof(int)));
+            g_num_sms_dev[dev] = sms;
+        }
     }
+    g_num_sms = g_num_sms_dev[dev];
+    g_err_flag = g_err_flag_dev[dev];
     return TF_OK;
 }
 
@@ -1255,6 +1269,17 @@ TF_API int tf_conv2d_nhwc(const float* x, const float* x_lo, int B, int H, int W
     return tfg::conv_fprop(a, (cudaStream_t)stream);
 }
 
+// 1x1 stride-1 GEMM with the residual epilogue: y[M,Cout] = x[M,Cin] * w^T + (res_mask bit ? res : 0)  -- the kernel the
+// training backward uses for "dx = conv1 dgrad + masked upstream gradient" (the masked term is never materialised) and
+// the inference forward for conv3 + shortcut.  res_mask: optional, 1 bit per element of res ((M*Cout+31)/32 words).
+TF_API int tf_conv2d_nhwc_res(const float* x, int B, int H, int W, int Cin, const float* w_packed, int Cout, const float* res,
+                              const uint32_t* res_mask, float* y, void* stream) {
+    tfg::ConvArgs a = {};
+    a.x = x; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.w = w_packed; a.Cout = Cout; a.ksize = 1; a.y = y;
+    a.res = res; a.res_mask = res_mask;
+    return tfg::conv_fprop(a, (cudaStream_t)stream);
+}
+
 // dw_packed[Cout][ksize*ksize][Cin] += sum_pixels dy[pixel, co] * x[pixel (+) tap, ci]   (caller zeroes dw_packed)
 TF_API int tf_conv2d_wgrad_nhwc(const float* x, const float* dy, int B, int H, int W, int Cin, int Cout, int ksize,
                                 float* dw_packed, void* stream) {
@@ -1305,12 +1330,14 @@ TF_API int tf_dgrad_s2_taps(int ksize, int py, int px, int* tap_w, int* tap_ox, 
     return s2_class_taps(ksize, py, px, tap_w, tap_ox, tap_oy);
 }
 
-// Reads (and clears) the device-side pipeline error flag set by a timed-out mbarrier wait.
+// Reads (and clears) the current device's pipeline error flag (set by a timed-out mbarrier wait).
 TF_API int tf_gemm_error_flag(int* value) {
     TF_REQUIRE(value, "tf_gemm_error_flag: null");
     *value = 0;
-    if (!g_err_flag) return TF_OK;
-    TF_CHECK_CUDA(cudaMemcpy(value, g_err_flag, sizeof(int), cudaMemcpyDeviceToHost));
-    TF_CHECK_CUDA(cudaMemset(g_err_flag, 0, sizeof(int)));
+    int dev = 0;
+    TF_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEVICES || !g_err_flag_dev[dev]) return TF_OK;
+    TF_CHECK_CUDA(cudaMemcpy(value, g_err_flag_dev[dev], sizeof(int), cudaMemcpyDeviceToHost));
+    TF_CHECK_CUDA(cudaMemset(g_err_flag_dev[dev], 0, sizeof(int)));
     return TF_OK;
 }

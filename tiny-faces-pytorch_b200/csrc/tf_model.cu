@@ -88,8 +88,20 @@ struct Model {
     size_t bwd_region_bytes = 0;
     int plan_B = 0, plan_H = 0, plan_W = 0, plan_training = -1, plan_mode = 0, plan_epoch = -1; size_t plan_need = 0;   // cached dry run
     bool side_enabled = true;
+    int side_dev = -1;                    // device the internal streams / events were created on
+    void destroy_side() {
+        if (!side) return;
+        cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_pack);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_region[i]); cudaEventDestroy(ev_chain[i]); }
+        side = nullptr; chain = nullptr;
+    }
     int ensure_side() {
-        if (!side_enabled || side) return TF_OK;
+        if (!side_enabled) return TF_OK;
+        int dev = 0;
+        TF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (side && side_dev != dev) destroy_side();          // the model moved to another GPU
+        if (side) return TF_OK;
+        side_dev = dev;
         TF_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -101,12 +113,7 @@ struct Model {
         TF_CHECK_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, greatest));
         return TF_OK;
     }
-    ~Model() {
-        if (side) {
-            cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_pack);
-            for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_region[i]); cudaEventDestroy(ev_chain[i]); }
-        }
-    }
+    ~Model() { destroy_side(); }
     // dW (OIHW) = unpack(wgrad(x, dy)) on stream s2 (the side stream, or the chain itself when there is none).
     // A 1x1 convolution's packed gradient [Cout][1][Cin] IS the OIHW tensor: it is accumulated straight into the
     // caller's gradient, no staging buffer / unpack pass.

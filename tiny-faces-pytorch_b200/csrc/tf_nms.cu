@@ -23,11 +23,6 @@ constexpr int COLS_PER_CTA = 256;
 
 using namespace tfnms;
 
-__global__ void iota_kernel(int* v, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = i;
-}
-
 template <typename T>
 __global__ void gather_sorted_kernel(const T* __restrict__ boxes, const int* __restrict__ order, int n,
                                      Box<T>* __restrict__ sb, T* __restrict__ area) {
@@ -188,7 +183,7 @@ struct Plan {
         size_t a = 0;
         auto add = [&](size_t b) { a = tf_align_up(a, 256) + b; };
         add(sizeof(int) * n); add(sizeof(int) * n);                 // iota, order
-        add(sizeof(T) * n);                                          // sorted keys
+        add(sizeof(T) * n); add(sizeof(T) * n);                      // canonical keys, sorted keys
         add(cub_bytes);
         add(sizeof(Box<T>) * n); add(sizeof(T) * n);                 // sorted boxes, areas
         add(sizeof(Box<T>) * n); add(sizeof(T) * n);                 // kept boxes, areas
@@ -207,6 +202,7 @@ int run_nms(const void* boxes, const void* scores, int64_t n, double thr, long l
     TfArena ar(ws, ws_bytes);
     int* iota = ar.take<int>(n);
     int* order = ar.take<int>(n);
+    T* keys_in = ar.take<T>(n);
     T* keys = ar.take<T>(n);
     void* cub_tmp = ar.take<char>(plan.cub_bytes);
     Box<T>* sb = ar.take<Box<T>>(n);
@@ -219,9 +215,9 @@ int run_nms(const void* boxes, const void* scores, int64_t n, double thr, long l
     const bool prefilter = thr >= 0.0;
     const int ni = (int)n;
     TF_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    iota_kernel<<<(ni + 255) / 256, 256, 0, st>>>(iota, ni);
+    prep_keys_kernel<T><<<(ni + 255) / 256, 256, 0, st>>>((const T*)scores, ni, keys_in, iota);      // torch.sort's NaN / -0.0 ordering
     size_t cb = plan.cub_bytes;
-    TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, cb, (const T*)scores, keys, (const int*)iota, order,
+    TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairsDescending(cub_tmp, cb, (const T*)keys_in, keys, (const int*)iota, order,
                                                             ni, 0, (int)sizeof(T) * 8, st));
     gather_sorted_kernel<T><<<(ni + 255) / 256, 256, 0, st>>>((const T*)boxes, order, ni, sb, area);
     for (int start = 0; start < ni; start += NB) {
@@ -252,7 +248,12 @@ size_t sweep_workspace_bytes(int64_t n, int elem_bytes);
 template <typename T>
 int run_nms_sweep(const void* boxes, const void* scores, int64_t n, double thr, long long* keep, long long* num_keep,
                   void* ws, size_t ws_bytes, cudaStream_t st);
+template <typename T>
+int sweep_stats(int64_t n, void* ws, size_t ws_bytes, long long* out4, cudaStream_t st);
 }
+
+TF_API int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int algorithm,
+                       int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
 
 // test hook: 0 = automatic choice, 1 = force the blocked bit-matrix path, 2 = force the sort-and-sweep path
 TF_API int tf_nms_set_algorithm(int algo) {
@@ -272,19 +273,34 @@ TF_API int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes) {
 
 TF_API int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold,
                   int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
+    return tf_nms_algo(boxes, scores, n, elem_bytes, iou_threshold, g_nms_algo, keep, num_keep, workspace, workspace_bytes, stream);
+}
+
+// algorithm: 0 = automatic (sort-and-sweep for n >= 4096 and thr >= 0, else the blocked bit-matrix), 1 = blocked bit-matrix,
+// 2 = sort-and-sweep.  Purely stream-ordered (graph-capturable): the sort-and-sweep path reports an edge list that does
+// not fit the workspace as *num_keep = -1 ON THE DEVICE; the caller, who has to read the count anyway before it can use
+// `keep`, then calls again with algorithm 1 (exact for every input) or a larger workspace.
+TF_API int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int algorithm,
+                       int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
     TF_REQUIRE(n >= 0 && n < (1ll << 31) && (elem_bytes == 8 || elem_bytes == 4), "tf_nms: bad args");
-    TF_REQUIRE(num_keep, "tf_nms: num_keep is null");
+    TF_REQUIRE(num_keep && algorithm >= 0 && algorithm <= 2, "tf_nms: num_keep is null / bad algorithm");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { TF_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st)); return TF_OK; }
     TF_REQUIRE(boxes && scores && keep && workspace, "tf_nms: null pointer");
-    const bool sweep = iou_threshold >= 0.0 && (g_nms_algo == 2 || (g_nms_algo == 0 && n >= SWEEP_MIN_N));
-    if (sweep) {
-        const int rc = elem_bytes == 8
+    const bool sweep = iou_threshold >= 0.0 && (algorithm == 2 || (algorithm == 0 && n >= SWEEP_MIN_N));
+    if (sweep)
+        return elem_bytes == 8
             ? tfnms::run_nms_sweep<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st)
             : tfnms::run_nms_sweep<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
-        if (rc <= 0) return rc;          // > 0: conflict list too large for the workspace -> exact fallback below
-    }
     if (elem_bytes == 8)
         return run_nms<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
     return run_nms<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
+}
+
+// Diagnostics of the last sort-and-sweep run on this workspace (SYNCHRONISES the stream; not part of the data path):
+// out4 = {conflict edges, IoU pair tests (counted only under tf_debug_set(13, 1)), resolution rounds, edge capacity}.
+TF_API int tf_nms_sweep_stats(int64_t n, int elem_bytes, void* workspace, size_t workspace_bytes, int64_t* out4, void* stream) {
+    TF_REQUIRE(n > 0 && out4 && workspace && (elem_bytes == 8 || elem_bytes == 4), "tf_nms_sweep_stats: bad args");
+    return elem_bytes == 8 ? tfnms::sweep_stats<double>(n, workspace, workspace_bytes, (long long*)out4, (cudaStream_t)stream)
+                           : tfnms::sweep_stats<float>(n, workspace, workspace_bytes, (long long*)out4, (cudaStream_t)stream);
 }

@@ -21,6 +21,8 @@ _SIGS = {
     "tf_nms_set_algorithm": (c_i32, [c_i32]),
     "tf_nms_workspace_bytes": (c_i32, [c_i64, c_i32, ctypes.POINTER(c_sz)]),
     "tf_nms": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "tf_nms_algo": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_f64, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "tf_nms_sweep_stats": (c_i32, [c_i64, c_i32, c_vp, c_sz, ctypes.POINTER(c_i64), c_vp]),
     "tf_decode_workspace_bytes": (c_i32, [c_i64, c_i64, c_i64, ctypes.POINTER(c_sz)]),
     "tf_decode": (c_i32, [c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32, c_i32, c_i32, c_i32,
                           ctypes.POINTER(c_f64), c_f32, c_u32, c_u32, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
@@ -43,7 +45,18 @@ _SIGS = {
     "tf_pyramid_workspace_bytes": (c_i32, [c_i32, c_i32, c_i32, ctypes.POINTER(c_sz)]),
     "tf_pyramid_level": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32,
                                  ctypes.POINTER(c_f32), ctypes.POINTER(c_f32), c_vp, c_vp, c_sz, c_vp]),
+    "tf_bn_workspace_bytes": (c_i32, [ctypes.POINTER(c_sz)]),
+    "tf_bn_train_fwd": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_f32, c_f32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp,
+                                c_vp, c_vp, c_sz, c_vp]),
+    "tf_bn_eval_fwd": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    "tf_bn_bwd": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp]),
+    "tf_maxpool_fwd": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "tf_maxpool_bwd": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "tf_head_workspace_bytes": (c_i32, [c_i32, ctypes.POINTER(c_sz)]),
+    "tf_head_upsample_add_fwd": (c_i32, [c_vp, c_vp, c_vp] + [c_i32] * 7 + [c_vp, c_vp, c_sz, c_vp]),
+    "tf_head_upsample_add_bwd": (c_i32, [c_vp, c_vp] + [c_i32] * 7 + [c_vp, c_vp, c_vp, c_sz, c_vp]),
     "tf_conv2d_nhwc": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "tf_conv2d_nhwc_res": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "tf_conv2d_nhwc_strided": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "tf_conv2d_wgrad_nhwc_strided": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "tf_conv_plan": (c_i32, [c_i32] * 11 + [ctypes.POINTER(c_i32)]),

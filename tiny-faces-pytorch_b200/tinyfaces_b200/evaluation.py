@@ -56,8 +56,7 @@ def nms(boxes, scores, iou_threshold):
         raise RuntimeError("nms: boxes and scores should have the same dtype")
     src = boxes.device
     dev = src if boxes.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    keep, count = ops.nms_device(boxes.to(dev), scores.to(dev), iou_threshold)
-    return keep[: int(count.item())].to(src)
+    return ops.nms_keep(boxes.to(dev), scores.to(dev), iou_threshold).to(src)
 
 
 def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True, sync=True):
@@ -101,8 +100,7 @@ def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, 
     all_scores = [s[:n] for (_b, s, _c), n in zip(levels, counts)]
     boxes = torch.cat(all_boxes) if all_boxes else torch.zeros((0, 4), dtype=torch.float64, device=device)
     scores = torch.cat(all_scores) if all_scores else torch.zeros(0, dtype=torch.float64, device=device)
-    keep, count = ops.nms_device(boxes, scores, nms_thresh)         # evaluation.py:84
-    keep = keep[: int(count.item())]
+    keep = ops.nms_keep(boxes, scores, nms_thresh)                  # evaluation.py:84
     dets = boxes[keep].cpu().numpy()                                # evaluation.py:85-87
     if return_scores:
         return dets, scores[keep].cpu().numpy()
@@ -110,7 +108,7 @@ def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, 
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU
-def gather_level_candidates(per_level, num_levels, group=None, dst=0):
+def gather_level_candidates(per_level, num_levels, group=None, dst=0, device=None):
     """Scale-sharded inference exchange step.  ``per_level``: {level_index: (boxes [n,4] f64, scores [n] f64)} for
     the pyramid levels this rank evaluated.  Every rank contributes its levels; rank ``dst`` receives all
     candidates concatenated in level order (the reference's ``scales`` order, evaluation.py:78) -- which is what
@@ -119,8 +117,17 @@ def gather_level_candidates(per_level, num_levels, group=None, dst=0):
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
+    # `device`: where this rank's collective buffers live.  A rank that owns no level (more ranks than levels) has no
+    # tensor to infer it from -- under NCCL a CPU tensor there would hang the collective.
     any_t = next(iter(per_level.values()))[0] if per_level else None
-    dev = any_t.device if any_t is not None else torch.device("cpu")
+    if device is not None:
+        dev = torch.device(device)
+    elif any_t is not None:
+        dev = any_t.device
+    elif dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    else:
+        dev = torch.device("cpu")
     counts = torch.zeros(num_levels, dtype=torch.int64, device=dev)
     for lv, (b, _s) in per_level.items():
         counts[lv] = b.shape[0]
@@ -180,8 +187,7 @@ def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thres
         with torch.no_grad():
             output = model(x)
         per_level[i] = decode_level(output, templates, prob_thresh, rf, scale)
-    boxes, scores = gather_level_candidates(per_level, len(levels), group=group, dst=0)
+    boxes, scores = gather_level_candidates(per_level, len(levels), group=group, dst=0, device=device)
     if rank != 0:
         return None
-    keep, count = ops.nms_device(boxes, scores, nms_thresh)
-    return boxes[keep[: int(count.item())]].cpu().numpy()
+    return boxes[ops.nms_keep(boxes, scores, nms_thresh)].cpu().numpy()

@@ -5,6 +5,15 @@ Same constructor, same parameter / buffer names (``state_dict`` is key-compatibl
 NCHW fp32 contract, and it participates in autograd.  The arithmetic, however, never touches torch.nn: the
 whole trunk + heads forward and backward run inside libtinyfaces_b200.so (tcgen05 implicit-GEMM convolutions,
 fused BN / ReLU / residual kernels) through ``tf_model_forward`` / ``tf_model_backward``.  There is no CPU path.
+
+Restrictions that differ from an ordinary nn.Module (both raise instead of computing something wrong):
+  * one grad-enabled forward in flight per model: the backward's saved activations live in the executor's single
+    workspace, so ``backward()`` must run before the next ``forward()`` of the same model;
+  * ``precision``: "fast" (default) = one TF32 tensor-core product per GEMM -- what the reference itself runs on CUDA
+    (torch.backends.cudnn.allow_tf32 defaults to True); measured against the fp32 CPU reference on the conditioned
+    synthetic weights its score map is off by ~5e-3 (max-norm) and its weight gradients by 20-30 % rel-L2 (error
+    amplification of the untrained net).  "parity" = 3xTF32 (fp32-equivalent products): score map within
+    1e-3, ~2x the step time, 2x the activation memory.
 """
 import ctypes
 
@@ -31,6 +40,10 @@ class _Executor:
         self.workspace = None
         self._sizes = {}
         self._out_shapes = {}
+        # Every training forward overwrites the activations / BN statistics / ReLU masks the backward reads (they live in
+        # the ONE workspace).  `generation` counts forwards; an autograd node remembers the generation it belongs to and
+        # refuses to back-propagate through a workspace that a later forward has overwritten.
+        self.generation = 0
 
     def __del__(self):
         try:
@@ -81,8 +94,10 @@ def _run_forward(module, x):
         check(lib().tf_model_output_shape(ex.handle, H, W, ctypes.byref(h3), ctypes.byref(w3)), "tf_model_output_shape")
         shp = ex._out_shapes[key] = (h3.value, w3.value)
     out = torch.empty((B, 5 * module.num_templates, shp[0], shp[1]), dtype=torch.float32, device=x.device)
-    check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, float(module.bn_momentum), out.data_ptr(),
-                                 ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
+    ex.generation += 1
+    with torch.cuda.device(x.device):       # the library creates streams / tensor maps on the CURRENT device
+        check(lib().tf_model_forward(ex.handle, x.data_ptr(), B, H, W, ptrs, int(training), mode, float(module.bn_momentum),
+                                     out.data_ptr(), ws.data_ptr(), ws.numel(), stream_ptr(x.device)), "tf_model_forward")
     if training:
         torch._foreach_add_(module._bn_counters(), 1)        # num_batches_tracked of all 94 BN layers, one launch
     return out
@@ -93,12 +108,19 @@ class _TrunkFunction(torch.autograd.Function):
     def forward(ctx, x, module, *tensors):
         out = _run_forward(module, x)
         ctx.module = module
+        ctx.generation = module._executor.generation
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         module = ctx.module
         ex = module._executor
+        if ctx.generation != ex.generation:
+            raise RuntimeError(
+                "DetectionModel.backward: the forward this graph node belongs to (#%d) is no longer the executor's last "
+                "forward (#%d).  The activations saved for the backward live in ONE workspace that every forward overwrites: "
+                "only one forward may be in flight per model -- call backward() before the next forward() (or use a second "
+                "DetectionModel instance sharing the parameters)." % (ctx.generation, ex.generation))
         grad_out = grad_out.contiguous()
         named = dict(zip(module._tables()[2], module._tables()[1]))
         grads = {}
@@ -111,8 +133,9 @@ class _TrunkFunction(torch.autograd.Function):
                 ptrs[i] = g.data_ptr()
             else:
                 ptrs[i] = None
-        check(lib().tf_model_backward(ex.handle, grad_out.data_ptr(), ptrs, stream_ptr(grad_out.device)),
-              "tf_model_backward")
+        with torch.cuda.device(grad_out.device):
+            check(lib().tf_model_backward(ex.handle, grad_out.data_ptr(), ptrs, stream_ptr(grad_out.device)),
+                  "tf_model_backward")
         out = [None, None]
         for name in module._autograd_names:
             out.append(grads.get(name))

@@ -67,6 +67,7 @@ def _tables(in_size, out_size, device):
     return t
 
 
+@ops._on_tensor_device
 def pyramid_level(img, size, mean, std):
     """img: CUDA float32 [3,H,W] in [0,1]; returns the normalised [1,3,H',W'] level whose shorter side is `size`."""
     _, H, W = img.shape

@@ -89,12 +89,19 @@ class InputPipeline:
         self.tail += 1
 
 
-def train_pipelined(model, loss_fn, optimizer, batches, device, group=None):
+def _meter_value(meter, device):
+    a = getattr(meter, "_average", 0)
+    return a.detach().to(torch.float32) if isinstance(a, torch.Tensor) else torch.tensor(float(a), device=device)
+
+
+def train_pipelined(model, loss_fn, optimizer, batches, device, group=None, with_meters=False):
     """Step loop over an iterable of HOST batches with the copies and the loss read-back taken off the critical path:
     batch i+1 is staged while batch i computes, and the loss of step i is read (from a pinned buffer) only after step
-    i+1 has been enqueued.  Yields one Python float per step, in order."""
+    i+1 has been enqueued.  Yields one Python float per step, in order; with_meters=True yields
+    (loss, class_average, reg_average) -- the running averages AS OF THAT STEP, snapshotted on the device right after it
+    (reading loss_fn.class_average.average from the consumer would see step i+1's update and synchronise on it)."""
     pipe = InputPipeline(device)
-    host_loss = torch.empty(2, dtype=torch.float32).pin_memory()
+    host_loss = torch.empty((2, 3), dtype=torch.float32).pin_memory()
     loss_ready = [None, None]
     it = iter(batches)
     nxt = next(it, None)
@@ -106,7 +113,12 @@ def train_pipelined(model, loss_fn, optimizer, batches, device, group=None):
         x, c, r = pipe.next()
         loss = train_step(model, loss_fn, optimizer, x, c, r, group)
         pipe.release()
-        host_loss[i % 2].copy_(loss.detach(), non_blocking=True)
+        if with_meters:
+            snap = torch.stack([loss.detach().to(torch.float32), _meter_value(loss_fn.class_average, pipe.device),
+                                _meter_value(loss_fn.reg_average, pipe.device)])
+            host_loss[i % 2].copy_(snap, non_blocking=True)
+        else:
+            host_loss[i % 2, 0].copy_(loss.detach(), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(pipe.device))
         loss_ready[i % 2] = ev
@@ -115,12 +127,16 @@ def train_pipelined(model, loss_fn, optimizer, batches, device, group=None):
             pipe.stage(*nxt)                         # overlaps the step just enqueued
         if pending is not None:
             loss_ready[pending % 2].synchronize()
-            yield float(host_loss[pending % 2])
+            yield _emit(host_loss[pending % 2], with_meters)
         pending = i
         i += 1
     if pending is not None:
         loss_ready[pending % 2].synchronize()
-        yield float(host_loss[pending % 2])
+        yield _emit(host_loss[pending % 2], with_meters)
+
+
+def _emit(row, with_meters):
+    return (float(row[0]), float(row[1]), float(row[2])) if with_meters else float(row[0])
 
 
 def train(model, loss_fn, optimizer, dataloader, epoch, device):
@@ -128,5 +144,5 @@ def train(model, loss_fn, optimizer, dataloader, epoch, device):
     model = model.to(device)
     model.train()
     n = len(dataloader)
-    for idx, _ in enumerate(train_pipelined(model, loss_fn, optimizer, dataloader, device)):
-        print_state(idx, epoch, n, loss_fn.class_average.average, loss_fn.reg_average.average)
+    for idx, (_loss, cls_avg, reg_avg) in enumerate(train_pipelined(model, loss_fn, optimizer, dataloader, device, with_meters=True)):
+        print_state(idx, epoch, n, cls_avg, reg_avg)            # the averages as of step idx (trainer.py:89-90)
