@@ -75,6 +75,9 @@ int tf_detloss_fwd_bwd(const float* output, const float* labels, const float* re
 int tf_detloss_sample_workspace_bytes(int B, size_t* bytes_host);
 int tf_detloss_sample_device(float* labels /* [B,L] in place */, int B, int64_t L, int max_pos, int max_neg,
                              uint64_t seed, void* workspace, size_t workspace_bytes, void* stream);
+/* same with a DEVICE draw counter mixed into the seed and incremented by the call (a fresh sample per CUDA-graph replay) */
+int tf_detloss_sample_device_ctr(float* labels, int B, int64_t L, int max_pos, int max_neg, uint64_t seed,
+                                 uint64_t* counter_dev, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- tcgen05 implicit-GEMM convolutions (NHWC fp32 storage, TF32 tensor-core math, fp32 accumulate): the
  * building block behind every nn.Conv2d of tinyfaces/models/model.py:90-106 and its autograd backward.
@@ -157,8 +160,27 @@ int tf_model_workspace_bytes(void* handle, int B, int H, int W, int training, in
 int tf_model_forward(void* handle, const float* x, int B, int H, int W, const void* const* params_host, int training,
                      int mode, float bn_momentum, float* out, void* workspace, size_t workspace_bytes, void* stream);
 int tf_model_backward(void* handle, const float* dout, void* const* grads_host, void* stream);
+/* tf_model_backward + bucket-completion events for an overlapped gradient all-reduce (the reference has no
+ * multi-GPU path, trainer.py:83-87 is the single-device step this extends): events_host[k] (a caller-owned cudaEvent_t) is
+ * recorded as soon as every gradient of the residual blocks with forward index >= event_first_block_host[k] has been
+ * enqueued (blocks 0..29 = layer1.0 .. layer3.22; score_res4 counts as block 29, score_res3 as block 7, the stem as
+ * block -1; first blocks descending).  The events live on an internal stream: wait on them, do not query the caller's. */
+int tf_model_backward_ex(void* handle, const float* dout, void* const* grads_host, int num_events, void* const* events_host,
+                         const int* event_first_block_host, void* stream);
 int tf_model_get_tensor(void* handle, const char* name, float* dst, int64_t capacity, int* shape4_host, void* stream);
 int tf_model_upsample_offdiag(void* handle, float* value_host, void* stream);
+
+/* ---- optimizer step: replaces optimizer.step() + scheduler.step() of tinyfaces/main.py:67-70,81-83 (torch.optim.SGD with
+ * momentum and weight decay over the parameter groups of models/model.py:67-87, StepLR) on FLAT fp32 buffers, one launch per
+ * gradient bucket, stream-ordered behind that bucket's all-reduce:
+ *   g = grad_scale*grad + wd*p;  buf = momentum*buf + g;  p -= lr * (*lr_scale_dev) * buf      (dampening 0, no Nesterov)
+ * n % 4 == 0; segment s = [seg_begin_host[s], seg_begin_host[s+1]) with its own base lr / weight decay (<= 8 segments, begins
+ * multiples of 4); lr_scale_dev (optional DEVICE float) is the StepLR factor, written by tf_steplr_update:
+ *   *epoch_dev += advance;  *lr_scale_dev = gamma ^ (*epoch_dev / step_size). */
+int tf_sgd_step(float* params, const float* grads, float* momentum_buf, int64_t n, int num_segments,
+                const int64_t* seg_begin_host, const float* seg_lr_host, const float* seg_wd_host, float momentum,
+                float grad_scale, const float* lr_scale_dev, void* stream);
+int tf_steplr_update(float* lr_scale_dev, int64_t* epoch_dev, int step_size, float gamma, int advance, void* stream);
 
 #ifdef __cplusplus
 }

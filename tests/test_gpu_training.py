@@ -1,0 +1,199 @@
+"""GPU tests of the training-step machinery added around the executor: the flat parameter / gradient store and its
+bucket events, the library's SGD(+StepLR) kernel against torch.optim.SGD / StepLR (main.py:67-70,81-83), the CUDA-graph
+replay of the whole step against the eager step, the graph-replayed inference forward, and the one-forward-in-flight guard.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(seed=1, precision="fast"):
+    from oracle import synth
+    from tinyfaces_b200.models.model import DetectionModel
+    sd = synth.synthetic_state_dict(seed=seed, bn3_gamma=0.25, beta_jitter=0.1)
+    m = DetectionModel(pretrained_weights=None, num_templates=25)
+    m.load_state_dict(sd)
+    m.precision = precision
+    return m.to(DEV).train()
+
+
+def _batch(B, H, W, seed):
+    from oracle import synth
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, H, W, generator=g)
+    cm, rm = synth.synthetic_targets(B, (H + 7) // 8, (W + 7) // 8, seed=seed, p_neg=0.6, p_pos=0.2)
+    return x.to(DEV), torch.from_numpy(cm).to(DEV), torch.from_numpy(rm).to(DEV)
+
+
+def _maxdiff(a, b):
+    return float((a.double() - b.double()).abs().max())
+
+
+def test_flat_store_layout_and_gradients_equal_autograd_path():
+    from tinyfaces_b200.optim import FlatParams, _block_of
+    x, cm, rm = _batch(2, 64, 96, 3)
+    cot = torch.randn(2, 125, 8, 12, generator=torch.Generator().manual_seed(9)).to(DEV)
+    ref = _model()
+    out = ref(x)
+    (out * cot).sum().backward()
+    ref_grads = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+    m = _model()
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    flat = FlatParams(m, bucket_bytes=8 << 20)
+    # layout: completion order, padded to 4, buckets contiguous, first blocks descending, every trained tensor present
+    blocks = [_block_of(n) for n in flat.names]
+    assert blocks == sorted(blocks, reverse=True) and blocks[0] == 29 and blocks[-1] == -1
+    assert all(o % 4 == 0 for o in flat.offsets) and flat.total % 4 == 0
+    assert flat.buckets[0][0] == 0 and flat.buckets[-1][1] == flat.total and len(flat.buckets) >= 4
+    assert all(a[1] == b[0] for a, b in zip(flat.buckets, flat.buckets[1:]))
+    fb = [b[2] for b in flat.buckets]
+    assert fb == sorted(fb, reverse=True) and fb[-1] == -1
+    assert set(flat.names) == set(ref_grads)
+    for k, p in m.named_parameters():
+        assert torch.equal(p.detach(), before[k])                      # re-pointing kept the values
+    assert flat.is_valid()
+    out2 = m(x)
+    (out2 * cot).sum().backward()
+    torch.cuda.synchronize()
+    for k, p in m.named_parameters():
+        if k in ref_grads:
+            assert p.grad.data_ptr() == flat.flat_grad.data_ptr() + 4 * flat.offsets[flat.names.index(k)]
+            d = _maxdiff(p.grad, ref_grads[k])
+            assert d <= 1e-5 * float(ref_grads[k].abs().max()) + 1e-12, (k, d)     # same kernels: fp32 reduction order only
+        else:
+            assert p.grad is None
+    # a second backward OVERWRITES (zero_grad + backward semantics)
+    out3 = m(x)
+    (out3 * cot).sum().backward()
+    torch.cuda.synchronize()
+    k = "model.layer3.22.conv3.weight"
+    assert _maxdiff(dict(m.named_parameters())[k].grad, ref_grads[k]) <= 1e-5 * float(ref_grads[k].abs().max())
+
+
+def test_flat_sgd_matches_torch_sgd_and_steplr():
+    """3 + 3 steps with momentum 0.9, weight decay 5e-4, the four lr groups of model.py:67-87 and a StepLR(2, 0.1):
+    torch.optim.SGD + StepLR on the autograd path vs tf_sgd_step + tf_steplr_update on the flat path."""
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    from tinyfaces_b200.optim import FlatSGD
+    from tinyfaces_b200.trainer import train_step
+    a, b = _model(), _model()
+    start = {k: p.detach().clone() for k, p in a.named_parameters()}
+    lr = 2e-6
+    oa = torch.optim.SGD(a.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4)
+    sched = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.1)
+    ob = FlatSGD(b, b.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4, bucket_bytes=16 << 20)
+    ca, cb = DetectionCriterion(25, sampler="device", seed=5), DetectionCriterion(25, sampler="device", seed=5)
+    for step in range(5):
+        x, cm, rm = _batch(2, 64, 96, 20 + step)
+        la = train_step(a, ca, oa, x, cm.clone(), rm)
+        lb = train_step(b, cb, ob, x, cm.clone(), rm)
+        assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(la)), (step, float(la), float(lb))
+        sched.step()
+        ob.steplr(2, 0.1)
+    torch.cuda.synchronize()
+    assert abs(float(ob.lr_scale) - 0.01) < 1e-7 and int(ob.epoch) == 5
+    pb = dict(b.named_parameters())
+    for k, p in a.named_parameters():
+        moved = float((p.detach() - start[k]).abs().max())
+        d = _maxdiff(p.detach(), pb[k].detach())
+        assert d <= 2e-3 * moved + 1e-9, (k, d, moved)                 # relative to how far the optimizer moved the tensor
+        if k.startswith("model.fc") or k == "score4_upsample.weight":
+            assert moved == 0.0 and d == 0.0                           # untouched by both (grad None / lr 0)
+    # BN running statistics are not the optimizer's business but must agree too
+    sa, sb = a.state_dict(), b.state_dict()
+    assert _maxdiff(sa["model.layer3.22.bn3.running_var"], sb["model.layer3.22.bn3.running_var"]) <= 1e-5
+
+
+def test_sgd_kernel_against_formula():
+    """tf_sgd_step on raw buffers: segments with their own lr / wd, lr_scale from device memory."""
+    import ctypes
+    from tinyfaces_b200 import _lib
+    n = 4096 + 8
+    g = torch.Generator().manual_seed(0)
+    p = torch.randn(n, generator=g).to(DEV); gr = torch.randn(n, generator=g).to(DEV); m = torch.randn(n, generator=g).to(DEV)
+    p0, m0 = p.double().clone(), m.double().clone()
+    begins = (ctypes.c_int64 * 3)(0, 1000, 4000)
+    lrs = (ctypes.c_float * 3)(0.1, 0.01, 0.0)
+    wds = (ctypes.c_float * 3)(5e-4, 0.0, 1e-2)
+    scale = torch.tensor([0.5], device=DEV)
+    _lib.check(_lib.lib().tf_sgd_step(p.data_ptr(), gr.data_ptr(), m.data_ptr(), n, 3, begins, lrs, wds, 0.9, 1.0, scale.data_ptr(),
+                                      _lib.stream_ptr(torch.device(DEV))), "tf_sgd_step")
+    seg = torch.bucketize(torch.arange(n, device=DEV), torch.tensor([1000, 4000], device=DEV), right=True)
+    lr = torch.tensor([0.1, 0.01, 0.0], dtype=torch.float32).double().to(DEV)[seg] * 0.5
+    wd = torch.tensor([5e-4, 0.0, 1e-2], dtype=torch.float32).double().to(DEV)[seg]
+    mref = 0.9 * m0 + (gr.double() + wd * p0)
+    pref = p0 - lr * mref
+    assert _maxdiff(m, mref) < 1e-6 and _maxdiff(p, pref) < 1e-6
+
+
+def test_graphed_train_step_matches_eager():
+    """warm-up (2 eager steps on batch 0) + capture + replays on batches 1, 2 == eager steps on batches 0, 0, 1, 2: same
+    losses, same parameters, same device-sampler draws (the draw counter lives on the device), meters bumped per replay."""
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    from tinyfaces_b200.optim import FlatSGD
+    from tinyfaces_b200.trainer import GraphedTrainStep, train_step
+    batches = [_batch(2, 64, 96, 40 + i) for i in range(3)]
+    lr = 1e-6
+    a, b = _model(), _model()
+    oa = FlatSGD(a, a.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4)
+    ob = FlatSGD(b, b.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4)
+    ca, cb = DetectionCriterion(25, sampler="device", seed=7), DetectionCriterion(25, sampler="device", seed=7)
+    eager = []
+    for i in (0, 0, 1, 2):
+        x, cm, rm = batches[i]
+        eager.append(float(train_step(a, ca, oa, x, cm.clone(), rm)))
+    x, cm, rm = batches[0]
+    step = GraphedTrainStep(b, cb, ob, x, cm, rm, warmup=2)
+    got = []
+    for i in (1, 2):
+        x, cm, rm = batches[i]
+        got.append(float(step(x, cm, rm)))
+    torch.cuda.synchronize()
+    for e, g_ in zip(eager[2:], got):
+        assert abs(e - g_) <= 1e-4 * abs(e), (eager, got)
+    pb = dict(b.named_parameters())
+    for k in ("model.layer3.22.conv3.weight", "model.conv1.weight", "score_res3.bias", "model.layer1.0.bn1.weight"):
+        pa = dict(a.named_parameters())[k]
+        assert _maxdiff(pa.detach(), pb[k].detach()) <= 1e-5 * float(pa.detach().abs().max()), k
+    assert cb.class_average.num_averaged == ca.class_average.num_averaged == 8
+    assert abs(cb.class_average.average - ca.class_average.average) <= 1e-4 * abs(ca.class_average.average)
+    assert int(cb._draws) == int(ca._draws) == 5
+
+
+def test_inference_graph_replay_matches_eager():
+    from oracle import synth
+    m = _model()
+    sd = synth.calibrate_running_stats(synth.synthetic_state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1),
+                                       torch.randn(2, 3, 96, 136, generator=torch.Generator().manual_seed(4)))
+    m.load_state_dict(sd)
+    m.eval()
+    xs = [torch.randn(1, 3, 200, 216, generator=torch.Generator().manual_seed(i)).to(DEV) for i in range(3)]
+    big = torch.randn(1, 3, 400, 400, generator=torch.Generator().manual_seed(9)).to(DEV)
+    with torch.no_grad():
+        ref = [m(x).clone() for x in xs]
+        ref_big = m(big).clone()
+        m.cuda_graphs = True
+        got = [m(x).clone() for x in xs]                 # first call captures, the others replay
+        got_big = m(big).clone()                         # a second shape: its own graph (and possibly a new workspace)
+        again = m(xs[1]).clone()
+    assert len(m.__dict__["_graphs"]) >= 1
+    for r, g_ in zip(ref, got):
+        assert _maxdiff(r, g_) <= 1e-5 * float(r.abs().max())
+    assert _maxdiff(ref_big, got_big) <= 1e-5 * float(ref_big.abs().max())
+    assert _maxdiff(ref[1], again) <= 1e-5 * float(ref[1].abs().max())
+
+
+def test_second_forward_before_backward_raises():
+    m = _model()
+    x, _, _ = _batch(2, 64, 96, 1)
+    out1 = m(x)
+    out2 = m(x)
+    with pytest.raises(RuntimeError, match="no longer the executor's last forward"):
+        out1.sum().backward()
+    out2.sum().backward()                                # the latest forward is fine
+    assert dict(m.named_parameters())["model.conv1.weight"].grad is not None

@@ -235,12 +235,12 @@ __global__ void __launch_bounds__(32 * FIN_LANES) bn_bwd_finalize_kernel(float* 
     coef[2 * C + c] = (float)(q / (double)M);
 }
 __global__ void __launch_bounds__(32 * FIN_LANES) colsum_finalize_kernel(float* __restrict__ partial, int nblk, int C, int Cout,
-                                       float* __restrict__ out) {
+                                       float* __restrict__ out, int accumulate) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double s, q;
     reduce_partials<false>(partial, nblk, C, c, s, q);
     if (threadIdx.y != 0 || c >= Cout) return;
-    out[c] = (float)s;
+    out[c] = accumulate ? (float)((double)out[c] + s) : (float)s;
 }
 
 // out = act( y*scale + shift (+ res | + res*rscale + rshift) ); optional 1-bit ReLU mask of the result
@@ -538,7 +538,8 @@ __global__ void __launch_bounds__(EW_THREADS) head_combine_fwd_kernel(const floa
 }
 // adjoint, step 1: ds3[b,y,x,c] = dout[b,c,y,x] (padded channels = 0) -- an NCHW -> NHWC transpose through shared memory
 __global__ void __launch_bounds__(EW_THREADS) head_transpose_bwd_kernel(const float* __restrict__ dout, int B, int H3, int W3,
-                                                                        int Cn, int Cp, float* __restrict__ ds3) {
+                                                                        int Cn, int Cp, float* __restrict__ ds3,
+                                                                        float* __restrict__ ds3_lo) {
     extern __shared__ float tile[];                     // [Cp][HEAD_TX + 1]
     const int x0 = blockIdx.x * HEAD_TX, y = blockIdx.y, b = blockIdx.z;
     const int nx = min(HEAD_TX, W3 - x0);
@@ -549,13 +550,17 @@ __global__ void __launch_bounds__(EW_THREADS) head_transpose_bwd_kernel(const fl
     __syncthreads();
     for (int e = threadIdx.x; e < nx * Cp; e += EW_THREADS) {
         const int xl = e / Cp, c = e - xl * Cp;
-        ds3[(((size_t)b * H3 + y) * W3 + x0 + xl) * Cp + c] = tile[c * (HEAD_TX + 1) + xl];
+        const float v = tile[c * (HEAD_TX + 1) + xl];
+        const size_t o = (((size_t)b * H3 + y) * W3 + x0 + xl) * Cp + c;
+        if (ds3_lo) { const float h = hi_part(v); ds3[o] = h; ds3_lo[o] = v - h; }      // parity mode: exact (hi, lo) TF32 split
+        else ds3[o] = v;
     }
 }
 // adjoint, step 2: ds4[b,i,j,c] = sum_{y,x} ds3[b,y,x,c] * up[c][y+1-2i][x+1-2j]   (channel-fastest on both sides)
-__global__ void __launch_bounds__(EW_THREADS) head_upsample_bwd_kernel(const float* __restrict__ ds3, const float* __restrict__ up,
+__global__ void __launch_bounds__(EW_THREADS) head_upsample_bwd_kernel(const float* __restrict__ ds3, const float* __restrict__ ds3_lo,
+                                                                       const float* __restrict__ up,
                                                                        int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
-                                                                       float* __restrict__ ds4) {
+                                                                       float* __restrict__ ds4, float* __restrict__ ds4_lo) {
     const int total = B * H4 * W4 * Cp;
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < total; u += gridDim.x * blockDim.x) {
         const int c = u % Cp, pix = u / Cp;
@@ -570,11 +575,13 @@ __global__ void __launch_bounds__(EW_THREADS) head_upsample_bwd_kernel(const flo
                 for (int kx = 0; kx < 4; ++kx) {
                     const int x = 2 * j - 1 + kx;
                     if (x < 0 || x >= W3) continue;
-                    v += ds3[(((size_t)b * H3 + y) * W3 + x) * Cp + c] * up[c * 16 + ky * 4 + kx];
+                    const size_t o = (((size_t)b * H3 + y) * W3 + x) * Cp + c;
+                    v += (ds3_lo ? ds3[o] + ds3_lo[o] : ds3[o]) * up[c * 16 + ky * 4 + kx];
                 }
             }
         }
-        ds4[u] = v;
+        if (ds4_lo) { const float h = hi_part(v); ds4[u] = h; ds4_lo[u] = v - h; }
+        else ds4[u] = v;
     }
 }
 // up[c][k] = w[c][c][k]  (the ConvTranspose2d weight must be diagonal, model.py:45-65); offdiag = max |off-diagonal|
@@ -671,12 +678,12 @@ int column_stats(const float* y, long long M, int C, float* partial, int* nblk, 
     *nblk = nb;
     return TF_OK;
 }
-int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st) {
+int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st, int accumulate) {
     RC_CARVEOUT(colreduce_kernel<2>); RC_CARVEOUT(colsum_finalize_kernel);
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "column_sum: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0);
-    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out);
+    colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out, accumulate);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -738,12 +745,12 @@ int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, i
     return TF_OK;
 }
 int head_combine_bwd(const float* dout_nchw, const float* up, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
-                     float* ds3, float* ds4, cudaStream_t st) {
+                     float* ds3, float* ds4, cudaStream_t st, float* ds3_lo, float* ds4_lo) {
     TF_REQUIRE(Cp <= HEAD_CMAX && H3 <= 65535 && B <= 65535, "head_combine_bwd: unsupported shape");
     TF_REQUIRE((long long)B * H4 * W4 * Cp < (1ll << 31), "head_combine_bwd: tensor too large");
     const size_t smem = (size_t)Cp * (HEAD_TX + 1) * sizeof(float);
-    head_transpose_bwd_kernel<<<dim3((W3 + HEAD_TX - 1) / HEAD_TX, H3, B), EW_THREADS, smem, st>>>(dout_nchw, B, H3, W3, Cn, Cp, ds3);
-    head_upsample_bwd_kernel<<<ew_blocks((long long)B * H4 * W4 * Cp), EW_THREADS, 0, st>>>(ds3, up, B, H3, W3, H4, W4, Cn, Cp, ds4);
+    head_transpose_bwd_kernel<<<dim3((W3 + HEAD_TX - 1) / HEAD_TX, H3, B), EW_THREADS, smem, st>>>(dout_nchw, B, H3, W3, Cn, Cp, ds3, ds3_lo);
+    head_upsample_bwd_kernel<<<ew_blocks((long long)B * H4 * W4 * Cp), EW_THREADS, 0, st>>>(ds3, ds3_lo, up, B, H3, W3, H4, W4, Cn, Cp, ds4, ds4_lo);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

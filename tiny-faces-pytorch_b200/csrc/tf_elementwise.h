@@ -22,7 +22,7 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask /*
                 float* gmask_out, int mode, float* slots /* [BN_BWD_SLOTS][2][C] zeros, left zeroed */, float* coef, cudaStream_t st);
 // per-channel (sum, sum^2) partials of y[M, C] -> partial[*nblk][2][C] (bn_finalize_train reduces them)
 int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st);
-int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st);
+int column_sum(const float* a, long long M, int C, int Cout, float* out, float* partial, cudaStream_t st, int accumulate = 0);
 int masked_add(const float* a, const float* act, const float* b, long long n, float* out, cudaStream_t st);
 int stem_im2col(const float* x_nchw, int B, int H, int W, int Ho, int Wo, int K_pad, float* col, float* col_lo, int mode,
                 cudaStream_t st);
@@ -42,7 +42,8 @@ int pack_weights_batched(const PackJob* jobs_device, int njobs, long long total,
 int unpack_wgrad(const float* dwp, int O, int I, int taps, int I_pad, float* dw, cudaStream_t st);
 int head_combine_fwd(const float* s3, const float* s4, const float* up, int B, int H3, int W3, int H4, int W4, int Cn,
                      int Cp, float* out_nchw, cudaStream_t st);
+// ds3_lo / ds4_lo (both or neither): parity mode -- the gradients are stored as exact (hi, lo) TF32 splits
 int head_combine_bwd(const float* dout_nchw, const float* up, int B, int H3, int W3, int H4, int W4, int Cn, int Cp,
-                     float* ds3, float* ds4, cudaStream_t st);
+                     float* ds3, float* ds4, cudaStream_t st, float* ds3_lo = nullptr, float* ds4_lo = nullptr);
 int extract_upsample_diag(const float* w, int Cn, float* up, float* offdiag_max, cudaStream_t st);
 }  // namespace tfe

@@ -94,8 +94,9 @@ struct SelState { unsigned int total, bin1, before1, bin2, before2, keep_all; };
 __device__ __forceinline__ int label_class(float y) { return y > 0.f ? 0 : (y < 0.f ? 1 : -1); }
 
 __global__ void samp_hist1_kernel(const float* __restrict__ labels, long long L, unsigned long long seed,
-                                  unsigned int* __restrict__ hist1) {
+                                  const unsigned long long* __restrict__ ctr, unsigned int* __restrict__ hist1) {
     const int b = blockIdx.y;
+    if (ctr) seed += *ctr * 0xD1342543DE82EF95ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
         const int c = label_class(labels[b * L + i]);
         if (c < 0) continue;
@@ -131,8 +132,10 @@ __global__ void __launch_bounds__(1024) samp_find_kernel(const unsigned int* __r
     }
 }
 __global__ void samp_hist2_kernel(const float* __restrict__ labels, long long L, unsigned long long seed,
-                                  const SelState* __restrict__ st, unsigned int* __restrict__ hist2) {
+                                  const unsigned long long* __restrict__ ctr, const SelState* __restrict__ st,
+                                  unsigned int* __restrict__ hist2) {
     const int b = blockIdx.y;
+    if (ctr) seed += *ctr * 0xD1342543DE82EF95ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
         const int c = label_class(labels[b * L + i]);
         if (c < 0) continue;
@@ -143,9 +146,10 @@ __global__ void samp_hist2_kernel(const float* __restrict__ labels, long long L,
     }
 }
 __global__ void samp_apply_kernel(float* __restrict__ labels, long long L, unsigned long long seed,
-                                  const SelState* __restrict__ st, unsigned int* __restrict__ ties,
-                                  unsigned int limit_pos, unsigned int limit_neg) {
+                                  const unsigned long long* __restrict__ ctr, const SelState* __restrict__ st,
+                                  unsigned int* __restrict__ ties, unsigned int limit_pos, unsigned int limit_neg) {
     const int b = blockIdx.y;
+    if (ctr) seed += *ctr * 0xD1342543DE82EF95ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
         const int c = label_class(labels[b * L + i]);
         if (c < 0) continue;
@@ -161,6 +165,8 @@ __global__ void samp_apply_kernel(float* __restrict__ labels, long long L, unsig
         if (!keep) labels[b * L + i] = 0.0f;
     }
 }
+
+__global__ void samp_bump_kernel(unsigned long long* ctr) { *ctr += 1; }
 
 }  // namespace
 
@@ -186,6 +192,9 @@ TF_API int tf_detloss_fwd_bwd(const float* output, const float* labels, const fl
     return TF_OK;
 }
 
+TF_API int tf_detloss_sample_device_ctr(float* labels, int B, int64_t L, int max_pos, int max_neg, uint64_t seed,
+                                        uint64_t* counter_dev, void* workspace, size_t workspace_bytes, void* stream);
+
 TF_API int tf_detloss_sample_workspace_bytes(int B, size_t* bytes) {
     TF_REQUIRE(bytes && B > 0, "tf_detloss_sample_workspace_bytes: bad args");
     *bytes = (size_t)B * 2 * 65536 * 4 * 2 + (size_t)B * 2 * (sizeof(SelState) + 4) + 1024;
@@ -195,6 +204,12 @@ TF_API int tf_detloss_sample_workspace_bytes(int B, size_t* bytes) {
 // labels [B, L] fp32 in {-1,0,+1}, IN PLACE: at most max_pos positives and max_neg negatives survive per image.
 TF_API int tf_detloss_sample_device(float* labels, int B, int64_t L, int max_pos, int max_neg, uint64_t seed,
                                     void* workspace, size_t workspace_bytes, void* stream) {
+    return tf_detloss_sample_device_ctr(labels, B, L, max_pos, max_neg, seed, nullptr, workspace, workspace_bytes, stream);
+}
+// Same, with a DEVICE draw counter: the hash seed is seed + f(*counter_dev) and the call increments the counter, so a
+// captured CUDA graph draws a fresh sample on every replay (a by-value seed would be frozen into the graph).
+TF_API int tf_detloss_sample_device_ctr(float* labels, int B, int64_t L, int max_pos, int max_neg, uint64_t seed,
+                                        uint64_t* counter_dev, void* workspace, size_t workspace_bytes, void* stream) {
     TF_REQUIRE(labels && workspace && B > 0 && L > 0 && max_pos >= 0 && max_neg >= 0, "tf_detloss_sample_device: bad args");
     size_t need;
     tf_detloss_sample_workspace_bytes(B, &need);
@@ -205,13 +220,15 @@ TF_API int tf_detloss_sample_device(float* labels, int B, int64_t L, int max_pos
     unsigned int* hist2 = ar.take<unsigned int>((size_t)B * 2 * 65536);
     SelState* sel = ar.take<SelState>(B * 2);
     unsigned int* ties = ar.take<unsigned int>(B * 2);
+    const unsigned long long* ctr = reinterpret_cast<const unsigned long long*>(counter_dev);
     TF_CHECK_CUDA(cudaMemsetAsync(workspace, 0, need, st));
     dim3 grid((unsigned)std::min<long long>((L + 255) / 256, 592), B);
-    samp_hist1_kernel<<<grid, 256, 0, st>>>(labels, L, seed, hist1);
+    samp_hist1_kernel<<<grid, 256, 0, st>>>(labels, L, seed, ctr, hist1);
     samp_find_kernel<<<B * 2, 1024, 0, st>>>(hist1, sel, max_pos, max_neg, 0);
-    samp_hist2_kernel<<<grid, 256, 0, st>>>(labels, L, seed, sel, hist2);
+    samp_hist2_kernel<<<grid, 256, 0, st>>>(labels, L, seed, ctr, sel, hist2);
     samp_find_kernel<<<B * 2, 1024, 0, st>>>(hist2, sel, max_pos, max_neg, 1);
-    samp_apply_kernel<<<grid, 256, 0, st>>>(labels, L, seed, sel, ties, max_pos, max_neg);
+    samp_apply_kernel<<<grid, 256, 0, st>>>(labels, L, seed, ctr, sel, ties, max_pos, max_neg);
+    if (counter_dev) samp_bump_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(counter_dev));
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

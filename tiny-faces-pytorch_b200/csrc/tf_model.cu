@@ -85,6 +85,9 @@ struct Model {
     int wgrad_mode = 2, chain_priority = 1;
     struct PendingWgrad { tfg::WgradArgs w; size_t dw_elems; int O, I, taps, I_pad; float* gw; };
     std::vector<PendingWgrad> pending;
+    // tf_model_backward_ex: event k is recorded (on the weight-gradient stream) once every gradient of the blocks with index
+    // > bucket_blocks[k] is enqueued -- the caller's collective for that bucket waits on it and overlaps the rest of the backward
+    std::vector<void*> bucket_events; std::vector<int> bucket_blocks;
     size_t bwd_region_bytes = 0;
     int plan_B = 0, plan_H = 0, plan_W = 0, plan_training = -1, plan_mode = 0, plan_epoch = -1; size_t plan_need = 0;   // cached dry run
     bool side_enabled = true;
@@ -113,7 +116,10 @@ struct Model {
         TF_CHECK_CUDA(cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, greatest));
         return TF_OK;
     }
-    ~Model() { destroy_side(); }
+    ~Model() {
+        destroy_side();
+        for (int i = 0; i < TABLE_SLOTS; ++i) if (table_dev[i]) cudaFree(table_dev[i]);
+    }
     // dW (OIHW) = unpack(wgrad(x, dy)) on stream s2 (the side stream, or the chain itself when there is none).
     // A 1x1 convolution's packed gradient [Cout][1][Cin] IS the OIHW tensor: it is accumulated straight into the
     // caller's gradient, no staging buffer / unpack pass.
@@ -200,18 +206,52 @@ struct Model {
         float* wp_lo = mode == 2 ? ar.f(n) : nullptr;
         packed[{c.w, transpose}] = {wp, wp_lo};
         tfe::PackJob j;
+        memset(&j, 0, sizeof(j));                               // (the table is compared bytewise: no stale padding)
         j.src = ar.dry ? nullptr : P(c.w); j.dst = wp; j.dst_lo = wp_lo; j.oscale = oscale;
         j.O_src = c.cout; j.I_src = c.cin; j.taps = taps; j.transpose = transpose; j.O_pad = O_pad; j.I_pad = I_pad;
         j.begin = jobs_total;
         jobs_total += (long long)n;
         jobs.push_back(j);
     }
+    // Job tables (weight packing, eval-mode BN) live in PERSISTENT device slots with a host mirror: a forward whose table
+    // equals the cached one -- every step after the first for a given shape / parameter set -- uploads nothing.  That
+    // removes three small H2D copies per step and makes the call graph-capturable (a copy from pageable host memory
+    // cannot be captured); a table that differs DURING capture is an error: run one eager step first.
+    static constexpr int TABLE_SLOTS = 4, TABLE_BYTES = 24576;
+    char* table_dev[TABLE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<char> table_host[TABLE_SLOTS];
+    int table_dev_id = -1;
+    int table_slot = 0;
+    int upload_table(const void* src, size_t bytes, cudaStream_t st, const void** dev_out) {
+        TF_REQUIRE(table_slot < TABLE_SLOTS && bytes <= (size_t)TABLE_BYTES, "job table too large (%zu bytes, slot %d)", bytes, table_slot);
+        int dev = 0;
+        TF_CHECK_CUDA(cudaGetDevice(&dev));
+        if (table_dev_id != dev) {
+            for (int i = 0; i < TABLE_SLOTS; ++i) { if (table_dev[i]) cudaFree(table_dev[i]); table_dev[i] = nullptr; table_host[i].clear(); }
+            table_dev_id = dev;
+        }
+        const int k = table_slot++;
+        if (!table_dev[k]) TF_CHECK_CUDA(cudaMalloc(&table_dev[k], TABLE_BYTES));
+        std::vector<char>& h = table_host[k];
+        if (h.size() != bytes || memcmp(h.data(), src, bytes) != 0) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            TF_CHECK_CUDA(cudaStreamIsCapturing(st, &cs));
+            TF_REQUIRE(cs == cudaStreamCaptureStatusNone, "tf_model: the job tables changed during stream capture -- run one eager call with the same shape / parameters first");
+            // Stream-ordered overwrite: every earlier reader of this slot ran on `st` or on a stream `st` has since joined
+            // (forward: ev_pack), and the side stream is forked from `st` before it uploads.  The source is pageable, so
+            // the runtime stages it before returning -- `src` may be reused immediately.
+            TF_CHECK_CUDA(cudaMemcpyAsync(table_dev[k], src, bytes, cudaMemcpyHostToDevice, st));
+            h.assign(reinterpret_cast<const char*>(src), reinterpret_cast<const char*>(src) + bytes);
+        }
+        *dev_out = table_dev[k];
+        return TF_OK;
+    }
     int prepack_flush(cudaStream_t st) {
         const size_t bytes = jobs.size() * sizeof(tfe::PackJob);
-        tfe::PackJob* dev = reinterpret_cast<tfe::PackJob*>(ar.f((bytes + 3) / 4 + 16));
         if (!ar.dry && !jobs.empty()) {
-            TF_CHECK_CUDA(cudaMemcpyAsync(dev, jobs.data(), bytes, cudaMemcpyHostToDevice, st));
-            RC(tfe::pack_weights_batched(dev, (int)jobs.size(), jobs_total, mode, st));
+            const void* dev = nullptr;
+            RC(upload_table(jobs.data(), bytes, st, &dev));
+            RC(tfe::pack_weights_batched(reinterpret_cast<const tfe::PackJob*>(dev), (int)jobs.size(), jobs_total, mode, st));
         }
         jobs.clear(); jobs_total = 0;
         return TF_OK;
@@ -272,6 +312,7 @@ struct Model {
             float* sc = ar.f(b.C); float* sh = ar.f(b.C);
             eval_ss[b.gamma] = {sc, sh};
             tfe::BnEvalJob j;
+            memset(&j, 0, sizeof(j));
             j.gamma = ar.dry ? nullptr : P(b.gamma); j.beta = ar.dry ? nullptr : P(b.beta);
             j.run_mean = ar.dry ? nullptr : P(b.rm); j.run_var = ar.dry ? nullptr : P(b.rv);
             j.scale = sc; j.shift = sh; j.begin = total;
@@ -281,10 +322,10 @@ struct Model {
         add(stem_bn);
         for (const BlockP& bp : blocks) { add(bp.b1); add(bp.b2); add(bp.b3); if (bp.has_ds) add(bp.bd); }
         const size_t bytes = ej.size() * sizeof(tfe::BnEvalJob);
-        tfe::BnEvalJob* dev = reinterpret_cast<tfe::BnEvalJob*>(ar.f((bytes + 3) / 4 + 16));
         if (!ar.dry) {
-            TF_CHECK_CUDA(cudaMemcpyAsync(dev, ej.data(), bytes, cudaMemcpyHostToDevice, st));
-            RC(tfe::bn_scale_shift_eval_batched(dev, (int)ej.size(), total, eps, st));
+            const void* dev = nullptr;
+            RC(upload_table(ej.data(), bytes, st, &dev));
+            RC(tfe::bn_scale_shift_eval_batched(reinterpret_cast<const tfe::BnEvalJob*>(dev), (int)ej.size(), total, eps, st));
         }
         return TF_OK;
     }
@@ -380,6 +421,7 @@ struct Model {
         return prepack_flush(st);
     }
     int forward(const float* x_nchw, float* out_nchw, cudaStream_t st) {
+        table_slot = 0;
         H2 = (H - 1) / 2 + 1; W2 = (W - 1) / 2 + 1;
         Hp = (H2 - 1) / 2 + 1; Wp = (W2 - 1) / 2 + 1;
         partial = ar.f((size_t)tfe::COLREDUCE_MAX_BLOCKS * 2 * 2 * 1024);   // main + tail-launch statistics rows
@@ -637,6 +679,8 @@ struct Model {
         ar.off = fwd_mark;
         if (!ar.dry) RC(ensure_side());
         pending.clear();
+        bool region_recorded[2] = {false, false};     // (waiting on a previous call's event is pointless and breaks stream capture)
+        size_t next_event = 0;
         // experiment switches: tf_debug_set(5, 1 + mode) picks the weight-gradient schedule, tf_debug_set(6, 1) keeps the
         // chain on the caller's stream (no priority)
         wgrad_mode = tfg::debug_flag(5) ? tfg::debug_flag(5) - 1 : 2;
@@ -650,21 +694,25 @@ struct Model {
         }
         const long long M3 = (long long)B * H3 * W3, M4 = (long long)B * H4 * W4;
         float* ds3 = ar.f((size_t)M3 * Cp); float* ds4 = ar.f((size_t)M4 * Cp);
+        // parity mode: the head gradients are exact (hi, lo) splits too, so that the head dgrad / wgrad GEMMs run the same
+        // 3xTF32 products as the trunk (round 1 fed them single TF32 operands: 5e-4 on every gradient below the heads)
+        float* ds3_lo = mode == 2 ? ar.f((size_t)M3 * Cp) : nullptr; float* ds4_lo = mode == 2 ? ar.f((size_t)M4 * Cp) : nullptr;
         if (!ar.dry) {
             TF_CHECK_CUDA(cudaMemsetAsync(bwd_slots, 0, (size_t)tfe::BN_BWD_SLOTS * 2 * 1024 * sizeof(float), st));   // every BN backward leaves it zeroed
-            RC(tfe::head_combine_bwd(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4, st));
-            if (G(grads, s3_b)) RC(tfe::column_sum(ds3, M3, Cp, Cn, G(grads, s3_b), partial, st));
-            if (G(grads, s4_b)) RC(tfe::column_sum(ds4, M4, Cp, Cn, G(grads, s4_b), partial, st));
+            RC(tfe::head_combine_bwd(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4, st, ds3_lo, ds4_lo));
+            // bias gradients: column sums of hi (+ lo): the lo parts are ~2^-12 of hi, their sum is added by a second pass
+            if (G(grads, s3_b)) RC(bias_grad(ds3, ds3_lo, M3, G(grads, s3_b), st));
+            if (G(grads, s4_b)) RC(bias_grad(ds4, ds4_lo, M4, G(grads, s4_b), st));
         }
         // head weight gradients and input gradients (as 1x1 "units" with padded Cout)
-        Unit h3; h3.c.w = s3_w; h3.c.cin = 512; h3.c.cout = Cp; h3.c.k = 1; h3.x = res3; h3.x_lo = nullptr; h3.B = B; h3.H = H3; h3.W = W3; h3.Ho = H3; h3.Wo = W3;
-        Unit h4 = h3; h4.c.w = s4_w; h4.c.cin = 1024; h4.x = res4; h4.H = H4; h4.W = W4; h4.Ho = H4; h4.Wo = W4;
+        Unit h3; h3.c.w = s3_w; h3.c.cin = 512; h3.c.cout = Cp; h3.c.k = 1; h3.x = res3; h3.x_lo = res3_lo; h3.B = B; h3.H = H3; h3.W = W3; h3.Ho = H3; h3.Wo = W3;
+        Unit h4 = h3; h4.c.w = s4_w; h4.c.cin = 1024; h4.x = res4; h4.x_lo = res4_lo; h4.H = H4; h4.W = W4; h4.Ho = H4; h4.Wo = W4;
         float* dres4 = ar.f((size_t)M4 * 1024);
         // input gradients ping-pong between two buffers; one scratch region is reused by every other block
         size_t mx = 0;
         for (const BlockS& s : bs) mx = std::max(mx, (size_t)s.B * s.H * s.W * s.u1.c.cin);
         float* dxbuf[2] = {ar.f(mx), ar.f(mx)};
-        RC(head_bwd(h4, ds4, dres4, 0, grads, st));
+        RC(head_bwd(h4, ds4, ds4_lo, dres4, 0, grads, st));
         const size_t scratch_mark = ar.off;
         // Two scratch regions alternate between blocks: the side stream may still be reading block i's dy tensors
         // (weight gradients) while the chain already works on block i-1 (and, with deferred weight gradients, i-2 has
@@ -680,13 +728,19 @@ struct Model {
             if (!ar.dry && side) {
                 // deferred weight gradients of block i+1 (other region): start them now, next to this block's bn3 backward
                 RC(wgrad_flush(st));
-                if (wgrad_mode == 2) TF_CHECK_CUDA(cudaEventRecord(ev_region[r ^ 1], side));
-                TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[r], 0));
+                // bucket events (tf_model_backward_ex): every weight / BN gradient of the blocks > i is now enqueued
+                while (next_event < bucket_events.size() && bucket_blocks[next_event] >= i) {
+                    if (wgrad_mode != 2) break;          // (the other schedules have no per-block flush points)
+                    TF_CHECK_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[next_event], side));
+                    ++next_event;
+                }
+                if (wgrad_mode == 2) { TF_CHECK_CUDA(cudaEventRecord(ev_region[r ^ 1], side)); region_recorded[r ^ 1] = true; }
+                if (region_recorded[r]) TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_region[r], 0));
             }
             float* dx = dxbuf[i & 1];
             RC(block_backward(s, dcur, dx, grads, st));
-            if (i == 7) RC(head_bwd(h3, ds3, dx, 1, grads, st));   // res3 also feeds score_res3: dx(block 7 input) += head dgrad
-            if (!ar.dry && side && wgrad_mode != 2) TF_CHECK_CUDA(cudaEventRecord(ev_region[r], side));
+            if (i == 7) RC(head_bwd(h3, ds3, ds3_lo, dx, 1, grads, st));   // res3 also feeds score_res3: dx(block 7 input) += head dgrad
+            if (!ar.dry && side && wgrad_mode != 2) { TF_CHECK_CUDA(cudaEventRecord(ev_region[r], side)); region_recorded[r] = true; }
             max_used = std::max(max_used, ar.off - (scratch_mark + (size_t)r * region));
             dcur = dx;
         }
@@ -711,22 +765,33 @@ struct Model {
         }
         if (!ar.dry && side) {                       // join: the caller's stream sees every gradient
             RC(wgrad_flush(st));
+            for (; next_event < bucket_events.size(); ++next_event)       // remaining buckets (layer 1, stem): complete here
+                TF_CHECK_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[next_event], side));
             TF_CHECK_CUDA(cudaEventRecord(ev_join, side));
             TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
             if (st != caller) {
                 TF_CHECK_CUDA(cudaEventRecord(ev_chain[1], st));
                 TF_CHECK_CUDA(cudaStreamWaitEvent(caller, ev_chain[1], 0));
             }
+        } else if (!ar.dry) {
+            for (; next_event < bucket_events.size(); ++next_event) TF_CHECK_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[next_event], st));
         }
         return TF_OK;
     }
+    // bias gradient of a head: column sums of ds (hi) and, in parity mode, of its lo part added on top
+    int bias_grad(const float* ds, const float* ds_lo, long long M, float* gb, cudaStream_t st) {
+        RC(tfe::column_sum(ds, M, Cp, Cn, gb, partial, st));
+        if (ds_lo) RC(tfe::column_sum(ds_lo, M, Cp, Cn, gb, partial, st, 1));
+        return TF_OK;
+    }
     // head (score_res3 / score_res4) backward: weight gradient [Cn, Cin] and dres (+)= ds * W
-    int head_bwd(const Unit& h, const float* ds, float* dres, int accumulate, void* const* grads, cudaStream_t st) {
+    int head_bwd(const Unit& h, const float* ds, const float* ds_lo, float* dres, int accumulate, void* const* grads, cudaStream_t st) {
         const ConvP& c = h.c;
         float* gw = G(grads, c.w);
         if (gw && !ar.dry) {
             tfg::WgradArgs w = {};
             w.x = h.x; w.dy = ds; w.B = h.B; w.H = h.H; w.W = h.W; w.Cin = c.cin; w.Cout = Cp; w.ksize = 1;
+            if (h.x_lo && ds_lo) { w.x_lo = h.x_lo; w.dy_lo = ds_lo; }
             RC(wgrad_async(w, (size_t)Cp * c.cin, Cn, c.cin, 1, c.cin, gw, st));
         }
         float *wt, *wt_lo;
@@ -734,12 +799,16 @@ struct Model {
         RC(pack(ct, c.cin, Cp, 1, &wt, &wt_lo, st));                 // [Cin][1][Cp], columns >= Cn are zero
         tfg::ConvArgs a = {};
         a.x = ds; a.B = h.B; a.H = h.H; a.W = h.W; a.Cin = Cp; a.w = wt; a.Cout = c.cin; a.ksize = 1; a.y = dres; a.accumulate = accumulate;
+        if (ds_lo && wt_lo) { a.x_lo = ds_lo; a.w_lo = wt_lo; }
         if (!ar.dry) RC(tfg::conv_fprop(a, st));
         return TF_OK;
     }
 };
 
 }  // namespace
+
+TF_API int tf_model_backward_ex(void* handle, const float* dout, void* const* grads, int num_events, void* const* events,
+                                const int* event_first_block, void* stream);
 
 TF_API int tf_model_create(int num_templates, void** handle) {
     TF_REQUIRE(handle && num_templates > 0 && num_templates <= 32, "tf_model_create: bad args");
@@ -796,10 +865,28 @@ TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, c
 // dout: [B,5T,H3,W3] NCHW.  grads: num_params device pointers (null = not wanted); conv / head weights in OIHW,
 // BN gamma/beta, head biases.  Must follow a training forward on the same workspace.
 TF_API int tf_model_backward(void* handle, const float* dout, void* const* grads, void* stream) {
+    return tf_model_backward_ex(handle, dout, grads, 0, nullptr, nullptr, stream);
+}
+// tf_model_backward that also records `num_events` caller-owned cudaEvent_t's while the backward is being enqueued: event k is
+// recorded as soon as every gradient (conv weights, BN gamma / beta, head weights / biases) of the residual blocks with forward
+// index >= event_first_block[k] has been enqueued (blocks 0..29 = layer1.0 .. layer3.22; score_res4 counts as block 29, score_res3 as block 7, the
+// stem as block -1; event_first_block must be descending).  A gradient all-reduce bucket that waits on event k therefore
+// overlaps the rest of the backward.  Events with first_block <= 0 complete at the end.
+TF_API int tf_model_backward_ex(void* handle, const float* dout, void* const* grads, int num_events, void* const* events,
+                                const int* event_first_block, void* stream) {
     TF_REQUIRE(handle && dout && grads, "tf_model_backward: null pointer");
+    TF_REQUIRE(num_events >= 0 && num_events <= 64 && (num_events == 0 || (events && event_first_block)), "tf_model_backward_ex: bad events");
     Model* m = reinterpret_cast<Model*>(handle);
     TF_REQUIRE(!m->ar.dry && m->ar.base, "tf_model_backward: no forward state");
-    return m->backward(dout, grads, (cudaStream_t)stream);
+    m->bucket_events.clear(); m->bucket_blocks.clear();
+    for (int k = 0; k < num_events; ++k) {
+        TF_REQUIRE(events[k] && (k == 0 || event_first_block[k] <= event_first_block[k - 1]), "tf_model_backward_ex: events must be non-null, first blocks descending");
+        m->bucket_events.push_back(events[k]);
+        m->bucket_blocks.push_back(event_first_block[k] - 1);        // recorded when the loop reaches block index first_block - 1
+    }
+    const int rc = m->backward(dout, grads, (cudaStream_t)stream);
+    m->bucket_events.clear(); m->bucket_blocks.clear();
+    return rc;
 }
 // Debug / test hook: locate an internal NHWC activation of the last forward ("stem", "pool", "block<i>.out",
 // "block<i>.u<1|2|3|d>.<y|a>") and copy it (device to device) into dst (capacity in floats).

@@ -31,6 +31,7 @@ _SIGS = {
     "tf_detloss_fwd_bwd": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_f32, c_vp, c_vp, c_vp]),
     "tf_detloss_sample_workspace_bytes": (c_i32, [c_i32, ctypes.POINTER(c_sz)]),
     "tf_detloss_sample_device": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i32, c_u64, c_vp, c_sz, c_vp]),
+    "tf_detloss_sample_device_ctr": (c_i32, [c_vp, c_i32, c_i64, c_i32, c_i32, c_u64, c_vp, c_vp, c_sz, c_vp]),
     "tf_model_create": (c_i32, [c_i32, ctypes.POINTER(c_vp)]),
     "tf_model_destroy": (c_i32, [c_vp]),
     "tf_model_num_params": (c_i32, [c_vp]),
@@ -40,8 +41,12 @@ _SIGS = {
     "tf_model_forward": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(c_vp), c_i32, c_i32, c_f32, c_vp, c_vp,
                                  c_sz, c_vp]),
     "tf_model_backward": (c_i32, [c_vp, c_vp, ctypes.POINTER(c_vp), c_vp]),
+    "tf_model_backward_ex": (c_i32, [c_vp, c_vp, ctypes.POINTER(c_vp), c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_i32), c_vp]),
     "tf_model_get_tensor": (c_i32, [c_vp, ctypes.c_char_p, c_vp, c_i64, ctypes.POINTER(c_i32), c_vp]),
     "tf_model_upsample_offdiag": (c_i32, [c_vp, ctypes.POINTER(c_f32), c_vp]),
+    "tf_sgd_step": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(c_i64), ctypes.POINTER(c_f32), ctypes.POINTER(c_f32),
+                            c_f32, c_f32, c_vp, c_vp]),
+    "tf_steplr_update": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_i32, c_vp]),
     "tf_pyramid_workspace_bytes": (c_i32, [c_i32, c_i32, c_i32, ctypes.POINTER(c_sz)]),
     "tf_pyramid_level": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_i32,
                                  ctypes.POINTER(c_f32), ctypes.POINTER(c_f32), c_vp, c_vp, c_sz, c_vp]),

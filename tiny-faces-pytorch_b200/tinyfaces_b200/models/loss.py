@@ -15,17 +15,30 @@ from .utils import balance_sampling
 
 
 class AvgMeter:
-    """loss.py:7-21 with the accumulation kept on the device: reading ``average`` is the only sync point."""
+    """loss.py:7-21 with the accumulation kept on the device (a running SUM updated in place, so that it also works
+    inside a captured CUDA graph -- the replay driver only bumps ``num_averaged``); reading ``average`` is the only
+    sync point."""
 
     def __init__(self):
         self.reset()
 
     def update(self, loss, size):
-        n = self.num_averaged
-        m = n + size
-        loss = loss.detach() if isinstance(loss, torch.Tensor) else loss
-        self._average = ((n * self._average) + loss) / m
-        self.num_averaged = m
+        if isinstance(loss, torch.Tensor):
+            loss = loss.detach()
+            if not isinstance(self._sum, torch.Tensor) or self._sum.device != loss.device:
+                prev = float(self._sum) if self._sum is not None else 0.0
+                self._sum = torch.full((), prev, dtype=torch.float64, device=loss.device)
+            self._sum.add_(loss * size)
+        else:
+            self._sum = (self._sum if self._sum is not None else 0.0) + loss * size
+        self.num_averaged += size
+
+    @property
+    def _average(self):
+        """running average = sum(loss_i * size_i) / sum(size_i) (algebraically the reference's recurrence)"""
+        if self._sum is None or self.num_averaged == 0:
+            return 0
+        return self._sum / self.num_averaged
 
     @property
     def average(self):
@@ -33,7 +46,10 @@ class AvgMeter:
         return float(a) if isinstance(a, torch.Tensor) else a
 
     def reset(self):
-        self._average = 0
+        if getattr(self, "_sum", None) is not None and isinstance(self._sum, torch.Tensor):
+            self._sum.zero_()                    # keep the tensor: a captured graph holds its address
+        else:
+            self._sum = None
         self.num_averaged = 0
 
 
@@ -66,7 +82,7 @@ class DetectionCriterion(nn.Module):
         self.sampler = sampler
         self.sample_size = sample_size
         self._seed = seed
-        self._step = 0
+        self._draws = None                  # device draw counter of the device sampler (a fresh sample per call / graph replay)
         self.class_average = AvgMeter()
         self.reg_average = AvgMeter()
         self.masked_class_loss = None       # 0-dim tensors: the masked SUMS (the reference's per-element maps are
@@ -90,8 +106,9 @@ class DetectionCriterion(nn.Module):
         lab = class_map.clone()
         max_pos = int(self.sample_size * self.pos_fraction)
         max_neg = int(max_pos * (1 - self.pos_fraction) / self.pos_fraction)
-        self._step += 1
-        ops.detloss_sample_device_(lab, max_pos, max_neg, seed=(self._seed << 32) + self._step)
+        if self._draws is None or self._draws.device != lab.device:
+            self._draws = torch.ones(1, dtype=torch.int64, device=lab.device)
+        ops.detloss_sample_device_(lab, max_pos, max_neg, seed=self._seed << 32, counter=self._draws)
         return lab
 
     def forward(self, output, class_map, regression_map):

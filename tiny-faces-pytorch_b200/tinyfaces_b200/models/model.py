@@ -84,8 +84,13 @@ def _run_forward(module, x):
                 raise RuntimeError("DetectionModel parameters must be contiguous float32 tensors on the input's device")
         # the ctypes pointer table of the ~570 parameters / buffers costs ~0.3 ms to build: once per parameter set
         # (optimizers update parameters in place, so the addresses are stable; _apply() drops the cache)
+        flat = module.__dict__.get("_flat")
+        if flat is not None and not flat.is_valid():
+            raise RuntimeError("DetectionModel: the parameters were moved / re-allocated after the flat parameter store "
+                               "(tinyfaces_b200.optim.FlatParams / FlatSGD) was built -- build the optimizer after model.to(device)")
         ptrs = (ctypes.c_void_p * len(table))(*[t.data_ptr() for t in table])
         cached = module.__dict__["_ptr_table"] = (table, x.device, ptrs)
+        module.__dict__.pop("_graphs", None)             # captured inference graphs hold the old parameter addresses
     ptrs = cached[2]
     key = (H, W)
     shp = ex._out_shapes.get(key)
@@ -122,6 +127,21 @@ class _TrunkFunction(torch.autograd.Function):
                 "only one forward may be in flight per model -- call backward() before the next forward() (or use a second "
                 "DetectionModel instance sharing the parameters)." % (ctx.generation, ex.generation))
         grad_out = grad_out.contiguous()
+        flat = module.__dict__.get("_flat")
+        if flat is not None:
+            # flat-gradient fast path (tinyfaces_b200.optim.FlatParams): the library writes every gradient straight into the
+            # persistent flat buffer the .grad tensors view (OVERWRITING: zero_grad() + backward() semantics) and records the
+            # bucket events the overlapped all-reduce / SGD pipeline waits on
+            table = module.__dict__.get("_flat_grad_table")
+            if table is None or table[0] is not flat:
+                table = module.__dict__["_flat_grad_table"] = (flat, flat.grad_pointer_table(ex.names))
+            with torch.cuda.device(grad_out.device):
+                check(lib().tf_model_backward_ex(ex.handle, grad_out.data_ptr(), table[1], len(flat.events), flat._ev_ptrs,
+                                                 flat._ev_blocks, stream_ptr(grad_out.device)), "tf_model_backward_ex")
+            for p, g in zip(flat.params, flat.grad_views):
+                if p.grad is not g:
+                    p.grad = g
+            return (None, None) + (None,) * len(module._autograd_names)
         named = dict(zip(module._tables()[2], module._tables()[1]))
         grads = {}
         ptrs = (ctypes.c_void_p * len(ex.names))()
@@ -160,6 +180,8 @@ class DetectionModel(nn.Module):
         self._init_bilinear()
         self.precision = "fast"
         self.bn_momentum = 0.1                                # nn.BatchNorm2d default
+        self.cuda_graphs = False                              # eval / no_grad forwards of small inputs replay a captured CUDA graph
+        self.cuda_graph_max_pixels = 1300 * 1300              # (larger levels are not launch-bound)
         self._executor_obj = None
         self._checked_upsample = False
 
@@ -192,6 +214,7 @@ class DetectionModel(nn.Module):
         self.__dict__.pop("_cache", None)
         self.__dict__.pop("_bn_cnt", None)
         self.__dict__.pop("_ptr_table", None)
+        self.__dict__.pop("_graphs", None)
         return super()._apply(fn, *args, **kwargs)
 
     def _bn_counters(self):
@@ -233,9 +256,39 @@ class DetectionModel(nn.Module):
               "tf_model_get_tensor")
         return t
 
+    def _graph_forward(self, x):
+        """Inference forward replayed from a CUDA graph captured per (input shape, precision, workspace): the small pyramid
+        levels are launch-bound (~300 launches for < 1 ms of GPU work).  The returned tensor is the graph's static output:
+        valid until the next forward of the same shape (get_detections consumes it, stream-ordered, before that)."""
+        ex = self._executor
+        graphs = self.__dict__.setdefault("_graphs", {})
+        ws = ex.workspace
+        key = (tuple(x.shape), self.precision, ws.data_ptr() if ws is not None else 0, x.device.index)
+        g = graphs.get(key)
+        if g is None:
+            static_x = x.detach().clone().contiguous()
+            _run_forward(self, static_x)                                  # eager: sizes the workspace, fills the library's caches
+            ws = ex.workspace
+            key = (tuple(x.shape), self.precision, ws.data_ptr(), x.device.index)
+            for k in [k for k in graphs if k[2] != ws.data_ptr()]:        # graphs captured on a workspace that has been replaced
+                del graphs[k]
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                static_out = _run_forward(self, static_x)
+            g = graphs[key] = (graph, static_x, static_out)
+        graph, static_x, static_out = g
+        static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        ex.generation += 1
+        return static_out
+
     def forward(self, x):
         if torch.is_grad_enabled():
             out = _TrunkFunction.apply(x, self, *self._tables()[1])
+        elif (self.cuda_graphs and not self.training and x.is_cuda and self._checked_upsample
+              and x.shape[0] * x.shape[2] * x.shape[3] <= self.cuda_graph_max_pixels):
+            out = self._graph_forward(x)
         else:
             out = _run_forward(self, x)      # torch.no_grad(): skip autograd.Function.apply over ~300 parameter tensors
         if not self._checked_upsample:

@@ -151,16 +151,17 @@ def detloss_fwd_bwd(output, labels, regression_map, reg_weight=1.0):
 
 
 @_on_tensor_device
-def detloss_sample_device_(labels, max_pos, max_neg, seed):
-    """In-place device balance sampler on labels [B,T,H,W]."""
+def detloss_sample_device_(labels, max_pos, max_neg, seed, counter=None):
+    """In-place device balance sampler on labels [B,T,H,W].  counter: optional device int64 [1] draw counter (mixed into
+    the seed, incremented by the call)."""
     require_cuda(labels, "labels")
     B = labels.shape[0]
     L = labels[0].numel()
     sz = ctypes.c_size_t()
     check(lib().tf_detloss_sample_workspace_bytes(B, ctypes.byref(sz)), "tf_detloss_sample_workspace_bytes")
     ws = _workspace(labels.device, sz.value)
-    check(lib().tf_detloss_sample_device(ptr(labels), B, L, int(max_pos), int(max_neg), int(seed) & (2**64 - 1),
-                                         ptr(ws), ws.numel(), stream_ptr(labels.device)), "tf_detloss_sample_device")
+    check(lib().tf_detloss_sample_device_ctr(ptr(labels), B, L, int(max_pos), int(max_neg), int(seed) & (2**64 - 1), ptr(counter),
+                                             ptr(ws), ws.numel(), stream_ptr(labels.device)), "tf_detloss_sample_device")
     return labels
 
 

@@ -1,9 +1,12 @@
-"""train -- drop-in for /root/reference/tinyfaces/trainer.py:68-90 (the step loop), plus the data-parallel
-pieces the reference does not have: one process per GPU, batch-sharded, gradients SUM-reduced over NCCL
-(the reference loss is a sum, loss.py:87-88, so the reduction must not divide).
+"""train -- drop-in for /root/reference/tinyfaces/trainer.py:68-90 (the step loop), plus what the reference does not
+have: the data-parallel step (one process per GPU, batch-sharded, gradients SUM-reduced over NCCL -- the reference loss
+is a sum, loss.py:87-88, so the reduction must not divide), the overlapped bucket pipeline (optim.reduce_and_step) and
+a CUDA-graph replay of the whole step (GraphedTrainStep: ~900 launches per step collapse into one graph launch).
 """
 import torch
 import torch.distributed as dist
+
+from .optim import FlatSGD, reduce_and_step
 
 
 def print_state(idx, epoch, size, loss_cls, loss_reg):
@@ -12,7 +15,8 @@ def print_state(idx, epoch, size, loss_cls, loss_reg):
 
 
 def allreduce_gradients(parameters, group=None):
-    """SUM all-reduce of every existing .grad as ONE flat fp32 buffer (110.9 MB for the trunk + heads)."""
+    """SUM all-reduce of every existing .grad as ONE flat fp32 buffer (fallback for a plain torch optimizer; with FlatSGD
+    the gradients already live in one buffer and are reduced bucket by bucket DURING the backward)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     grads = [p.grad for p in parameters if p.grad is not None]
@@ -25,18 +29,68 @@ def allreduce_gradients(parameters, group=None):
         n = g.numel()
         views.append(flat[off:off + n].view_as(g))
         off += n
-    torch._foreach_copy_(grads, views)        # one multi-tensor launch instead of ~300 small copies (1 ms per step at N > 1)
+    torch._foreach_copy_(grads, views)        # one multi-tensor launch instead of ~300 small copies
 
 
 def train_step(model, loss_fn, optimizer, img, class_map, regression_map, group=None):
-    """One forward / loss / backward / (all-reduce) / SGD step on tensors already on the device."""
+    """One forward / loss / backward / all-reduce / SGD step on tensors already on the device (trainer.py:78-87).
+    With a FlatSGD optimizer the all-reduce and the optimizer run per gradient bucket on a communication stream while the
+    backward is still producing the earlier layers' gradients."""
     output = model(img)
     loss = loss_fn(output, class_map, regression_map)
     optimizer.zero_grad()
     loss.backward()
-    allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]], group)
-    optimizer.step()
+    if isinstance(optimizer, FlatSGD):
+        reduce_and_step(optimizer, group)
+    else:
+        allreduce_gradients([p for g in optimizer.param_groups for p in g["params"]], group)
+        optimizer.step()
     return loss
+
+
+class GraphedTrainStep:
+    """The whole training step (forward, loss incl. OHEM + device sampler, backward, bucketed all-reduce, SGD) captured
+    ONCE into a CUDA graph and replayed per batch: the ~900 kernel launches (and their ~2 ms of host + launch-gap time,
+    which is most of a step at the small per-GPU batch of BASELINE configs[3]) become one graph launch.
+
+    Requirements: static shapes, ``DetectionCriterion(sampler="device")``, a FlatSGD optimizer whose schedule lives on the
+    device (``optimizer.steplr``), and ``warmup`` eager steps first (they size the workspace and fill the library's caches;
+    they are real optimizer steps on the given batch)."""
+
+    def __init__(self, model, loss_fn, optimizer, img, class_map, regression_map, group=None, warmup=2):
+        if not isinstance(optimizer, FlatSGD):
+            raise RuntimeError("GraphedTrainStep needs a tinyfaces_b200.optim.FlatSGD optimizer")
+        if getattr(loss_fn, "sampler", "device") != "device":
+            raise RuntimeError("GraphedTrainStep needs the device sampler (the numpy sampler runs on the host)")
+        self.model, self.loss_fn, self.optimizer, self.group = model, loss_fn, optimizer, group
+        self.static = tuple(t.detach().clone().float().contiguous() for t in (img, class_map, regression_map))
+        self.batch = img.shape[0]
+        dev = img.device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.static[1].copy_(class_map)                      # OHEM edits the class map in place
+                train_step(model, loss_fn, optimizer, *self.static, group=group)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.static[1].copy_(class_map)
+        with torch.cuda.graph(self.graph):
+            self.loss = train_step(model, loss_fn, optimizer, *self.static, group=group)
+        # the capture itself did not execute anything: undo its host-side meter bookkeeping
+        for m in (loss_fn.class_average, loss_fn.reg_average):
+            m.num_averaged -= self.batch
+
+    def __call__(self, img, class_map, regression_map):
+        """Copies the batch into the graph's static inputs (device->device, or host->device for pinned host tensors),
+        replays, returns the (static) loss tensor -- valid until the next call."""
+        for dst, src in zip(self.static, (img, class_map, regression_map)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for m in (self.loss_fn.class_average, self.loss_fn.reg_average):
+            m.num_averaged += self.batch
+        return self.loss
 
 
 class InputPipeline:
@@ -94,12 +148,13 @@ def _meter_value(meter, device):
     return a.detach().to(torch.float32) if isinstance(a, torch.Tensor) else torch.tensor(float(a), device=device)
 
 
-def train_pipelined(model, loss_fn, optimizer, batches, device, group=None, with_meters=False):
+def train_pipelined(model, loss_fn, optimizer, batches, device, group=None, with_meters=False, graph=False):
     """Step loop over an iterable of HOST batches with the copies and the loss read-back taken off the critical path:
     batch i+1 is staged while batch i computes, and the loss of step i is read (from a pinned buffer) only after step
     i+1 has been enqueued.  Yields one Python float per step, in order; with_meters=True yields
     (loss, class_average, reg_average) -- the running averages AS OF THAT STEP, snapshotted on the device right after it
-    (reading loss_fn.class_average.average from the consumer would see step i+1's update and synchronise on it)."""
+    (reading loss_fn.class_average.average from the consumer would see step i+1's update and synchronise on it).
+    graph=True replays a GraphedTrainStep (captured on the first batch; its warm-up steps train on that batch)."""
     pipe = InputPipeline(device)
     host_loss = torch.empty((2, 3), dtype=torch.float32).pin_memory()
     loss_ready = [None, None]
@@ -109,9 +164,12 @@ def train_pipelined(model, loss_fn, optimizer, batches, device, group=None, with
         pipe.stage(*nxt)
     i = 0
     pending = None                                   # index of the step whose loss has not been yielded yet
+    graphed = graph if isinstance(graph, GraphedTrainStep) else None
     while nxt is not None:
         x, c, r = pipe.next()
-        loss = train_step(model, loss_fn, optimizer, x, c, r, group)
+        if graph and graphed is None:
+            graphed = GraphedTrainStep(model, loss_fn, optimizer, x, c, r, group)
+        loss = graphed(x, c, r) if graphed is not None else train_step(model, loss_fn, optimizer, x, c, r, group)
         pipe.release()
         if with_meters:
             snap = torch.stack([loss.detach().to(torch.float32), _meter_value(loss_fn.class_average, pipe.device),
