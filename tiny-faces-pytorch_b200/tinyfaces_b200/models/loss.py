@@ -28,14 +28,15 @@ class AvgMeter:
             if not isinstance(self._sum, torch.Tensor) or self._sum.device != loss.device:
                 prev = float(self._sum) if self._sum is not None else 0.0
                 self._sum = torch.full((), prev, dtype=torch.float64, device=loss.device)
-            self._sum.add_(loss * size)
+            self._sum.add_(loss)
         else:
-            self._sum = (self._sum if self._sum is not None else 0.0) + loss * size
+            self._sum = (self._sum if self._sum is not None else 0.0) + loss
         self.num_averaged += size
 
     @property
     def _average(self):
-        """running average = sum(loss_i * size_i) / sum(size_i) (algebraically the reference's recurrence)"""
+        """sum(loss_i) / sum(size_i): algebraically the reference's recurrence average = (n * average + loss) / (n + size),
+        loss.py:13-17 (the batch loss is NOT weighted by its size there)"""
         if self._sum is None or self.num_averaged == 0:
             return 0
         return self._sum / self.num_averaged
@@ -127,6 +128,29 @@ class DetectionCriterion(nn.Module):
         self.class_average.update(sums[0], output.size(0))          # loss.py:90-91
         self.reg_average.update(sums[1], output.size(0))
         return total
+
+    def loss_and_grad(self, output, class_map, regression_map):
+        """forward() without autograd: returns (total loss, d total / d output).  The fused kernel produces both in one
+        pass anyway; the autograd-free training step (trainer.train_step_flat, the CUDA-graph step) feeds the gradient
+        straight into DetectionModel.backward_flat.  Same side effects as forward() (in-place OHEM, meters, attributes)."""
+        if not output.is_cuda:
+            raise RuntimeError("DetectionCriterion: output must be a CUDA tensor (no CPU fallback)")
+        with torch.no_grad():
+            out_c = output.detach().contiguous()
+            cm = class_map if (class_map.is_contiguous() and class_map.dtype == torch.float32) else class_map.float().contiguous()
+            ops.detloss_ohem_(out_c, cm)
+            if cm is not class_map:
+                class_map.copy_(cm)
+            labels = self.balance_sample(cm)
+            sums, grad = ops.detloss_fwd_bwd(out_c, labels, regression_map.float().contiguous(), float(self.reg_weight))
+            sums32 = sums.to(torch.float32)
+            total = sums32[0] + float(self.reg_weight) * sums32[1]
+            self.masked_class_loss = sums32[0]
+            self.masked_reg_loss = sums32[1]
+            self.total_loss = total
+            self.class_average.update(sums32[0], output.size(0))
+            self.reg_average.update(sums32[1], output.size(0))
+        return total, grad
 
     def reset(self):
         self.class_average.reset()

@@ -256,6 +256,28 @@ class DetectionModel(nn.Module):
               "tf_model_get_tensor")
         return t
 
+    def forward_train_flat(self, x):
+        """Training forward WITHOUT autograd bookkeeping (pairs with backward_flat; needs a FlatParams / FlatSGD store)."""
+        if self.__dict__.get("_flat") is None:
+            raise RuntimeError("forward_train_flat needs tinyfaces_b200.optim.FlatParams / FlatSGD on this model")
+        if not self.training:
+            raise RuntimeError("forward_train_flat: the model is in eval mode")
+        with torch.no_grad():
+            return _run_forward(self, x)
+
+    def backward_flat(self, grad_out):
+        """Backward of the last forward_train_flat: every gradient is written into the flat store (overwriting) and the
+        bucket events of the overlapped all-reduce / SGD pipeline are recorded.  No autograd engine involved."""
+        flat = self.__dict__.get("_flat")
+        ex = self._executor
+        table = self.__dict__.get("_flat_grad_table")
+        if table is None or table[0] is not flat:
+            table = self.__dict__["_flat_grad_table"] = (flat, flat.grad_pointer_table(ex.names))
+        grad_out = grad_out.contiguous()
+        with torch.cuda.device(grad_out.device):
+            check(lib().tf_model_backward_ex(ex.handle, grad_out.data_ptr(), table[1], len(flat.events), flat._ev_ptrs,
+                                             flat._ev_blocks, stream_ptr(grad_out.device)), "tf_model_backward_ex")
+
     def _graph_forward(self, x):
         """Inference forward replayed from a CUDA graph captured per (input shape, precision, workspace): the small pyramid
         levels are launch-bound (~300 launches for < 1 ms of GPU work).  The returned tensor is the graph's static output:

@@ -48,6 +48,17 @@ def train_step(model, loss_fn, optimizer, img, class_map, regression_map, group=
     return loss
 
 
+def train_step_flat(model, loss_fn, optimizer, img, class_map, regression_map, group=None):
+    """The same step without the autograd engine (FlatSGD only): the loss kernel already returns d loss / d output, which
+    goes straight into the executor's backward.  This is what GraphedTrainStep captures (the engine's end-of-backward
+    stream bookkeeping waits on events recorded outside the capture, which a stream capture rejects)."""
+    output = model.forward_train_flat(img)
+    loss, grad = loss_fn.loss_and_grad(output, class_map, regression_map)
+    model.backward_flat(grad)
+    reduce_and_step(optimizer, group)
+    return loss
+
+
 class GraphedTrainStep:
     """The whole training step (forward, loss incl. OHEM + device sampler, backward, bucketed all-reduce, SGD) captured
     ONCE into a CUDA graph and replayed per batch: the ~900 kernel launches (and their ~2 ms of host + launch-gap time,
@@ -71,13 +82,13 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
                 self.static[1].copy_(class_map)                      # OHEM edits the class map in place
-                train_step(model, loss_fn, optimizer, *self.static, group=group)
+                train_step_flat(model, loss_fn, optimizer, *self.static, group=group)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         self.static[1].copy_(class_map)
-        with torch.cuda.graph(self.graph):
-            self.loss = train_step(model, loss_fn, optimizer, *self.static, group=group)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.loss = train_step_flat(model, loss_fn, optimizer, *self.static, group=group)
         # the capture itself did not execute anything: undo its host-side meter bookkeeping
         for m in (loss_fn.class_average, loss_fn.reg_average):
             m.num_averaged -= self.batch

@@ -7,7 +7,7 @@ from tinyfaces_b200 import synthetic
 from tinyfaces_b200.models.loss import DetectionCriterion
 from tinyfaces_b200.models.model import DetectionModel
 from tinyfaces_b200.optim import FlatSGD
-from tinyfaces_b200.trainer import GraphedTrainStep, train_step
+from tinyfaces_b200.trainer import GraphedTrainStep, train_step, train_step_flat
 
 def run(B, H, W, mode, steps=10, precision="fast"):
     dev = torch.device("cuda:0")
@@ -24,7 +24,7 @@ def run(B, H, W, mode, steps=10, precision="fast"):
     else:
         opt = FlatSGD(m, m.learnable_parameters(1e-7), momentum=0.9, weight_decay=5e-4)
         if mode == "flat":
-            fn = lambda: train_step(m, crit, opt, x, cm.clone(), rm)
+            fn = lambda: train_step_flat(m, crit, opt, x, cm.clone(), rm)
         else:
             g = GraphedTrainStep(m, crit, opt, x, cm, rm)
             fn = lambda: g(x, cm, rm)
@@ -50,7 +50,9 @@ if __name__ == "__main__":
             except Exception as ex:
                 print(json.dumps(dict(B=B, H=H, W=W, mode=mode, error=str(ex)[:400])), flush=True)
             torch.cuda.empty_cache()
-    try:
-        print(json.dumps(run(8, 960, 1280, "flat", steps=5, precision="parity")), flush=True)
-    except Exception as ex:
-        print(json.dumps(dict(mode="parity", error=str(ex)[:400])), flush=True)
+    for mode in ("flat", "graph"):
+        try:
+            print(json.dumps(run(8, 960, 1280, mode, steps=5, precision="parity")), flush=True)
+        except Exception as ex:
+            print(json.dumps(dict(mode="parity-" + mode, error=str(ex)[:400])), flush=True)
+        torch.cuda.empty_cache()
