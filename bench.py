@@ -1,16 +1,21 @@
 #!/usr/bin/env python
-"""Headline benchmark: detector training step (forward + loss + backward + SGD) images/s, plus NMS boxes/s.
+"""Headline benchmark: detector training step (forward + loss + backward + all-reduce + SGD) images/s, plus NMS boxes/s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Workload at N=1 = BASELINE.json configs[1]: batch-8 1280x960 synthetic images (tensor 8x3x960x1280), full
-fwd+loss+bwd(+SGD) on one B200.  N>1 (torchrun, one rank per GPU): the same per-GPU batch on every rank with a
-SUM gradient all-reduce over NCCL -> weak scaling.  `--impl reference` times the reference's CPU path (the oracle
-port of it -- /root/reference does not exist on the GPU box) on the host cores.
-One JSON line on stdout (rank 0).
+fwd+loss+bwd+SGD on one B200, the whole step replayed from ONE CUDA graph.  N>1 (torchrun, one rank per GPU): the same
+per-GPU batch on every rank with the bucketed SUM gradient all-reduce over NCCL overlapped with the backward -> weak
+scaling.  Extra keys on the same JSON line: `parity_mode` (the 3xTF32 arithmetic that meets the 1e-3 tolerance, timed, with
+both modes' measured error against the reference's golden output at this very shape), `roofline` (the kernel class with
+the largest time share) + `roofline_classes`, `nms` (stage breakdown, pair tests/s), `inference` (configs[2]),
+`cfg3` (configs[3]: batch-32 500x500 strong scaling) and `cfg4` (configs[4]: 8-scale sharded pyramid inference).
+`--impl reference` times the reference's CPU path (the oracle port of it -- /root/reference does not exist on the GPU
+box) on the host cores.  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -26,7 +31,9 @@ import torch         # noqa: E402
 
 H_IMG, W_IMG, B_PER_GPU, T = 960, 1280, 8, 25
 FWD_GFLOP_PER_IMG, STEP_GFLOP_PER_IMG = 346.1, 1032.5
+STEP_GFLOP_PER_IMG_500 = 218.0
 METRIC = "train-step images/sec (fwd+loss+bwd+SGD), batch-8 1280x960 per GPU"
+NMS_EXTENT_FACTOR = 0.35                                        # synthetic box density: ~25 % of the boxes survive (10-30 %)
 
 
 def peaks():
@@ -88,7 +95,7 @@ def _best_thread_count():
 
 def cpu_reference_step_rate(steps, warmup, sample_hw=(480, 640), batch=1):
     """The reference's CPU path (oracle port: same torch CPU ops, same loss incl. the numpy sampler), fp32, on the
-    host threads that run it fastest.  The sample is B=1 at 480x640 (a quarter of the 960x1280 image: per-image conv
+    host threads that run it fastest.  The sample is B=1 at 480x640 (a QUARTER of the 960x1280 image area: per-image conv
     cost is proportional to area), scaled to 960x1280-image units.  Returns (images/s, threads, sample description)."""
     from oracle import loss_oracle, model_oracle, synth
     cores = _best_thread_count()
@@ -120,8 +127,8 @@ def cpu_reference_step_rate(steps, warmup, sample_hw=(480, 640), batch=1):
             times.append(dt)
     t = float(np.mean(times))
     area = (H * W) / float(H_IMG * W_IMG)
-    return batch * area / t, cores, ("%d timed step(s) of B=%d %dx%d on %d of %d host threads (mean %.2f s/step), scaled by "
-                                     "area to %dx%d images" % (steps, batch, H, W, cores, os.cpu_count() or 1, t, H_IMG, W_IMG))
+    return batch * area / t, cores, ("%d timed step(s) of B=%d %dx%d (a quarter-area sample) on %d of %d host threads (mean %.2f s/step), "
+                                     "scaled by area to %dx%d images" % (steps, batch, H, W, cores, os.cpu_count() or 1, t, H_IMG, W_IMG))
 
 
 def run_reference(args):
@@ -132,11 +139,251 @@ def run_reference(args):
     v, cores, sample = cpu_reference_step_rate(steps, warmup)
     line = dict(impl="reference", metric=METRIC, value=v, unit="images/s", n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=1000.0 / v, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fp32",
-                data="synthetic", config=dict(workload="batch-8 1280x960 fwd+loss+bwd+SGD per GPU (CPU arm samples B=1)",
+                data="synthetic", config=dict(workload="batch-8 1280x960 fwd+loss+bwd+SGD per GPU (CPU arm samples B=1 at 480x640, quarter area)",
                                               per_gpu_batch=B_PER_GPU, image=[H_IMG, W_IMG]),
                 cpu_baseline=dict(value=v, unit="images/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=v, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ helpers (GPU arm)
+def _event_time(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps / 1000.0
+
+
+def build_step(dev, B, H, W, precision, seed, group, lr=1e-7, graph=True):
+    """(model, criterion, optimizer, step callable, static device batch, graphed?)"""
+    from tinyfaces_b200 import synthetic
+    from tinyfaces_b200.models.loss import DetectionCriterion
+    from tinyfaces_b200.models.model import DetectionModel
+    from tinyfaces_b200.optim import FlatSGD
+    from tinyfaces_b200.trainer import GraphedTrainStep, train_step_flat
+    torch.manual_seed(0)
+    model = DetectionModel(pretrained_weights=None, num_templates=T).to(dev)
+    model.train()
+    model.precision = precision
+    crit = DetectionCriterion(T, sampler="device", seed=seed)
+    # main.py:25-27 defaults (momentum .9, weight decay 5e-4) with the learning rate scaled down for this UNTRAINED net: the
+    # reference's 1e-4 assumes ImageNet weights; on random-init weights and a summed loss it diverges to inf within a few
+    # steps (the optimizer's work per step does not depend on the value)
+    opt = FlatSGD(model, model.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4)
+    H3, W3 = (H + 7) // 8, (W + 7) // 8
+    img_h = synthetic.images(B, H, W, seed=seed).pin_memory()
+    cm_h, rm_h = synthetic.targets(B, H3, W3, T, seed=seed)
+    cm_h, rm_h = cm_h.pin_memory(), rm_h.pin_memory()
+    dev_batch = (img_h.to(dev), cm_h.to(dev), rm_h.to(dev))
+    graphed, err = None, None
+    if graph:
+        try:
+            graphed = GraphedTrainStep(model, crit, opt, *dev_batch, group=group, warmup=2)
+        except Exception as ex:  # noqa: BLE001
+            err = str(ex)[:300]
+            graphed = None
+            torch.cuda.synchronize()
+    if graphed is not None:
+        def step():
+            return graphed(*dev_batch)
+    else:
+        def step():
+            return train_step_flat(model, crit, opt, dev_batch[0], dev_batch[1].clone(), dev_batch[2], group)
+    return dict(model=model, crit=crit, opt=opt, step=step, host=(img_h, cm_h, rm_h), dev=dev_batch, graphed=graphed, graph_error=err)
+
+
+def timed_steps(fn, steps, warmup, world, dev):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def golden_forward_error(dev, precision):
+    """Forward of the benchmark shape itself against the REFERENCE's output (tests/golden/cfg2_b8_fwd.npz, produced by
+    oracle/make_golden.py from /root/reference): max-norm and L2 relative error of the 8x125x120x160 score map."""
+    from tinyfaces_b200 import synthetic
+    from tinyfaces_b200.models.model import DetectionModel
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cfg2_b8_fwd.npz"))
+    m = DetectionModel(pretrained_weights=None, num_templates=T)
+    m.load_state_dict(synthetic.state_dict(seed=1, bn3_gamma=0.25, beta_jitter=0.1))
+    m.precision = precision
+    m = m.to(dev).train()
+    B, C, H, W = (int(v) for v in g["shape"])
+    x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(int(g["seed"])))
+    with torch.no_grad():
+        out = m(x.to(dev))
+    step = int(g["step"])
+    sub = out[:, :, ::step, ::step].double().cpu().numpy()
+    ref = g["out_sub"].astype(np.float64)
+    res = dict(max_rel=float(np.abs(sub - ref).max() / float(g["out_max"])), l2_rel=float(np.linalg.norm(sub - ref) / np.linalg.norm(ref)))
+    del m, out
+    torch.cuda.empty_cache()
+    return res
+
+
+def roofline_classes(dev, pk):
+    """The layer-3 GEMM classes of the step at M = 8*60*80 = 38400 pixels, each timed ALONE with CUDA events on the launch
+    stream (-> compared with the burst peak), with their launch counts per training step."""
+    from tinyfaces_b200 import ops
+    B, Hc, Wc = B_PER_GPU, H_IMG // 16, W_IMG // 16
+    rows = []
+
+    def add(name, kernel, count, flops, fn):
+        t = _event_time(fn, 40)
+        rows.append(dict(name=name, kernel=kernel, launches_per_step=count, us_per_launch=t * 1e6, algorithmic_gflop=flops / 1e9,
+                         tflops=flops / t / 1e12, frac_of_tf32_burst=flops / t / 1e12 / pk["tf32_burst"],
+                         ms_per_step=count * t * 1e3))
+    M = B * Hc * Wc
+    for name, cin, cout, k, n_f, n_w in (("3x3 256->256", 256, 256, 3, 22 + 22, 22), ("1x1 256->1024", 256, 1024, 1, 23 + 22, 22 + 23),
+                                          ("1x1 1024->256", 1024, 256, 1, 22 + 23, 22 + 23)):
+        x = torch.randn(B, Hc, Wc, cin, device=dev)
+        w = torch.randn(cout, k * k, cin, device=dev) * 0.02
+        y = torch.empty(B, Hc, Wc, cout, device=dev)
+        dy = torch.randn(B, Hc, Wc, cout, device=dev)
+        dw = torch.zeros(cout, k * k, cin, device=dev)
+        flops = 2.0 * M * cin * cout * k * k
+        add("fprop/dgrad " + name, "conv_gemm_kernel / conv_gemm2_kernel", n_f, flops, lambda: ops.conv2d_nhwc(x, w, k, out=y))
+        add("wgrad " + name, "conv_wgrad_kernel<256>", n_w, flops, lambda: ops.conv2d_wgrad_nhwc(x, dy, k, out=dw))
+        del x, w, y, dy, dw
+    return rows
+
+
+def nms_report(dev, n, pk, with_cpu):
+    """tf_nms on n synthetic float64 boxes (centres U(0,S)^2 with S chosen so that ~25 % survive, sizes U(10,70)^2, 1 %
+    exact duplicates): end-to-end time, stage breakdown (the library stops after a stage under tf_debug_set(14, k)),
+    IoU pair tests and the bytes the algorithm that ran actually moves."""
+    from tinyfaces_b200 import ops, synthetic
+    from tinyfaces_b200._lib import lib
+    bx, sc = synthetic.boxes(n, seed=0, extent=NMS_EXTENT_FACTOR * 40.0 * math.sqrt(n / 4.0))
+    bxd, scd = bx.to(dev), sc.to(dev)
+    t_all = _event_time(lambda: ops.nms_device(bxd, scd, 0.3), 10)
+    keep, cnt = ops.nms_device(bxd, scd, 0.3)
+    k = int(cnt.item())
+    stages = {}
+    for stop, name in ((1, "sort+gather"), (2, "+sweep"), (3, "+resolve")):
+        lib().tf_debug_set(14, stop)
+        stages[name] = _event_time(lambda: ops.nms_device(bxd, scd, 0.3), 10)
+    lib().tf_debug_set(14, 0)
+    lib().tf_debug_set(13, 1)
+    ops.nms_device(bxd, scd, 0.3)
+    st = ops.nms_sweep_stats(n, 8, dev)
+    lib().tf_debug_set(13, 0)
+    # bytes of the sort-and-sweep algorithm: boxes+scores in, two key/index sorts (64-bit and 32-bit keys, w+r per radix pass
+    # is library-internal: counted once), rank- and x-ordered box copies, the edge list written once and read ~once, keep out
+    nbytes = n * 40 + n * (8 + 4) * 2 + n * (4 + 4) * 2 + 2 * n * 40 * 2 + st["edges"] * 8 * 2 + n * 3 + k * 8
+    rep = dict(n=n, kept=k, kept_frac=k / n, dtype="f64", thr=0.3, ms=t_all * 1e3, boxes_per_s=n / t_all,
+               stage_ms={"sort+gather": stages["sort+gather"] * 1e3, "sweep": (stages["+sweep"] - stages["sort+gather"]) * 1e3,
+                         "resolve": (stages["+resolve"] - stages["+sweep"]) * 1e3, "select": (t_all - stages["+resolve"]) * 1e3},
+               conflict_edges=st["edges"], resolve_rounds=st["rounds"], iou_pair_tests=st["pair_tests"],
+               pair_tests_per_s=st["pair_tests"] / t_all, all_pairs=n * (n - 1) // 2,
+               algorithm="sort-and-sweep + parallel fixed-point resolution (stream-ordered, no host sync)",
+               algorithmic_bytes=nbytes, algorithmic_gbs=nbytes / t_all / 1e9, hbm_frac=nbytes / t_all / 1e9 / pk["hbm_gbs"],
+               bound="latency / pair tests: %d dependent launches move %.0f MB -- the HBM roofline is not the limiter above N ~ 1e4 "
+                     "(SURVEY 8d); boxes/s and pair tests/s are the honest figures" % (20, nbytes / 1e6))
+    if with_cpu:
+        try:
+            from oracle import nms_oracle
+            t0 = time.perf_counter()
+            kc = nms_oracle.nms(bx.numpy(), sc.numpy(), 0.3)
+            dt = time.perf_counter() - t0
+            rep["cpu"] = dict(boxes_per_s=n / dt, s=dt, n=n, kept=int(len(kc)), same_keep=bool(np.array_equal(kc, keep[:k].cpu().numpy())),
+                              kind="port (plain-C restatement of torchvision's CPU nms, 1 thread)")
+        except Exception as ex:  # noqa: BLE001
+            rep["cpu"] = dict(error=str(ex)[:200])
+    return rep
+
+
+def cfg3_report(dev, world, rank, group, steps):
+    """BASELINE configs[3]: batch-32 500x500 training step, data-parallel: STRONG scaling (32 / N images per GPU)."""
+    B = 32 // world
+    st = build_step(dev, B, 500, 500, "fast", rank, group)
+    ms = timed_steps(st["step"], steps, 3, world, dev)
+    rep = dict(workload="BASELINE.json configs[3]: batch-32 500x500 step, %d image(s) per GPU, bucketed SUM all-reduce overlapped with "
+                        "the backward + SGD as its epilogue" % B, scaling="strong", global_batch=32, per_gpu_batch=B, n_gpus=world,
+               ms_per_step=ms / steps, images_per_s=32 * steps / (ms / 1e3), cuda_graph=st["graphed"] is not None,
+               graph_error=st["graph_error"], buckets=len(st["opt"].flat.buckets),
+               step_tflops_per_gpu=STEP_GFLOP_PER_IMG_500 * B / (ms / steps))
+    del st
+    torch.cuda.empty_cache()
+    return rep
+
+
+def cfg4_report(dev, world, rank, group, target_candidates=100000):
+    """BASELINE configs[4]: 8-scale pyramid of a 1250x1250 image (441 ... 5000 px), sharded over the ranks by level AND by
+    horizontal bands of the large levels (halo 448 px), candidate gather, global NMS on rank 0."""
+    import torch.distributed as dist
+    from torchvision import transforms
+    from tinyfaces_b200 import inference_bench
+    from tinyfaces_b200.evaluation import get_detections, get_detections_sharded
+    model = inference_bench.make_calibrated_model(dev)
+    tpl = inference_bench.load_templates()
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+    img = torch.rand(3, 1250, 1250, generator=torch.Generator().manual_seed(1))
+    scales = (-1.5, -1, -0.5, 0, 0.5, 1, 1.5, 2)
+    thr = inference_bench.threshold_for(model, img, tf, scales, target_candidates, dev)
+    rep = dict(workload="BASELINE.json configs[4]: 8-scale pyramid of a 1250x1250 image (levels %s px) + global NMS"
+                        % [int(1250 * 2 ** s) for s in scales], n_gpus=world, prob_thresh=thr)
+
+    def timed(fn):
+        """device time of fn() on this rank's stream (CUDA events), MAX over the ranks"""
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return r, float(ms.item())
+    with torch.no_grad():
+        single = None
+        if rank == 0:
+            get_detections(model, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev)      # warm-up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            single = get_detections(model, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev)
+            e1.record()
+            torch.cuda.synchronize()
+            rep["single_gpu_ms"] = e0.elapsed_time(e1)
+            rep["detections"] = int(len(single))
+        if world > 1:
+            for spatial, key in ((False, "level_sharded"), (True, "level+band_sharded")):
+                get_detections_sharded(model, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
+                                       group=group, spatial=spatial)                                                  # warm-up
+                (res, ms) = timed(lambda: get_detections_sharded(model, img, tpl, inference_bench.RF, tf, prob_thresh=thr,
+                                                                scales=scales, device=dev, group=group, spatial=spatial,
+                                                                return_plan=True))
+                if rank == 0:
+                    dets, jobs = res
+                    rep[key] = dict(ms=ms, speedup_vs_single=rep["single_gpu_ms"] / ms, identical_to_single_gpu=bool(np.array_equal(dets, single)),
+                                    jobs=len(jobs), bands_per_level=[sum(1 for j in jobs if j[0] == lv) for lv in range(len(scales))])
+    del model
+    torch.cuda.empty_cache()
+    return rep
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -149,8 +396,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nms-n", type=int, default=100000)
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline + e2e only")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay")
     ap.add_argument("--breakdown", default="", help="write a per-kernel time table of one step to this file")
-    ap.add_argument("--profile-mode", action="store_true", help="only the timed steps (for runs under ncu)")
+    ap.add_argument("--profile-mode", action="store_true", help="only the timed steps, eager (for runs under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -158,70 +407,37 @@ def main():
         args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
-    from tinyfaces_b200 import ops, synthetic
-    from tinyfaces_b200.models.loss import DetectionCriterion
-    from tinyfaces_b200.models.model import DetectionModel
-    from tinyfaces_b200.trainer import train_step
+    from tinyfaces_b200.trainer import train_pipelined
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
 
-    torch.manual_seed(0)
-    model = DetectionModel(pretrained_weights=None, num_templates=T).to(dev)
-    model.train()
-    crit = DetectionCriterion(T, sampler="device", seed=rank)
-    # main.py:25-27 defaults (momentum .9, weight decay 5e-4) with the learning rate scaled down for this UNTRAINED net: the
-    # reference's 1e-4 assumes ImageNet weights; on random-init weights and a summed loss it diverges to inf within a few
-    # steps (the optimizer's work per step does not depend on the value)
-    opt = torch.optim.SGD(model.learnable_parameters(1e-7), momentum=0.9, weight_decay=5e-4, fused=True)
+    st = build_step(dev, B_PER_GPU, H_IMG, W_IMG, "fast", rank, group, graph=not (args.no_graph or args.profile_mode))
+    model, crit, opt, step_resident = st["model"], st["crit"], st["opt"], st["step"]
+    img_h, cm_h, rm_h = st["host"]
     B = B_PER_GPU
-    H3, W3 = (H_IMG + 7) // 8, (W_IMG + 7) // 8
-    img_h = synthetic.images(B, H_IMG, W_IMG, seed=rank).pin_memory()
-    cm_h, rm_h = synthetic.targets(B, H3, W3, T, seed=rank)
-    cm_h, rm_h = cm_h.pin_memory(), rm_h.pin_memory()
-    img_d, cm_d, rm_d = img_h.to(dev), cm_h.to(dev), rm_h.to(dev)
-
-    def step_resident():
-        return train_step(model, crit, opt, img_d, cm_d.clone(), rm_d)
-
-    def run_e2e(steps):
-        """`steps` steps through the public loop (trainer.train_pipelined): every step copies its inputs from pinned host
-        memory (double-buffered on a copy stream) and its loss is read back to the host (one step late)."""
-        from tinyfaces_b200.trainer import train_pipelined
-        return list(train_pipelined(model, crit, opt, ((img_h, cm_h, rm_h) for _ in range(steps)), dev))
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
 
     sampler = ClockSampler(local)
     sampler.start()
-    ms_total = timed(step_resident, args.steps, args.warmup)
+    ms_total = timed_steps(step_resident, args.steps, args.warmup, world, dev)
     if args.profile_mode:
         sampler.stop_flag = True
         if rank == 0:
             print(json.dumps(dict(profile_mode=True, ms_per_step=ms_total / args.steps)))
         return
+
+    def run_e2e(steps):
+        """`steps` steps through the public loop (trainer.train_pipelined): every step copies its inputs from pinned host
+        memory (double-buffered on a copy stream) and its loss is read back to the host (one step late)."""
+        return list(train_pipelined(model, crit, opt, ((img_h, cm_h, rm_h) for _ in range(steps)), dev, group=group,
+                                    graph=st["graphed"] if st["graphed"] is not None else False))
     run_e2e(2)                                                       # warm-up of the pipelined loop (slot allocation)
     if world > 1:
         dist.barrier()
@@ -248,82 +464,22 @@ def main():
                 data="synthetic",
                 config=dict(workload="BASELINE.json configs[1]: batch-8 1280x960 (8x3x960x1280) fwd+loss+bwd+SGD per GPU",
                             per_gpu_batch=B, global_batch=B * world, image=[H_IMG, W_IMG], templates=T,
-                            precision="fast (1xTF32 operands, fp32 accumulate/storage)", sampler="device",
-                            parallelism="dp%d (batch-sharded, SUM grad all-reduce, per-shard BN)" % world,
+                            precision="fast (1xTF32 operands, fp32 accumulate/storage); see parity_mode for the 3xTF32 arithmetic",
+                            sampler="device", cuda_graph=st["graphed"] is not None, graph_error=st["graph_error"],
+                            optimizer="library SGD kernel per gradient bucket (momentum .9, wd 5e-4), %d buckets" % len(opt.flat.buckets),
+                            parallelism="dp%d (batch-sharded, bucketed SUM grad all-reduce overlapped with the backward, per-shard BN)" % world,
                             l2="step working set (~28 GB) >> 126 MB L2; no explicit flush"),
-                e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                e2e=dict(value=e2e_value, unit="images/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=12,
                          ms_per_step=ms_e2e / args.steps,
-                         how="trainer.train_pipelined: pinned host batch -> device every step (double-buffered on a copy "
-                             "stream, overlapping the previous step), loss read back to the host every step (one step late)"),
+                         how="trainer.train_pipelined(graph=...): pinned host batch -> device every step (double-buffered on a copy "
+                             "stream, overlapping the previous step), device->device into the graph's static inputs, graph replay, "
+                             "loss read back to the host every step (one step late)"),
                 clocks=sampler.summary())
     line["loss"] = dict(first=e2e_losses[0], last=e2e_losses[-1], finite=bool(np.all(np.isfinite(e2e_losses))))
     line["step_tflops"] = STEP_GFLOP_PER_IMG * value / 1000.0
     line["step_frac_of_tf32_sustained"] = line["step_tflops"] / (pk["tf32_sustained"] * world)
 
-    # ---- isolated micro-benchmarks first (roofline kernel, NMS, pyramid inference): torch.profiler leaves CUPTI attached,
-    #      which slows the host round trips of the latency-bound NMS afterwards
-    if rank == 0:
-        # ---- roofline of the dominant kernel: layer3 3x3 256->256 at this config (8x60x80), isolated, CUDA events
-        Bc, Hc, Wc, C = B, H3 // 2, W3 // 2, 256
-        xc = torch.randn(Bc, Hc, Wc, C, device=dev)
-        wc = torch.randn(C, 9, C, device=dev) * 0.02
-        yc = torch.empty(Bc, Hc, Wc, C, device=dev)
-        for _ in range(5):
-            ops.conv2d_nhwc(xc, wc, 3, out=yc)
-        torch.cuda.synchronize()
-        reps = 50
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            ops.conv2d_nhwc(xc, wc, 3, out=yc)
-        e1.record()
-        torch.cuda.synchronize()
-        t_launch = e0.elapsed_time(e1) / reps / 1000.0
-        flops = 2.0 * Bc * Hc * Wc * C * C * 9
-        ach = flops / t_launch / 1e12
-        traffic, pipe = None, None
-        try:
-            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                rec = json.load(f)["conv_gemm_kernel<256> 3x3 256->256 M=38400"]
-            traffic, pipe = rec["dram_read_bytes"] + rec["dram_write_bytes"], rec["tensor_pipe_active_pct"]
-        except Exception:  # noqa: BLE001
-            pass
-        line["roofline"] = dict(bound="tensor", kernel="conv_gemm_kernel<256> (3x3 256->256, M=%d)" % (Bc * Hc * Wc),
-                                achieved=ach, peak=pk["tf32_burst"], unit="TFLOP/s", frac=ach / pk["tf32_burst"],
-                                traffic=traffic, traffic_source="profiles/roofline_traffic.json (ncu --set full)",
-                                ncu_tensor_pipe_active_pct=pipe, algorithmic_flops_per_launch=flops,
-                                peak_source=pk["source"], us_per_launch=t_launch * 1e6)
-
-        # ---- NMS boxes/s (the second half of BASELINE.json's metric), N random boxes, float64
-        bx, sc = synthetic.boxes(args.nms_n, seed=0)
-        bx, sc = bx.to(dev), sc.to(dev)
-        for _ in range(2):
-            ops.nms_device(bx, sc, 0.3)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            keep, cnt = ops.nms_device(bx, sc, 0.3)
-        e1.record()
-        torch.cuda.synchronize()
-        t_nms = e0.elapsed_time(e1) / 5 / 1000.0
-        n, k = args.nms_n, int(cnt.item())
-        nms_bytes = n * 40 + 2 * n * 8 + 2 * ((n + 63) // 64) * min(n, 32768) * 8 + k * 8
-        line["nms"] = dict(n=n, kept=k, boxes_per_s=n / t_nms, ms=t_nms * 1e3, dtype="f64",
-                           algorithmic_gbs=nms_bytes / t_nms / 1e9, hbm_frac=nms_bytes / t_nms / 1e9 / pk["hbm_gbs"],
-                           note="pair-test (ALU) bound at this N, see DESIGN.md")
-
-        # ---- pyramid inference (BASELINE.json configs[2])
-        if not args.no_inference:
-            try:
-                from tinyfaces_b200 import inference_bench
-                imodel = inference_bench.make_calibrated_model(dev)      # fresh weights with calibrated BN statistics
-                line["inference"] = inference_bench.run(imodel, base=1250, target_candidates=args.nms_n)
-                del imodel
-            except Exception as ex:  # noqa: BLE001
-                line["inference"] = dict(error=str(ex)[:300])
-
-    # ---- kernel launch census of one step (CUPTI via torch.profiler; not timed).  The step contains the gradient
-    #      all-reduce, so EVERY rank runs it; only rank 0 records.
+    # ---- kernel launch census of one step (CUPTI via torch.profiler; not timed): kernels inside the replayed graph count
     prof = None
     try:
         if rank == 0:
@@ -341,40 +497,123 @@ def main():
             if prof is None:
                 raise RuntimeError("no profile")
             ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
-            mine = [e for e in ev if any(s in e.name for s in ("conv_gemm_kernel", "conv_wgrad_kernel", "kernel<", "_kernel"))
+            mine = [e for e in ev if any(s in e.name for s in ("conv_gemm_kernel", "conv_gemm2_kernel", "conv_wgrad_kernel", "kernel<", "_kernel"))
                     and "at::native" not in e.name and "nccl" not in e.name.lower()]
             line["gpu_launches"] = len(mine)
             line["gpu_launches_all"] = len(ev)
             tot = sum(e.device_time for e in ev) or 1.0
-            gemm = sum(e.device_time for e in ev if "conv_gemm_kernel" in e.name or "conv_wgrad_kernel" in e.name)
+            agg = {}
+            for e in ev:
+                a = agg.setdefault(e.name.split("(")[0][-60:], [0, 0.0])
+                a[0] += 1
+                a[1] += e.device_time
+            gemm = sum(t for k, (n, t) in agg.items() if "conv_gemm" in k or "conv_wgrad" in k)
             line["gemm_share_of_step"] = gemm / tot
+            line["top_kernels_by_time"] = [dict(kernel=k, launches=n, ms=t / 1e3, share=t / tot)
+                                           for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:8]]
             if args.breakdown:
-                agg = {}
+                agg2 = {}
                 for e in ev:
-                    a = agg.setdefault(e.name[:110], [0, 0.0])
+                    a = agg2.setdefault(e.name[:110], [0, 0.0])
                     a[0] += 1
                     a[1] += e.device_time
                 with open(args.breakdown, "w") as f:
                     f.write("# one training step, batch-8 960x1280, torch.profiler (CUPTI) device times\n")
                     f.write("%-112s %6s %10s %6s\n" % ("kernel", "calls", "total_us", "share"))
-                    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                    for k, (n, t) in sorted(agg2.items(), key=lambda kv: -kv[1][1]):
                         f.write("%-112s %6d %10.1f %5.1f%%\n" % (k, n, t, 100.0 * t / tot))
         except Exception as ex:      # noqa: BLE001
             line["gpu_launches"] = None
             line["profiler_error"] = str(ex)[:200]
 
+    # the eager (no graph) launch path of the same step, for reference
+    if st["graphed"] is not None and not args.no_extras:
+        from tinyfaces_b200.trainer import train_step_flat
+        eager = timed_steps(lambda: train_step_flat(model, crit, opt, st["dev"][0], st["dev"][1].clone(), st["dev"][2], group), 5, 2, world, dev)
+        line["eager_ms_per_step"] = eager / 5
+    del st, model, crit, opt, step_resident
+    torch.cuda.empty_cache()
+
+    extras = not args.no_extras
+    # ---- BASELINE configs[3] / configs[4] (every rank takes part)
+    if extras:
+        try:
+            rep = cfg3_report(dev, world, rank, group, max(5, min(args.steps, 20)))
+            if rank == 0:
+                line["cfg3"] = rep
+        except Exception as ex:  # noqa: BLE001
+            line["cfg3"] = dict(error=str(ex)[:300])
+        if not args.no_inference:
+            try:
+                rep = cfg4_report(dev, world, rank, group, args.nms_n)
+                if rank == 0:
+                    line["cfg4"] = rep
+            except Exception as ex:  # noqa: BLE001
+                line["cfg4"] = dict(error=str(ex)[:300])
+
+    if rank == 0 and extras:
+        # ---- the arithmetic that meets north_star's 1e-3: 3xTF32 (`parity`), timed at the same shape, and both modes' error
+        #      against the reference's golden output at this shape
+        if world == 1:
+            try:
+                fe = golden_forward_error(dev, "fast")
+                pe = golden_forward_error(dev, "parity")
+                ps = build_step(dev, B_PER_GPU, H_IMG, W_IMG, "parity", rank, None)
+                pms = timed_steps(ps["step"], 5, 2, 1, dev) / 5
+                line["parity_mode"] = dict(arithmetic="3xTF32 (hi*hi + lo*hi + hi*lo), fp32 accumulate / storage", ms_per_step=pms,
+                                           images_per_s=B_PER_GPU / (pms / 1e3), cuda_graph=ps["graphed"] is not None,
+                                           out_rel_err=pe, tolerance=1e-3, within_tolerance=pe["max_rel"] < 1e-3 and pe["l2_rel"] < 1e-3,
+                                           error_reference="tests/golden/cfg2_b8_fwd.npz: the reference's own 8x3x960x1280 train-mode forward")
+                line["fast_out_rel_err"] = fe
+                del ps
+                torch.cuda.empty_cache()
+            except Exception as ex:  # noqa: BLE001
+                line["parity_mode"] = dict(error=str(ex)[:300])
+        # ---- rooflines: every layer-3 GEMM class alone; the headline `roofline` is the class with the largest time per step
+        try:
+            rows = roofline_classes(dev, pk)
+            line["roofline_classes"] = rows
+            top = max(rows, key=lambda r: r["ms_per_step"])
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                    rec = json.load(f).get(top["name"])
+                traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"] if rec else None
+            except Exception:  # noqa: BLE001
+                pass
+            line["roofline"] = dict(bound="tensor", kernel="%s, %s (M=%d)" % (top["kernel"], top["name"], B_PER_GPU * (H_IMG // 16) * (W_IMG // 16)),
+                                    achieved=top["tflops"], peak=pk["tf32_burst"], unit="TFLOP/s", frac=top["frac_of_tf32_burst"],
+                                    traffic=traffic, traffic_source="profiles/roofline_traffic.json (ncu --set full)",
+                                    algorithmic_flops_per_launch=top["algorithmic_gflop"] * 1e9, us_per_launch=top["us_per_launch"],
+                                    launches_per_step=top["launches_per_step"], peak_source=pk["source"],
+                                    why="largest time per step among the kernel classes (launches x isolated time); see roofline_classes")
+        except Exception as ex:  # noqa: BLE001
+            line["roofline"] = dict(error=str(ex)[:300])
+        # ---- NMS boxes/s (the second half of BASELINE.json's metric)
+        try:
+            line["nms"] = nms_report(dev, args.nms_n, pk, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:  # noqa: BLE001
+            line["nms"] = dict(error=str(ex)[:300])
+        # ---- pyramid inference (BASELINE.json configs[2])
+        if not args.no_inference and world == 1:
+            try:
+                from tinyfaces_b200 import inference_bench
+                imodel = inference_bench.make_calibrated_model(dev)      # fresh weights with calibrated BN statistics
+                line["inference"] = inference_bench.run(imodel, base=1250, target_candidates=args.nms_n)
+                del imodel
+            except Exception as ex:  # noqa: BLE001
+                line["inference"] = dict(error=str(ex)[:300])
         # ---- CPU baseline beside it (bounded sample)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 v, cores, sample = cpu_reference_step_rate(steps=2, warmup=1)
                 line["cpu_baseline"] = dict(value=v, unit="images/s", cores=cores, kind="port", sample=sample)
-                from oracle import nms_oracle
-                nb, ns = synthetic.boxes(20000, seed=0)
-                t0 = time.perf_counter()
-                nms_oracle.nms(nb.numpy(), ns.numpy(), 0.3)
-                line["cpu_baseline"]["nms_boxes_per_s_n20000"] = 20000 / (time.perf_counter() - t0)
+                if isinstance(line.get("nms"), dict) and "cpu" in line["nms"]:
+                    line["cpu_baseline"]["nms_boxes_per_s"] = line["nms"]["cpu"].get("boxes_per_s")
+                    line["cpu_baseline"]["nms_n"] = args.nms_n
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = dict(error=str(ex)[:200])
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

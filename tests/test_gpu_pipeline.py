@@ -216,3 +216,31 @@ def test_pipelined_loop_equals_step_by_step():
     assert np.all(np.isfinite(plain))
     assert piped == plain, (piped, plain)
     assert len(set(plain)) > 1                          # different batches really went through
+
+
+def test_spatially_tiled_levels_reproduce_the_untiled_candidates_bit_for_bit():
+    """every level cut into 2 / 3 bands with a 448 px halo (>= half the 859 px receptive field) and decoded
+    with its global row offset gives EXACTLY the candidate list (boxes, scores, order) of the untiled forward -- hence the
+    same NMS result.  Odd sizes, a level whose band cut is clipped by the border, eval `fast` mode (fixed K order)."""
+    from torchvision import transforms
+    from tinyfaces_b200 import inference_bench
+    from tinyfaces_b200.evaluation import get_detections, get_detections_tiled
+    dev = torch.device("cuda:0")
+    m = inference_bench.make_calibrated_model(dev, seed=3)
+    tpl = inference_bench.load_templates()
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+    img = torch.rand(3, 1100, 1237, generator=torch.Generator().manual_seed(8))
+    scales = (0, 0.5)                                           # 1100x1237 and 1555x1749
+    with torch.no_grad():
+        o = m(torch.randn(1, 3, 512, 512, generator=torch.Generator().manual_seed(3)).to(dev))
+        thr = float(torch.sigmoid(o[:, :25]).flatten().kthvalue(int(0.97 * o[:, :25].numel())).values)
+        ref_b, ref_s = get_detections_tiled(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
+                                            bands=1, return_candidates=True)
+        assert ref_b.shape[0] > 1000
+        for bands in (2, 3, {1: 4}):
+            b, s = get_detections_tiled(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
+                                        bands=bands, return_candidates=True)
+            assert torch.equal(b, ref_b) and torch.equal(s, ref_s), bands
+        dets = get_detections(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev)
+        tiled = get_detections_tiled(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev, bands=3)
+    assert np.array_equal(dets, tiled)

@@ -1,0 +1,46 @@
+"""CPU: host-side planning of the spatially tiled / sharded pyramid inference (evaluation.plan_bands / plan_jobs)."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tiny-faces-pytorch_b200"))
+
+
+@pytest.mark.parametrize("H", [193, 500, 1250, 2500, 5000, 4999, 1237])
+@pytest.mark.parametrize("nb", [1, 2, 3, 5, 8, 16])
+def test_bands_cover_the_level_with_enough_halo(H, nb):
+    from tinyfaces_b200.evaluation import HALO_PX, out_rows, plan_bands
+    H3 = out_rows(H)
+    bands = plan_bands(H, nb)
+    assert bands[0][0] == 0 and bands[-1][1] == H3
+    for (r0, r1, y0, y1), nxt in zip(bands, bands[1:] + [None]):
+        assert r1 > r0 and (nxt is None or nxt[0] == r1)                  # disjoint, in order, complete
+        assert r0 % 2 == 0 and y0 % 16 == 0 and 0 <= y0 < y1 <= H
+        # every row of the band has its whole receptive field (radius 430 px) inside the tile or cut by the true border
+        assert y0 == 0 or 8 * r0 - 430 >= y0
+        assert y1 == H or 8 * (r1 - 1) + 430 < y1
+        assert HALO_PX >= 430
+        # the tile's own forward produces the rows the band needs
+        assert out_rows(y1 - y0) >= r1 - y0 // 8
+        if y1 == H:
+            assert out_rows(y1 - y0) == H3 - y0 // 8
+
+
+def test_job_plan_balances_the_five_level_pyramid():
+    from tinyfaces_b200.evaluation import plan_jobs
+    shapes = [(312, 312), (625, 625), (1250, 1250), (2500, 2500), (5000, 5000)]
+    total = sum(h * w for h, w in shapes)
+    for world in (1, 2, 4, 8):
+        jobs = plan_jobs(shapes, world, spatial=True)
+        assert [j[0] for j in jobs] == sorted(j[0] for j in jobs) and {j[0] for j in jobs} == set(range(5))
+        load = [0] * world
+        for lv, bi, r0, r1, y0, y1, owner in jobs:
+            assert 0 <= owner < world
+            load[owner] += (y1 - y0) * shapes[lv][1]
+        speedup = total / max(load)
+        assert speedup >= {1: 1.0, 2: 1.6, 4: 2.6, 8: 4.1}[world] - 1e-9, (world, speedup)
+    # level sharding alone is capped near 1.33x by the 5000^2 level (25 M of 33.3 M pixels)
+    jobs = plan_jobs(shapes, 8, spatial=False)
+    assert len(jobs) == 5

