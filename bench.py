@@ -147,6 +147,14 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ helpers (GPU arm)
+def _kernel_key(name):
+    """'void (anonymous namespace)::conv_gemm_kernel<256, false, true, false>(...)' -> 'conv_gemm_kernel<256, false, true, false>'"""
+    import re
+    m = re.search(r"([A-Za-z_][A-Za-z0-9_]*(?:<[^()]*>)?)\s*\(", name.replace("(anonymous namespace)::", ""))
+    return (m.group(1) if m else name)[:80]
+
+
+
 def _event_time(fn, reps, warm=3):
     for _ in range(warm):
         fn()
@@ -504,7 +512,7 @@ def main():
             tot = sum(e.device_time for e in ev) or 1.0
             agg = {}
             for e in ev:
-                a = agg.setdefault(e.name.split("(")[0][-60:], [0, 0.0])
+                a = agg.setdefault(_kernel_key(e.name), [0, 0.0])
                 a[0] += 1
                 a[1] += e.device_time
             gemm = sum(t for k, (n, t) in agg.items() if "conv_gemm" in k or "conv_wgrad" in k)
@@ -573,20 +581,27 @@ def main():
         try:
             rows = roofline_classes(dev, pk)
             line["roofline_classes"] = rows
-            top = max(rows, key=lambda r: r["ms_per_step"])
+            # the kernel (by name) with the largest time share of the step is conv_wgrad_kernel<256> (profiles/step_breakdown_*,
+            # `top_kernels_by_time`): its figure is the launch-weighted aggregate over its three layer-3 shape classes
+            wg = [r for r in rows if r["kernel"].startswith("conv_wgrad")]
+            flops = sum(r["algorithmic_gflop"] * 1e9 * r["launches_per_step"] for r in wg)
+            secs = sum(r["us_per_launch"] * 1e-6 * r["launches_per_step"] for r in wg)
+            launches = sum(r["launches_per_step"] for r in wg)
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                    rec = json.load(f).get(top["name"])
-                traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"] if rec else None
+                    rec = json.load(f).get("conv_wgrad_kernel<256>")
+                traffic = rec.get("dram_bytes_per_launch") if rec else None
             except Exception:  # noqa: BLE001
                 pass
-            line["roofline"] = dict(bound="tensor", kernel="%s, %s (M=%d)" % (top["kernel"], top["name"], B_PER_GPU * (H_IMG // 16) * (W_IMG // 16)),
-                                    achieved=top["tflops"], peak=pk["tf32_burst"], unit="TFLOP/s", frac=top["frac_of_tf32_burst"],
-                                    traffic=traffic, traffic_source="profiles/roofline_traffic.json (ncu --set full)",
-                                    algorithmic_flops_per_launch=top["algorithmic_gflop"] * 1e9, us_per_launch=top["us_per_launch"],
-                                    launches_per_step=top["launches_per_step"], peak_source=pk["source"],
-                                    why="largest time per step among the kernel classes (launches x isolated time); see roofline_classes")
+            line["roofline"] = dict(bound="tensor", kernel="conv_wgrad_kernel<256> (layer-3 weight gradients: 3x3 256->256, 1x1 256<->1024; M=%d pixels)"
+                                                           % (B_PER_GPU * (H_IMG // 16) * (W_IMG // 16)),
+                                    achieved=flops / secs / 1e12, peak=pk["tf32_burst"], unit="TFLOP/s", frac=flops / secs / 1e12 / pk["tf32_burst"],
+                                    traffic=traffic, traffic_source="profiles/roofline_traffic.json (ncu --set full, launch-weighted mean)",
+                                    algorithmic_flops_per_launch=flops / launches, us_per_launch=secs / launches * 1e6,
+                                    launches_per_step=launches, peak_source=pk["source"],
+                                    why="the kernel with the largest share of the step's kernel time (see top_kernels_by_time); every class is "
+                                        "timed alone with CUDA events on its launch stream; per-class figures in roofline_classes")
         except Exception as ex:  # noqa: BLE001
             line["roofline"] = dict(error=str(ex)[:300])
         # ---- NMS boxes/s (the second half of BASELINE.json's metric)

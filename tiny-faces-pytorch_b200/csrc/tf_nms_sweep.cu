@@ -42,6 +42,16 @@ constexpr int SC_EDGES = 0, SC_ECNT = 1, SC_UNDEC = 3, SC_PAIRS = 5, SC_ROUNDS =
 
 __device__ __forceinline__ float xkey_of(double v) { return __double2float_rn(v); }      // monotone non-decreasing
 __device__ __forceinline__ float xkey_of(float v) { return v; }
+__device__ __forceinline__ float lo_of(double v) { return __double2float_rd(v); }        // <= v
+__device__ __forceinline__ float lo_of(float v) { return v; }
+__device__ __forceinline__ float hi_of(double v) { return __double2float_ru(v); }        // >= v
+__device__ __forceinline__ float hi_of(float v) { return v; }
+
+// 16-byte sweep record of a box in x order: everything the candidate filter needs.  The sweep visits ~N * (boxes per
+// x-extent) candidates but only a few percent of them overlap in y: the filter reads this record (one 16 B load) and
+// touches the exact 32-byte box only for the survivors.  The float y-range is widened outwards (lo rounded down, hi
+// rounded up), so the filter is a superset of the exact test -- exactness is decided on the full-precision box.
+struct alignas(16) SweepRec { float x1, ylo, yhi; int rank; };
 
 template <typename T>
 __global__ void gather_rank_kernel(const T* __restrict__ boxes, const int* __restrict__ order, int n,
@@ -55,26 +65,32 @@ __global__ void gather_rank_kernel(const T* __restrict__ boxes, const int* __res
 }
 // x-ordered copies of the boxes so that the sweep streams them instead of gathering through xorder
 template <typename T>
-__global__ void gather_x_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area, const int* __restrict__ xorder, int n,
-                                Box<T>* __restrict__ xb, T* __restrict__ xarea) {
+__global__ void gather_x_kernel(const Box<T>* __restrict__ sb, const T* __restrict__ area, const int* __restrict__ xorder,
+                                const float* __restrict__ xsorted, int n, Box<T>* __restrict__ xb, T* __restrict__ xarea,
+                                SweepRec* __restrict__ rec) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int r = xorder[i];
-    xb[i] = sb[r];
+    const Box<T> b = sb[r];
+    xb[i] = b;
     xarea[i] = area[r];
+    SweepRec q;
+    q.x1 = xsorted[i]; q.ylo = lo_of(b.y1); q.yhi = hi_of(b.y2); q.rank = r;
+    rec[i] = q;
 }
 // One WARP per box a (position p in x order): the 32 lanes test 32 consecutive x-successors per step, so dense
 // inputs (real detections overlap thousands of x-neighbours) stay parallel.  Conflicts go to the edge list as
 // (earlier rank, later rank); entries past the capacity are counted but not stored (the result is then flagged).
 template <typename T>
 __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ xb, const T* __restrict__ xarea,
-                                                    const float* __restrict__ xs, const int* __restrict__ xorder, int n,
+                                                    const SweepRec* __restrict__ rec, int n,
                                                     double thr, unsigned long long* __restrict__ scalars,
                                                     int2* __restrict__ edges, unsigned long long cap, int count_pairs) {
     const int p = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (p >= n) return;
-    const int a = xorder[p];                       // rank (score order) of this box
+    const SweepRec ra = rec[p];
+    const int a = ra.rank;                         // rank (score order) of this box
     const Box<T> A = xb[p];
     const T aa = xarea[p];
     const float ax2 = xkey_of(A.x2);               // NaN: every comparison fails -> no candidates (such a box never conflicts)
@@ -84,11 +100,12 @@ __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ x
         bool live = false, hit = false;
         int b = 0;
         if (q < n) {
-            live = xs[q] <= ax2;                   // x order: once this fails, it fails for every later q
-            if (live) {
+            const SweepRec rq = rec[q];
+            live = rq.x1 <= ax2;                   // x order: once this fails, it fails for every later q
+            if (live && rq.ylo < ra.yhi && ra.ylo < rq.yhi) {          // widened float y ranges: a superset of the exact test
                 const Box<T> Bx = xb[q];
                 if (Bx.y1 < A.y2 && A.y1 < Bx.y2) {
-                    b = xorder[q];
+                    b = rq.rank;
                     ++tested;
                     hit = a < b ? suppresses<T>(A, aa, Bx, xarea[q], thr, true) : suppresses<T>(Bx, xarea[q], A, aa, thr, true);
                 }
@@ -194,7 +211,7 @@ struct SweepPlan {
         add(sort_bytes); add(select_bytes);
         add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas by rank
         add(4 * n); add(4 * n); add(4 * n);                               // x keys (float), sorted x keys, x order
-        add(sizeof(Box<T>) * n); add(sizeof(T) * n);                      // boxes / areas in x order
+        add(sizeof(Box<T>) * n); add(sizeof(T) * n); add(16 * n);         // boxes / areas / sweep records in x order
         add(zero_bytes); add(n); add(4 * n);                              // state | blocked | scalars, flags, selected
         const size_t fixed = a + 1024;
         // two ping-pong edge lists: the default is 128 conflicts per box; a larger caller workspace buys a larger list
@@ -246,6 +263,7 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     int* xorder = ar.take<int>(n);
     Box<T>* xb = ar.take<Box<T>>(n);
     T* xarea = ar.take<T>(n);
+    SweepRec* rec = ar.take<SweepRec>(n);
     unsigned char* zero = ar.take<unsigned char>(plan.zero_bytes);
     unsigned char* state = zero;
     unsigned char* blocked = zero + tf_align_up((size_t)n, 256);
@@ -265,10 +283,10 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     gather_rank_kernel<T><<<nb, 256, 0, st>>>((const T*)boxes, order, n, sb, area, xkey);
     sb_bytes = plan.sort_bytes;
     TF_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_tmp, sb_bytes, (const float*)xkey, xsorted, (const int*)iota, xorder, n, 0, 32, st));
-    gather_x_kernel<T><<<nb, 256, 0, st>>>(sb, area, xorder, n, xb, xarea);
+    gather_x_kernel<T><<<nb, 256, 0, st>>>(sb, area, xorder, xsorted, n, xb, xarea, rec);
     if (stop_after == 1) { TF_LAUNCH_CHECK(); return TF_OK; }
     const int sweep_blocks = (int)(((long long)n * 32 + 255) / 256);
-    sweep_kernel<T><<<sweep_blocks, 256, 0, st>>>(xb, xarea, xsorted, xorder, n, thr, scalars, edges0, (unsigned long long)plan.edge_cap,
+    sweep_kernel<T><<<sweep_blocks, 256, 0, st>>>(xb, xarea, rec, n, thr, scalars, edges0, (unsigned long long)plan.edge_cap,
                                                   tfg::debug_flag(13));
     if (stop_after == 2) { TF_LAUNCH_CHECK(); return TF_OK; }
     {
@@ -299,6 +317,7 @@ int sweep_stats(int64_t n, void* ws, size_t ws_bytes, long long* out4, cudaStrea
     TfArena ar(ws, ws_bytes);
     ar.take<int>(n); ar.take<int>(n); ar.take<T>(n); ar.take<T>(n); ar.take<char>(plan.sort_bytes); ar.take<char>(plan.select_bytes);
     ar.take<Box<T>>(n); ar.take<T>(n); ar.take<float>(n); ar.take<float>(n); ar.take<int>(n); ar.take<Box<T>>(n); ar.take<T>(n);
+    ar.take<SweepRec>(n);
     unsigned char* zero = ar.take<unsigned char>(plan.zero_bytes);
     unsigned long long h[SC_WORDS];
     TF_CHECK_CUDA(cudaMemcpyAsync(h, zero + 2 * tf_align_up((size_t)n, 256), sizeof(h), cudaMemcpyDeviceToHost, st));

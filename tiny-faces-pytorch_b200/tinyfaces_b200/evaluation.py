@@ -48,6 +48,15 @@ class _Pyramid:
         return self.tf(scaled).unsqueeze(0).float().to(self.device, non_blocking=True)
 
 
+def _to_device(model, device):
+    """model.to(device) (evaluation.py:33), skipped when the parameters already live there: nn.Module.to walks every
+    sub-module and drops the executor's cached pointer tables even when nothing moves."""
+    p = next(model.parameters(), None)
+    if p is not None and p.device == device:
+        return model
+    return model.to(device)
+
+
 def nms(boxes, scores, iou_threshold):
     """torchvision.ops.nms(boxes[N,4], scores[N], iou_threshold) -> int64[K] (descending score), bit-identical
     keep indices.  CPU inputs are moved to the current CUDA device and the result is returned on the input's
@@ -75,9 +84,10 @@ def decode_level(output, templates, prob_thresh, rf, scale, bug_compat=True, syn
     strides = (C * hw, W, 1, hw)                       # (b, y, x, c) element strides of an NCHW tensor
     out = output.contiguous()
     a, b = (0, H) if rows is None else rows
-    if row_offset:
+    if row_offset + a:
+        # the kernel numbers the rows of the VIEW from 0: view row j is global heat-map row row_offset + a + j.
         # cy = y * stride + offset is integer arithmetic (utils.py:53): shifting the offset by whole rows is exact
-        rf = dict(rf, offset=[int(rf["offset"][0]) + int(rf["stride"][0]) * int(row_offset), int(rf["offset"][1])])
+        rf = dict(rf, offset=[int(rf["offset"][0]) + int(rf["stride"][0]) * int(row_offset + a), int(rf["offset"][1])])
     view = out[:, :, a:b, :]
     boxes, scores, _, count = ops.decode_device(view, view[:, T:], None, strides, strides, B, b - a, W, T, templates,
                                                 prob_thresh, inv if bug_compat else 0, 0 if bug_compat else inv, rf, scale)
@@ -175,7 +185,7 @@ def get_detections_tiled(model, img, templates, rf, img_transforms, prob_thresh=
     """get_detections with every level cut into `bands` bands (an int or {level index: count}), all on ONE GPU: the
     single-device proof that spatial tiling reproduces the untiled result bit for bit."""
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    model = model.to(device)
+    model = _to_device(model, device)
     model.eval()
     templates = np.asarray(templates, dtype=np.float64)
     pyr = _Pyramid(img, img_transforms, device)
@@ -197,7 +207,7 @@ def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, 
                    device=None, return_scores=False, gpu_pyramid=True):
     """evaluation.py:20-87.  img: CHW float tensor in [0,1]; scales are exponents of 2; returns ndarray [K,4] float64."""
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    model = model.to(device)
+    model = _to_device(model, device)
     model.eval()
     templates = np.asarray(templates, dtype=np.float64)
     pyr = _Pyramid(img, img_transforms, device, gpu_pyramid)
@@ -281,7 +291,7 @@ def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thres
     import torch.distributed as dist
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    model = model.to(device)
+    model = _to_device(model, device)
     model.eval()
     templates = np.asarray(templates, dtype=np.float64)
     pyr = _Pyramid(img, img_transforms, device)

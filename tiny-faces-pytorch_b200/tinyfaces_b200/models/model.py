@@ -230,11 +230,12 @@ class DetectionModel(nn.Module):
         named_parameters() costs more host time than a small pyramid level takes on the GPU."""
         c = self.__dict__.get("_cache")
         if c is None:
-            named = dict(self.named_parameters())
-            params = [named[n] for n in self._executor.names if n in named]
+            pnamed = dict(self.named_parameters())
+            names = self._executor.names
+            params = [pnamed[n] for n in names if n in pnamed]
+            named = dict(pnamed)
             named.update(dict(self.named_buffers()))
-            c = ([named[n] for n in self._executor.names], params,
-                 [n for n in self._executor.names if n in dict(self.named_parameters())])
+            c = ([named[n] for n in names], params, [n for n in names if n in pnamed])
             self.__dict__["_cache"] = c
         return c
 
