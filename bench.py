@@ -395,6 +395,26 @@ def cfg4_report(dev, world, rank, group, target_candidates=100000):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+_PROGRESS = dict(line=None, phase="start", rank=0)
+
+
+def _watchdog(deadline_s):
+    """A stuck collective (or anything else) in one of the EXTRA sections must not cost the whole run: when the deadline
+    passes, rank 0 prints the line as far as it got (with the phase it was stuck in) and every rank exits."""
+    def run():
+        time.sleep(deadline_s)
+        if _PROGRESS["rank"] == 0 and _PROGRESS["line"] is not None:
+            line = dict(_PROGRESS["line"])
+            line["watchdog"] = "deadline of %d s passed during phase '%s': later sections are missing" % (deadline_s, _PROGRESS["phase"])
+            try:
+                print(json.dumps(line), flush=True)
+            except Exception:  # noqa: BLE001
+                pass
+        os._exit(0 if _PROGRESS["line"] is not None else 3)
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -408,6 +428,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay")
     ap.add_argument("--breakdown", default="", help="write a per-kernel time table of one step to this file")
     ap.add_argument("--profile-mode", action="store_true", help="only the timed steps, eager (for runs under ncu)")
+    ap.add_argument("--deadline", type=int, default=780, help="seconds after which the line collected so far is printed and the run ends")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -423,8 +444,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
+    _PROGRESS["rank"] = rank
+    if not args.profile_mode:
+        _watchdog(args.deadline)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     pk = peaks()
 
     st = build_step(dev, B_PER_GPU, H_IMG, W_IMG, "fast", rank, group, graph=not (args.no_graph or args.profile_mode))
@@ -483,6 +508,8 @@ def main():
                              "stream, overlapping the previous step), device->device into the graph's static inputs, graph replay, "
                              "loss read back to the host every step (one step late)"),
                 clocks=sampler.summary())
+    _PROGRESS["line"] = line
+    _PROGRESS["phase"] = "launch census"
     line["loss"] = dict(first=e2e_losses[0], last=e2e_losses[-1], finite=bool(np.all(np.isfinite(e2e_losses))))
     line["step_tflops"] = STEP_GFLOP_PER_IMG * value / 1000.0
     line["step_frac_of_tf32_sustained"] = line["step_tflops"] / (pk["tf32_sustained"] * world)
@@ -545,6 +572,7 @@ def main():
     extras = not args.no_extras
     # ---- BASELINE configs[3] / configs[4] (every rank takes part)
     if extras:
+        _PROGRESS["phase"] = "cfg3"
         try:
             rep = cfg3_report(dev, world, rank, group, max(5, min(args.steps, 20)))
             if rank == 0:
@@ -552,6 +580,7 @@ def main():
         except Exception as ex:  # noqa: BLE001
             line["cfg3"] = dict(error=str(ex)[:300])
         if not args.no_inference:
+            _PROGRESS["phase"] = "cfg4"
             try:
                 rep = cfg4_report(dev, world, rank, group, args.nms_n)
                 if rank == 0:
@@ -559,6 +588,7 @@ def main():
             except Exception as ex:  # noqa: BLE001
                 line["cfg4"] = dict(error=str(ex)[:300])
 
+    _PROGRESS["phase"] = "single-GPU extras (parity mode, rooflines, NMS, inference, CPU baseline)"
     if rank == 0 and extras:
         # ---- the arithmetic that meets north_star's 1e-3: 3xTF32 (`parity`), timed at the same shape, and both modes' error
         #      against the reference's golden output at this shape

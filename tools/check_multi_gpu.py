@@ -19,25 +19,37 @@ from tinyfaces_b200.models.model import DetectionModel
 from tinyfaces_b200.optim import FlatSGD
 from tinyfaces_b200.trainer import GraphedTrainStep, train_step_flat
 
+STAGE = sys.argv[1] if len(sys.argv) > 1 else "all"          # inference | dp | graph | all
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+
+
+def log(*a):
+    print("[rank %d]" % rank, *a, flush=True)
+
+
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
-m = inference_bench.make_calibrated_model(dev, seed=0)
-tpl = inference_bench.load_templates()
-tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
-img = torch.rand(3, 1100, 1237, generator=torch.Generator().manual_seed(2))
-scales = (-1, 0, 0.5)
-thr = inference_bench.threshold_for(m, img, tf, scales, 30000, dev)
-with torch.no_grad():
-    single = get_detections(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev) if rank == 0 else None
-    for spatial in (False, True):
-        sharded, jobs = get_detections_sharded(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
-                                               spatial=spatial, return_plan=True)
-        if rank == 0:
-            same = np.array_equal(sharded, single)
-            print("sharded inference (spatial=%s): %d jobs, %d dets, identical to single-GPU: %s" % (spatial, len(jobs), len(sharded), same), flush=True)
-            assert same
+import datetime
+dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
+log("process group up")
+if STAGE in ("inference", "all"):
+  m = inference_bench.make_calibrated_model(dev, seed=0)
+  tpl = inference_bench.load_templates()
+  tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
+  img = torch.rand(3, 1100, 1237, generator=torch.Generator().manual_seed(2))
+  scales = (-1, 0, 0.5)
+  thr = inference_bench.threshold_for(m, img, tf, scales, 30000, dev)
+  with torch.no_grad():
+      single = get_detections(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev) if rank == 0 else None
+      for spatial in (False, True):
+          sharded, jobs = get_detections_sharded(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
+                                                 spatial=spatial, return_plan=True)
+          if rank == 0:
+              same = np.array_equal(sharded, single)
+              print("sharded inference (spatial=%s): %d jobs, %d dets, identical to single-GPU: %s" % (spatial, len(jobs), len(sharded), same), flush=True)
+              assert same
+if STAGE == "inference":
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
 # ---- data-parallel step: eager, then CUDA graph
 torch.manual_seed(0)
 model = DetectionModel(pretrained_weights=None, num_templates=25).to(dev).train()
@@ -74,11 +86,15 @@ def params_identical():
     return bool(ok.item())
 
 
+log("bucketed step done, grad err %.2e" % err)
 for _ in range(2):
     loss = train_step_flat(model, crit2, opt, x, cm.clone(), rm)
 same_eager = params_identical()
-graph_ok, same_graph = True, None
+log("eager steps identical:", same_eager)
+graph_ok, same_graph = STAGE in ("graph", "all"), None
 try:
+    if not graph_ok:
+        raise RuntimeError("graph stage skipped")
     gs = GraphedTrainStep(model, crit2, opt, x, cm, rm, warmup=1)
     for _ in range(3):
         loss = gs(x, cm, rm)
