@@ -170,6 +170,19 @@ int tf_model_backward_ex(void* handle, const float* dout, void* const* grads_hos
 int tf_model_get_tensor(void* handle, const char* name, float* dst, int64_t capacity, int* shape4_host, void* stream);
 int tf_model_upsample_offdiag(void* handle, float* value_host, void* stream);
 
+/* ---- training-target generation: replaces DataProcessor.get_heatmaps + get_regression (tinyfaces/datasets/processor.py:157-277)
+ * and compute_dense_overlap (tinyfaces/datasets/dense_overlap.py:4-75): the dense template x ground-truth IoU volume (float64,
+ * reference operation order, np.around(., 14)), the per-cell best object -> (tx, ty, tw, th), the per-object best cell and
+ * the {-1, 0, +1} label rule with the padding-border exception.  bboxes: DEVICE [ng,4] float64, already filtered
+ * (x2 > x1, y2 > y1); templates_host: HOST [nt,4]; jitter: DEVICE [vsy,vsx,nt,ng] float64 = the np.random.rand draws of
+ * processor.py:203 (NULL: device noise from `seed`); pad_mask: DEVICE uint8 [vsy,vsx,nt] or NULL.  Outputs DEVICE float64:
+ * class_maps [vsy,vsx,nt], regress_maps [vsy,vsx,4nt] (tx.. ty.. tw.. th..), iou_out [vsy,vsx,nt,ng] (optional, perturbed). */
+int tf_targets_workspace_bytes(int vsy, int vsx, int nt, int ng, size_t* bytes_host);
+int tf_heatmap_targets(const double* bboxes, int ng, const double* templates_host, int nt, int vsy, int vsx, int ofy, int ofx,
+                       int sty, int stx, double pos_thresh, double neg_thresh, const double* jitter, uint64_t seed,
+                       const uint8_t* pad_mask, double* class_maps, double* regress_maps, double* iou_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* ---- optimizer step: replaces optimizer.step() + scheduler.step() of tinyfaces/main.py:67-70,81-83 (torch.optim.SGD with
  * momentum and weight decay over the parameter groups of models/model.py:67-87, StepLR) on FLAT fp32 buffers, one launch per
  * gradient bucket, stream-ordered behind that bucket's all-reduce:

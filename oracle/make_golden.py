@@ -272,8 +272,37 @@ def golden_baseline():
          out_chan_sum=o.astype(np.float64).sum(axis=(0, 2, 3)))
 
 
+def golden_targets():
+    """Training targets from the reference's own DataProcessor.get_heatmaps / get_padding (processor.py:115-277).  The
+    package __init__ of tinyfaces.datasets imports clustering code whose third-party dependencies (pyclust, pyclustering)
+    are not installed; they are irrelevant to this path and stubbed out for the import."""
+    from unittest import mock
+    for name in ("pyclust", "pyclustering", "pyclustering.cluster", "pyclustering.cluster.kmedoids", "pyclustering.utils",
+                 "pyclustering.utils.metric", "pyclustering.cluster.center_initializer"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    from tinyfaces.datasets.processor import DataProcessor
+    tpl = synth.load_templates()[:, :4]
+    r = np.random.RandomState(5)
+    cases = [
+        (np.array([[100., 120., 180., 220.], [300., 50., 330., 90.], [10., 10., 400., 450.]]), [20, 30, 480, 470], 11),
+        (np.concatenate([r.rand(9, 2) * 400, r.rand(9, 2) * 400], axis=1), [0, 0, 500, 500], 12),    # some boxes are invalid
+        (np.zeros((0, 4)), [50, 60, 300, 310], 13),
+        (np.array([[200., 200., 215., 218.], [200., 200., 215., 218.], [240., 100., 260., 130.]]), [0, 0, 500, 500], 14),   # duplicates
+    ]
+    b = cases[1][0]
+    b[:, 2:] = b[:, :2] + (r.rand(9, 2) - 0.2) * 150
+    for i, (boxes, paste, seed) in enumerate(cases):
+        p = DataProcessor((500, 500), (63, 63), 0.7, 0.3, tpl, rf=synth.RF)
+        pad = p.get_padding(paste)
+        np.random.seed(seed)
+        cls, reg, iou = p.get_heatmaps(boxes.copy(), pad)
+        save("targets_case%d.npz" % i, bboxes=boxes, paste_box=np.array(paste), np_seed=np.int64(seed), pad_mask=pad,
+             class_maps=cls.astype(np.int8), regress_maps=reg, iou_sum=np.float64(iou.sum()),
+             iou_sample=iou.reshape(-1)[::97].copy(), iou_shape=np.array(iou.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["model", "loss", "decode", "nms", "detections"]
+    which = sys.argv[1:] or ["model", "loss", "decode", "nms", "detections", "baseline", "targets"]
     for w in which:
         globals()["golden_" + w]()

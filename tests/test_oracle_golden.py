@@ -122,3 +122,16 @@ def test_model_oracle_at_cfg1_shape(name, training):
     step = int(g["step"])
     assert np.abs(out[:, :, ::step, ::step] - g["out_sub"]).max() <= 1e-3 * float(g["out_max"])
     assert abs(np.linalg.norm(out.astype(np.float64)) - float(g["out_l2"])) <= 1e-3 * float(g["out_l2"])
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_targets_oracle_against_reference_golden(case):
+    """get_heatmaps / get_regression / compute_dense_overlap (processor.py:157-277, dense_overlap.py:4-75): the vectorised
+    oracle against the reference's own output, same np.random seed -> identical labels, IoU volume and regression maps."""
+    from oracle import targets_oracle
+    g = np.load(os.path.join(G, "targets_case%d.npz" % case))
+    np.random.seed(int(g["np_seed"]))
+    cls, reg, iou = targets_oracle.get_heatmaps(g["bboxes"].copy(), g["pad_mask"], synth.load_templates(), synth.RF, (63, 63), 0.7, 0.3)
+    assert np.array_equal(cls.astype(np.int8), g["class_maps"])
+    assert tuple(iou.shape) == tuple(g["iou_shape"]) and np.array_equal(iou.reshape(-1)[::97], g["iou_sample"])
+    assert np.abs(reg - g["regress_maps"]).max() <= 1e-12

@@ -81,45 +81,80 @@ __global__ void gather_x_kernel(const Box<T>* __restrict__ sb, const T* __restri
 // One WARP per box a (position p in x order): the 32 lanes test 32 consecutive x-successors per step, so dense
 // inputs (real detections overlap thousands of x-neighbours) stay parallel.  Conflicts go to the edge list as
 // (earlier rank, later rank); entries past the capacity are counted but not stored (the result is then flagged).
+// One WARP per box a (position p in x order).  Phase 1 (cheap, every lane busy): the 32 lanes filter 32 consecutive
+// x-successors per step on the 16-byte records and push the survivors into a per-warp queue in shared memory.  Phase 2
+// (expensive, fp64 with a division): whenever 32 survivors are queued, every lane runs one exact IoU test.  Without the
+// queue ~2/3 of the steps had one or two lanes in the exact test while the other thirty waited for its latency.
+// Conflicts go to the edge list as (earlier rank, later rank); entries past the capacity are counted but not stored.
+template <typename T>
+__device__ __forceinline__ void sweep_exact(const Box<T>* __restrict__ xb, const T* __restrict__ xarea, const SweepRec* __restrict__ rec,
+                                            const Box<T>& A, T aa, int a, int q, bool active, double thr, int lane,
+                                            unsigned long long* __restrict__ scalars, int2* __restrict__ edges, unsigned long long cap,
+                                            unsigned int& tested) {
+    bool hit = false;
+    int b = 0;
+    if (active) {
+        const Box<T> Bx = xb[q];
+        if (Bx.y1 < A.y2 && A.y1 < Bx.y2) {
+            b = rec[q].rank;
+            ++tested;
+            hit = a < b ? suppresses<T>(A, aa, Bx, xarea[q], thr, true) : suppresses<T>(Bx, xarea[q], A, aa, thr, true);
+        }
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+        unsigned long long start = 0;
+        if (lane == 0) start = atomicAdd(scalars + SC_EDGES, (unsigned long long)__popc(m));
+        start = __shfl_sync(0xffffffffu, start, 0);
+        const unsigned long long e = start + __popc(m & ((1u << lane) - 1u));
+        if (hit && e < cap) edges[e] = a < b ? make_int2(a, b) : make_int2(b, a);
+    }
+}
 template <typename T>
 __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ xb, const T* __restrict__ xarea,
                                                     const SweepRec* __restrict__ rec, int n,
                                                     double thr, unsigned long long* __restrict__ scalars,
                                                     int2* __restrict__ edges, unsigned long long cap, int count_pairs) {
+    __shared__ int queue[8][64];
     const int p = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
-    if (p >= n) return;
+    if (p >= n) return;                            // (whole warps leave together: p is warp-uniform)
+    int* wq = queue[threadIdx.x >> 5];
     const SweepRec ra = rec[p];
     const int a = ra.rank;                         // rank (score order) of this box
     const Box<T> A = xb[p];
     const T aa = xarea[p];
     const float ax2 = xkey_of(A.x2);               // NaN: every comparison fails -> no candidates (such a box never conflicts)
     unsigned int tested = 0;
+    int qn = 0;                                    // queued survivors (warp-uniform, < 32 at the top of every step)
     for (int base = p + 1; base < n; base += 32) {
         const int q = base + lane;
-        bool live = false, hit = false;
-        int b = 0;
+        bool live = false, pass = false;
         if (q < n) {
             const SweepRec rq = rec[q];
             live = rq.x1 <= ax2;                   // x order: once this fails, it fails for every later q
-            if (live && rq.ylo < ra.yhi && ra.ylo < rq.yhi) {          // widened float y ranges: a superset of the exact test
-                const Box<T> Bx = xb[q];
-                if (Bx.y1 < A.y2 && A.y1 < Bx.y2) {
-                    b = rq.rank;
-                    ++tested;
-                    hit = a < b ? suppresses<T>(A, aa, Bx, xarea[q], thr, true) : suppresses<T>(Bx, xarea[q], A, aa, thr, true);
-                }
+            pass = live && rq.ylo < ra.yhi && ra.ylo < rq.yhi;         // widened float y ranges: a superset of the exact test
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            if (pass) wq[qn + __popc(m & ((1u << lane) - 1u))] = q;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                const int cand = wq[lane];
+                const int spill = lane + 32 < qn ? wq[lane + 32] : 0;
+                __syncwarp();
+                if (lane + 32 < qn) wq[lane] = spill;                  // move the overflow to the front
+                qn -= 32;
+                __syncwarp();
+                sweep_exact<T>(xb, xarea, rec, A, aa, a, cand, true, thr, lane, scalars, edges, cap, tested);
             }
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, hit);
-        if (m) {
-            unsigned long long start = 0;
-            if (lane == 0) start = atomicAdd(scalars + SC_EDGES, (unsigned long long)__popc(m));
-            start = __shfl_sync(0xffffffffu, start, 0);
-            const unsigned long long e = start + __popc(m & ((1u << lane) - 1u));
-            if (hit && e < cap) edges[e] = a < b ? make_int2(a, b) : make_int2(b, a);
-        }
         if (!__shfl_sync(0xffffffffu, (int)live, 31)) break;       // lane 31 past the x range: so is everything after
+    }
+    if (qn > 0) {
+        const int cand = lane < qn ? wq[lane] : 0;
+        sweep_exact<T>(xb, xarea, rec, A, aa, a, cand, lane < qn, thr, lane, scalars, edges, cap, tested);
     }
     if (count_pairs) {
         tested = (unsigned int)tf_warp_sum((int)tested);

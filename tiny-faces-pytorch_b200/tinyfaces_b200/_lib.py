@@ -44,6 +44,9 @@ _SIGS = {
     "tf_model_backward_ex": (c_i32, [c_vp, c_vp, ctypes.POINTER(c_vp), c_i32, ctypes.POINTER(c_vp), ctypes.POINTER(c_i32), c_vp]),
     "tf_model_get_tensor": (c_i32, [c_vp, ctypes.c_char_p, c_vp, c_i64, ctypes.POINTER(c_i32), c_vp]),
     "tf_model_upsample_offdiag": (c_i32, [c_vp, ctypes.POINTER(c_f32), c_vp]),
+    "tf_targets_workspace_bytes": (c_i32, [c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_sz)]),
+    "tf_heatmap_targets": (c_i32, [c_vp, c_i32, ctypes.POINTER(c_f64), c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f64, c_f64,
+                                   c_vp, c_u64, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "tf_sgd_step": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, ctypes.POINTER(c_i64), ctypes.POINTER(c_f32), ctypes.POINTER(c_f32),
                             c_f32, c_f32, c_vp, c_vp]),
     "tf_steplr_update": (c_i32, [c_vp, c_vp, c_i32, c_f32, c_i32, c_vp]),

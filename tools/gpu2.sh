@@ -11,7 +11,7 @@ echo "bench rc=$?"; tail -3 gpurun_out/bench_2gpu_r2a.err
 python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_2gpu_r2a.json"))
+    d=[json.loads(l) for l in open("gpurun_out/bench_2gpu_r2a.json") if l.startswith("{")][-1]
     for k in ("value","ms_per_step","eager_ms_per_step","watchdog","cfg3","cfg4"):
         print(k, json.dumps(d.get(k))[:900])
     print("config", json.dumps(d["config"])[:500]); print("e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"])
