@@ -74,8 +74,6 @@ template <int BN> struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + 1024 /*barriers*/ + 1024 /*align*/;
     static constexpr int RES_DROP = (32768 + STAGE_BYTES - 1) / STAGE_BYTES;   // operand stages given to the residual buffers (4 warps x 2 x 4 KB)
     static constexpr int FUSED_SMEM_BYTES = SMEM_BYTES + 1024;   // + the CTA's per-channel shift vector (= the 227 KB maximum for BN = 256)
-    static constexpr int WGRAD_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;   // epilogue overlays stage 0
-    static_assert(2 * EPI_BUF_BYTES <= STAGES * STAGE_BYTES, "wgrad epilogue buffers must fit in the operand ring");
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -617,15 +615,30 @@ struct WgradParams {
     int* err_flag;
 };
 
-template <int BN>
+// MT = number of 128-row accumulator tiles a CTA keeps in TMEM (MT * BN columns).  MT = 2: the SAME B (activation) tile of
+// a pipeline stage is multiplied with two dY tiles (Cout rows m0 .. m0+255), so a stage of 64 KB feeds twice the MMAs of
+// the 48 KB stage of MT = 1: 65 instead of 44 flop per byte brought into shared memory.  The kernel is L2->SM fill bound
+// (ncu, round 1: 48-56 % tensor pipe), so that ratio is what sets its speed.
+template <int BN, int MT> struct WgradCfg {
+    static constexpr int A_BYTES = MT * A_STAGE_BYTES;
+    static constexpr int STAGE_BYTES = A_BYTES + BN * 128;
+    static constexpr int STAGES_RAW = (196 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*barriers*/ + 1024 /*align*/;      // epilogue overlays stage 0
+    static constexpr int TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
+    static_assert(2 * EPI_BUF_BYTES <= STAGES * STAGE_BYTES, "wgrad epilogue buffers must fit in the operand ring");
+    static_assert(STAGES >= 3, "wgrad pipeline too shallow");
+};
+
+template <int BN, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = WgradCfg<BN, MT>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // The epilogue staging buffers overlay the first operand stage: the epilogue only starts once every MMA (hence every
-    // operand read and every TMA load) has completed.  That keeps the CTA at 194 KB of shared memory, so ~30 KB stay free
+    // operand read and every TMA load) has completed.  That keeps the CTA at ~194 KB of shared memory, so ~30 KB stay free
     // for the chain's elementwise blocks (1 KB reserved each) this kernel is meant to run next to.
     uint8_t* epi = smem;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -641,7 +654,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
         mbar_init(&tfull[0], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc<BN < 32 ? 32 : BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -651,7 +664,7 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
     const int units = p.m_tiles * p.n_tiles;
     const int unit = blockIdx.x % units, split = blockIdx.x / units;
     const int n0 = (unit % p.n_tiles) * BN;
-    const int m0 = (unit / p.n_tiles) * BLOCK_M;
+    const int m0 = (unit / p.n_tiles) * (BLOCK_M * MT);
     const int ncols = p.taps * p.cin;
     const int b_boxes = min(BN / 32, (ncols - n0 + 31) / 32);           // 32-column chunks of this tile that exist in dW
     const int pb0 = (int)((long long)p.num_pblocks * split / p.splits);
@@ -666,10 +679,11 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                 for (int seg = 0; seg < p.nseg; ++seg) {
                     mbar_wait(&empty[stage], phase ^ 1, p.err_flag, 11);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
                     // One TMA per operand (per tap for B): the channel axis is split into (32, C/32) so that a box
                     // (32 ch, 32 px, g groups) lands as g consecutive [32 px][128 B] slabs -- the MN-major layout the
                     // MMA wants -- instead of g separate 4 KB copies.  Groups past the tensor edge are zero-filled.
+                    // (MT = 2: the A box holds 8 groups = both 128-row dY tiles.)
                     mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
                     const int gb = p.b_groups;                       // 32-channel groups per B instruction
                     if (p.spatial) {
@@ -701,14 +715,17 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
                     mbar_wait(&full[stage], phase, p.err_flag, 13);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sb = sa + A_STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {       // 32 pixels = 4 MMAs of K = 8
                         // MN-major tf32: 32 channels (128 B) x 32 pixel rows per TMA box, SWIZZLE_128B_BASE32B atoms of
                         // 4 rows: LBO = next 32-channel box (4096 B), SBO = next 4-row group (512 B), K step = 8 rows
-                        const uint64_t ad = make_smem_desc(sa + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
                         const uint64_t bd = make_smem_desc(sb + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
-                        mma_tf32(tmem_base, ad, bd, idesc, (pb != pb0) || seg != 0 || j != 0);
+#pragma unroll
+                        for (int h = 0; h < MT; ++h) {
+                            const uint64_t ad = make_smem_desc(sa + h * A_STAGE_BYTES + j * 1024, 4096, 512, LAYOUT_SW128_BASE32B);
+                            mma_tf32(tmem_base + h * BN, ad, bd, idesc, (pb != pb0) || seg != 0 || j != 0);
+                        }
                     }
                     tc_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -723,29 +740,33 @@ conv_wgrad_kernel(const __grid_constant__ WgradMaps maps, const WgradParams p) {
             tc_fence_after();
             int ebuf = 0;
 #pragma unroll 1
-            for (int chunk = 0; chunk < b_boxes; ++chunk) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + chunk * 32, r);
-                tmem_ld_wait();
-                uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
-                if (store_thread) tma_store_wait_read<1>();
-                named_bar_sync_epi();
-                store_row_swizzled(smem_u32(buf), row, r);
-                fence_proxy_async();
-                named_bar_sync_epi();
-                if (store_thread) {
-                    if (p.plain_store) tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0);
-                    else               tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0);
-                    tma_store_commit();
+            for (int h = 0; h < MT; ++h) {
+                if (m0 + h * BLOCK_M >= p.cout) break;                 // (a dY tile past the tensor edge holds zeros)
+#pragma unroll 1
+                for (int chunk = 0; chunk < b_boxes; ++chunk) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + chunk * 32, r);
+                    tmem_ld_wait();
+                    uint8_t* buf = epi + ebuf * EPI_BUF_BYTES;
+                    if (store_thread) tma_store_wait_read<1>();
+                    named_bar_sync_epi();
+                    store_row_swizzled(smem_u32(buf), row, r);
+                    fence_proxy_async();
+                    named_bar_sync_epi();
+                    if (store_thread) {
+                        if (p.plain_store) tma_store_2d(&maps.d, buf, n0 + chunk * 32, m0 + h * BLOCK_M);
+                        else               tma_reduce_add_2d(&maps.d, buf, n0 + chunk * 32, m0 + h * BLOCK_M);
+                        tma_store_commit();
+                    }
+                    ebuf ^= 1;
                 }
-                ebuf ^= 1;
             }
             if (store_thread) tma_store_wait_all<0>();
             tc_fence_before();
         }
     }
     __syncthreads();
-    if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc<BN < 32 ? 32 : BN>(tmem_base); }
+    if (warp == 1) { __syncwarp(); tc_fence_after(); tmem_dealloc<Cfg::TMEM_COLS>(tmem_base); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -1021,16 +1042,16 @@ int launch_gemm2(const GemmMaps& maps, const GemmParams& p, int* stats_rows, cud
     if (p.scale || p.shift || p.relu || p.round_out) return launch_gemm2_variant<true>(maps, p, clusters, st);
     return launch_gemm2_variant<false>(maps, p, clusters, st);
 }
-template <int BN>
+template <int BN, int MT>
 int launch_wgrad(const WgradMaps& maps, const WgradParams& p, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = WgradCfg<BN, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::WGRAD_SMEM_BYTES));
+        TF_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = p.m_tiles * p.n_tiles * p.splits;
-    conv_wgrad_kernel<BN><<<grid, GEMM_THREADS, Cfg::WGRAD_SMEM_BYTES, st>>>(maps, p);
+    conv_wgrad_kernel<BN, MT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(maps, p);
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -1211,7 +1232,10 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
     WgradParams p = {};
     p.taps = a.ksize * a.ksize; p.cin = Cin; p.cout = Cout; p.err_flag = g_err_flag;
     p.nseg = a.x_lo ? 3 : 1;
-    p.m_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
+    // two accumulator tiles per CTA (dY rows m0 .. m0+255 share every activation tile) whenever Cout allows it;
+    // tf_debug_set(10, 1) keeps the one-tile kernel (A/B switch)
+    const int MT = (Cout % (2 * BLOCK_M) == 0 && !g_debug[10]) ? 2 : 1;
+    p.m_tiles = (Cout + BLOCK_M * MT - 1) / (BLOCK_M * MT);
     p.n_tiles = (ncols + BN - 1) / BN;
     {   // groups per B instruction: must divide both the tile (BN/32) and a tap's channel groups (Cin/32)
         int x = (Cin < BN ? Cin : BN) / 32, y = BN / 32;
@@ -1229,7 +1253,7 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
         p.spatial = 0; p.tiles_x = p.tiles_y = 1; p.tw = 32; p.th = 1;
         p.num_pblocks = (int)((M + 31) / 32);
         for (int s = 0; s < p.nseg; ++s) {
-            if ((rc = encode_3d_grouped(&maps.a[s], as[s], Cout, M, 32, BLOCK_M / 32))) return rc;
+            if ((rc = encode_3d_grouped(&maps.a[s], as[s], Cout, M, 32, MT * BLOCK_M / 32))) return rc;
             if ((rc = encode_3d_grouped(&maps.b[s], bs[s], Cin, M, 32, p.b_groups))) return rc;
         }
     } else {
@@ -1238,7 +1262,7 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
         p.tiles_x = (Wo + p.tw - 1) / p.tw; p.tiles_y = (Ho + p.th - 1) / p.th;
         p.num_pblocks = B * p.tiles_x * p.tiles_y;
         for (int s = 0; s < p.nseg; ++s) {
-            if ((rc = encode_5d_grouped(&maps.a[s], as[s], Cout, Wo, Ho, B, p.tw, p.th, BLOCK_M / 32))) return rc;
+            if ((rc = encode_5d_grouped(&maps.a[s], as[s], Cout, Wo, Ho, B, p.tw, p.th, MT * BLOCK_M / 32))) return rc;
             if ((rc = encode_5d_grouped(&maps.b[s], bs[s], Cin, W, H, B, p.tw, p.th, p.b_groups, stride))) return rc;
         }
     }
@@ -1249,9 +1273,14 @@ int conv_wgrad(const WgradArgs& a, cudaStream_t st) {
     if (splits < 1) splits = 1;
     if (g_debug[0]) { splits = 1; p.plain_store = 1; }
     p.splits = splits;
-    if (BN == 256) return launch_wgrad<256>(maps, p, st);
-    if (BN == 128) return launch_wgrad<128>(maps, p, st);
-    return launch_wgrad<64>(maps, p, st);
+    if (MT == 2) {
+        if (BN == 256) return launch_wgrad<256, 2>(maps, p, st);
+        if (BN == 128) return launch_wgrad<128, 2>(maps, p, st);
+        return launch_wgrad<64, 2>(maps, p, st);
+    }
+    if (BN == 256) return launch_wgrad<256, 1>(maps, p, st);
+    if (BN == 128) return launch_wgrad<128, 1>(maps, p, st);
+    return launch_wgrad<64, 1>(maps, p, st);
 }
 
 }  // namespace tfg

@@ -140,7 +140,7 @@ def plan_bands(H, nbands):
     return bands
 
 
-def plan_jobs(level_shapes, world, spatial=True):
+def plan_jobs(level_shapes, world, spatial=True, force_bands=None):
     """Work list for `world` ranks: [(level, band, r0, r1, y0, y1, owner)].  Levels are cut into bands only when that
     lowers the makespan of a longest-processing-time packing (cost = tile pixels, halo included); the band counts of
     the two largest levels are searched exhaustively."""
@@ -156,8 +156,8 @@ def plan_jobs(level_shapes, world, spatial=True):
             load[r] += j[6]
         return max(load), jobs
     order = sorted(range(len(level_shapes)), key=lambda i: -level_shapes[i][0] * level_shapes[i][1])
-    best = pack({})
-    if spatial and world > 1 and order:
+    best = pack(dict(force_bands) if force_bands else {})
+    if force_bands is None and spatial and world > 1 and order:
         big, second = order[0], (order[1] if len(order) > 1 else None)
         for nb in range(1, 2 * world + 1):
             for nb2 in (range(1, world + 1) if second is not None else [1]):
@@ -283,7 +283,7 @@ def gather_level_candidates(per_level, num_levels, group=None, dst=0, device=Non
 
 
 def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thresh=0.65, nms_thresh=0.3,
-                           scales=(-2, -1, 0, 1), device=None, group=None, spatial=True, return_plan=False):
+                           scales=(-2, -1, 0, 1), device=None, group=None, spatial=True, return_plan=False, force_bands=None):
     """get_detections sharded over the ranks of `group`: the pyramid levels -- and, with spatial=True, horizontal bands of
     the large levels (plan_jobs) -- are packed onto the ranks by cost, every rank evaluates its jobs, the candidates are
     gathered to rank 0 in (level, band) order, i.e. the single-GPU candidate order, and the global NMS runs there.
@@ -302,7 +302,7 @@ def get_detections_sharded(model, img, templates, rf, img_transforms, prob_thres
     for sc in levels:
         wo, ho = resized_size(W0, H0, int(min(H0, W0) * sc))
         shapes.append((ho, wo))
-    jobs = plan_jobs(shapes, world, spatial)
+    jobs = plan_jobs(shapes, world, spatial, force_bands)        # force_bands {level: count}: test hook
     per_job = {}
     level_cache = {}
     for ji, job in enumerate(jobs):

@@ -41,12 +41,12 @@ if STAGE in ("inference", "all"):
   thr = inference_bench.threshold_for(m, img, tf, scales, 30000, dev)
   with torch.no_grad():
       single = get_detections(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev) if rank == 0 else None
-      for spatial in (False, True):
+      for spatial, force in ((False, None), (True, None), (True, {2: 3, 1: 2})):
           sharded, jobs = get_detections_sharded(m, img, tpl, inference_bench.RF, tf, prob_thresh=thr, scales=scales, device=dev,
-                                                 spatial=spatial, return_plan=True)
+                                                 spatial=spatial, return_plan=True, force_bands=force)
           if rank == 0:
               same = np.array_equal(sharded, single)
-              print("sharded inference (spatial=%s): %d jobs, %d dets, identical to single-GPU: %s" % (spatial, len(jobs), len(sharded), same), flush=True)
+              print("sharded inference (spatial=%s, forced bands %s): %d jobs, %d dets, identical to single-GPU: %s" % (spatial, force, len(jobs), len(sharded), same), flush=True)
               assert same
 if STAGE == "inference":
     dist.barrier(); dist.destroy_process_group(); sys.exit(0)
