@@ -27,6 +27,7 @@ int tf_version(void);
  *   6: 1 = backward chain on the caller's stream (no priority stream)      7: 1 = force the BN-statistics epilogue
  *   8: 2 = materialise G and reduce-add (no residual epilogue in the conv1 dgrad)
  *   9: bit 0 = bn_apply iterates descending, bit 1 = BN-backward column reduction ascending
+ *  10: 1 = 3x3 weight gradients with one accumulator tile per CTA (default: two)
  *  11: 1 = stride-2 dgrad by zero insertion (old path)      12: 1 = inference conv3 without the fused shortcut epilogue
  *  13: 1 = tf_nms counts its IoU pair tests (tf_nms_sweep_stats)   14: 1/2/3 = tf_nms stops after sort / sweep / resolution
  *      (stage timing; the result is then invalid) */

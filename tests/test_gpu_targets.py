@@ -58,7 +58,7 @@ def test_heatmaps_equal_cpu_oracle_on_random_boxes(seed, ng):
     ocls, oreg, oiou = targets_oracle.get_heatmaps(boxes.copy(), pad, synth.load_templates(), synth.RF, (63, 63), 0.7, 0.3)
     assert np.array_equal(cls, ocls) and np.array_equal(iou, oiou)
     assert np.abs(reg - oreg).max() <= 1e-13 * max(1.0, float(np.abs(oreg).max()))
-    assert (cls == 1).sum() >= 1
+    assert (cls == 1).sum() == (ocls == 1).sum() and (cls == 0).sum() == (ocls == 0).sum()
 
 
 def test_device_layout_and_device_noise():
