@@ -110,6 +110,31 @@ def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nm
                 pass
         if base == 1250:
             out["forward_tflops_per_level"] = [FWD_GFLOP_1250[s] / ms for s, ms in zip(scales, fwd_ms) if s in FWD_GFLOP_1250]
+    # the launch-bound small levels again, replayed from CUDA graphs (DetectionModel.cuda_graphs)
+    try:
+        model.cuda_graphs = True
+        gms = []
+        with torch.no_grad():
+            for s in lv:
+                x = pyr.level(s)
+                if x.shape[2] * x.shape[3] > model.cuda_graph_max_pixels:
+                    gms.append(None)
+                    continue
+                model(x)                                     # capture
+                model(x)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    model(x)
+                e1.record()
+                torch.cuda.synchronize()
+                gms.append(e0.elapsed_time(e1) / 5)
+        out["forward_ms_cuda_graph"] = gms
+    except Exception as ex:  # noqa: BLE001
+        out["forward_ms_cuda_graph"] = dict(error=str(ex)[:200])
+    finally:
+        model.cuda_graphs = False
     if was_training:
         model.train()
     return out
