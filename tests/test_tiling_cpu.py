@@ -44,3 +44,18 @@ def test_job_plan_balances_the_five_level_pyramid():
     # level sharding alone is capped near 1.33x by the 5000^2 level (25 M of 33.3 M pixels)
     jobs = plan_jobs(shapes, 8, spatial=False)
     assert len(jobs) == 5
+
+
+def test_write_results_accepts_scores(tmp_path):
+    """evaluation.py:89-114 with the score column restored (the shipped get_detections drops it, so the shipped writer
+    raises): same file format, [K,5] or [K,4] + scores."""
+    import numpy as np
+    from tinyfaces_b200.evaluation import write_results
+    dets = np.array([[10.4, 20.6, 30.2, 50.9], [0.0, 1.0, 2.0, 3.0]])
+    f = write_results(dets, "0--Parade/0_Parade_x.jpg", "val", results_dir=str(tmp_path), scores=[0.5, 2.25])
+    lines = open(f).read().splitlines()
+    assert lines == ["0_Parade_x.jpg", "2", "10 21 21 31 0.5", "0 1 3 3 2.25"]
+    f2 = write_results(np.concatenate([dets, [[0.5], [2.25]]], axis=1), "a/b.jpg", "val", results_dir=str(tmp_path))
+    assert open(f2).read().splitlines()[2:] == lines[2:]
+    with pytest.raises(ValueError):
+        write_results(dets, "a/c.jpg", "val", results_dir=str(tmp_path))

@@ -25,6 +25,9 @@ inline int ew_blocks(long long n, int per_thread = 1) {
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// streaming read (evict-first): the big activation / gradient tensors are touched once per pass and must not push the
+// per-channel coefficient vectors out of the (deliberately small, see prefer_shared_carveout) L1
+__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                 for (int u = 0; u < 4; ++u) {
                     const long long row = descending ? M - 1 - (r + u * step) : r + u * step;
                     const long long i = row * C + g * 4;
-                    v[u] = ld4(a + i); y[u] = ld4(b + i); nib[u] = mask_nibble(mask, i);
+                    v[u] = ld4s(a + i); y[u] = ld4s(b + i); nib[u] = mask_nibble(mask, i);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -255,6 +258,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
     // is still in L2, and the consumer GEMM then starts at the front, which this pass wrote last
     const long long n4_up = (n4 + 31) & ~31ll;          // whole warps iterate together (the mask needs shuffles)
     const long long nchunks = (n4_up + blockDim.x - 1) / blockDim.x;
+    // a chunk is blockDim * 4 = 1024 consecutive floats, a multiple of C (a power of two <= 1024): the channel group of a
+    // thread is the same in every chunk, so its scale / shift live in registers for the whole kernel
+    const int c = (int)((threadIdx.x * 4) & (C - 1));
+    const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    float4 ra = make_float4(1.f, 1.f, 1.f, 1.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res && rscale) { ra = ld4(rscale + c); rb = ld4(rshift + c); }
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const long long t = (descending ? nchunks - 1 - ch : ch) * blockDim.x + threadIdx.x;
         if (t >= n4_up) continue;                       // (only whole warps drop out: n4_up and blockDim are multiples of 32)
@@ -262,16 +271,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
         const bool live = t < n4;
         float4 v = make_float4(0, 0, 0, 0);
         if (live) {
-            const int c = (int)(i & (long long)(C - 1));            // C is a power of two
-            v = ld4(y + i);
-            const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+            v = ld4s(y + i);
             v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
             if (res) {
-                float4 r = ld4(res + i);
-                if (rscale) {
-                    const float4 a = ld4(rscale + c), b = ld4(rshift + c);
-                    r.x = r.x * a.x + b.x; r.y = r.y * a.y + b.y; r.z = r.z * a.z + b.z; r.w = r.w * a.w + b.w;
-                }
+                float4 r = ld4s(res + i);
+                if (rscale) { r.x = r.x * ra.x + rb.x; r.y = r.y * ra.y + rb.y; r.z = r.z * ra.z + rb.z; r.w = r.w * ra.w + rb.w; }
                 v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
             if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
@@ -298,15 +302,41 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
                                                                   const float* __restrict__ coef, long long n4, int C,
                                                                   float* __restrict__ dy, float* __restrict__ dy_lo,
                                                                   float* __restrict__ gmask_out, int mode) {
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    // blockDim * 4 = 1024 floats per block row is a multiple of C: a thread's channel group is loop-invariant, so the five
+    // per-channel vectors are read ONCE into registers (they used to be re-read from L1/L2 for every float4: 5 of the 8 loads
+    // per iteration -- with the max-shared carveout the L1 is too small to keep them next to the streamed tensors)
+    const int c = (int)((threadIdx.x * 4) & (C - 1));
+    const float4 mu = ld4(mean + c), rs = ld4(rstd + c);
+    const float4 c0 = ld4(coef + c), c1 = ld4(coef + C + c), c2 = ld4(coef + 2 * C + c);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // two independent float4 groups per iteration: all six tensor loads are issued before the first use
+    for (; t + stride < n4; t += 2 * stride) {
+        const long long i0 = t * 4, i1 = (t + stride) * 4;
+        float4 g0 = ld4s(dout + i0), g1 = ld4s(dout + i1);
+        const float4 v0 = ld4s(y + i0), v1 = ld4s(y + i1);
+        if (mask) { const unsigned int n0 = mask_nibble(mask, i0), n1 = mask_nibble(mask, i1); apply_mask(g0, n0); apply_mask(g1, n1); }
+        else if (act) {
+            const float4 o0 = ld4(act + i0), o1 = ld4(act + i1);
+            if (!(o0.x > 0.f)) g0.x = 0.f; if (!(o0.y > 0.f)) g0.y = 0.f; if (!(o0.z > 0.f)) g0.z = 0.f; if (!(o0.w > 0.f)) g0.w = 0.f;
+            if (!(o1.x > 0.f)) g1.x = 0.f; if (!(o1.y > 0.f)) g1.y = 0.f; if (!(o1.z > 0.f)) g1.z = 0.f; if (!(o1.w > 0.f)) g1.w = 0.f;
+        }
+        if (gmask_out) { st4(gmask_out + i0, g0); st4(gmask_out + i1, g1); }
+        float4 r0, r1;
+        r0.x = c0.x * (g0.x - c1.x - (v0.x - mu.x) * rs.x * c2.x); r0.y = c0.y * (g0.y - c1.y - (v0.y - mu.y) * rs.y * c2.y);
+        r0.z = c0.z * (g0.z - c1.z - (v0.z - mu.z) * rs.z * c2.z); r0.w = c0.w * (g0.w - c1.w - (v0.w - mu.w) * rs.w * c2.w);
+        r1.x = c0.x * (g1.x - c1.x - (v1.x - mu.x) * rs.x * c2.x); r1.y = c0.y * (g1.y - c1.y - (v1.y - mu.y) * rs.y * c2.y);
+        r1.z = c0.z * (g1.z - c1.z - (v1.z - mu.z) * rs.z * c2.z); r1.w = c0.w * (g1.w - c1.w - (v1.w - mu.w) * rs.w * c2.w);
+        store_act(dy, dy_lo, i0, r0, mode);
+        store_act(dy, dy_lo, i1, r1, mode);
+    }
+    for (; t < n4; t += stride) {
         const long long i = t * 4;
-        const int c = (int)(i & (long long)(C - 1));            // C is a power of two
-        float4 g = ld4(dout + i);
+        float4 g = ld4s(dout + i);
         if (mask) apply_mask(g, mask_nibble(mask, i));
         else if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
         if (gmask_out) st4(gmask_out + i, g);
-        const float4 v = ld4(y + i), mu = ld4(mean + c), rs = ld4(rstd + c);
-        const float4 c0 = ld4(coef + c), c1 = ld4(coef + C + c), c2 = ld4(coef + 2 * C + c);
+        const float4 v = ld4s(y + i);
         float4 r;
         r.x = c0.x * (g.x - c1.x - (v.x - mu.x) * rs.x * c2.x);
         r.y = c0.y * (g.y - c1.y - (v.y - mu.y) * rs.y * c2.y);
@@ -649,7 +679,7 @@ int bn_scale_shift_eval_batched(const BnEvalJob* jobs_device, int njobs, int tot
 int bn_apply(const float* y, const float* scale, const float* shift, const float* res, const float* rscale,
              const float* rshift, int relu, long long M, int C, float* out, float* out_lo, int mode, unsigned int* mask_out,
              cudaStream_t st) {
-    TF_REQUIRE(C >= 4 && (C & (C - 1)) == 0, "bn_apply: C=%d must be a power of two", C);
+    TF_REQUIRE(C >= 4 && C <= 1024 && (C & (C - 1)) == 0, "bn_apply: C=%d must be a power of two in [4, 1024]", C);
     const long long n4 = M * C / 4;
     bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out,
                                                              tfg::debug_flag(9) & 1);

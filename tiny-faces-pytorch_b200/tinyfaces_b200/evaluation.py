@@ -230,6 +230,32 @@ def get_detections(model, img, templates, rf, img_transforms, prob_thresh=0.65, 
     return dets
 
 
+def write_results(dets, img_path, split, results_dir=None, scores=None):
+    """evaluation.py:89-114 (WIDER-FACE result file: "left top width height score" per detection), made to work: the
+    shipped function reads the score from column 4 of `dets`, but its get_detections returns [K,4] boxes only (SURVEY
+    App. A), so evaluate_model.py:58-67 raises on the first detection.  Here `dets` may be [K,5] (boxes + score, as the
+    file format intends) or [K,4] with `scores` [K] passed separately -- e.g. get_detections(..., return_scores=True)."""
+    from pathlib import Path
+    dets = np.asarray(dets)
+    if dets.ndim != 2 or dets.shape[1] not in (4, 5):
+        raise ValueError("write_results: dets must be [K,4] or [K,5]")
+    if dets.shape[1] == 4:
+        if scores is None:
+            raise ValueError("write_results: [K,4] detections need `scores` (get_detections(..., return_scores=True))")
+        dets = np.concatenate([dets, np.asarray(scores, dtype=np.float64).reshape(-1, 1)], axis=1)
+    results_dir = Path(results_dir or f"{split}_results")
+    filename = results_dir / img_path.replace('jpg', 'txt')
+    filename.parent.mkdir(parents=True, exist_ok=True)
+    with open(filename, 'w') as f:
+        f.write(img_path.split('/')[-1] + "\n")
+        f.write(str(dets.shape[0]) + "\n")
+        for x in dets:
+            left, top = np.round(x[0]), np.round(x[1])
+            width, height = np.round(x[2] - x[0] + 1), np.round(x[3] - x[1] + 1)
+            f.write(f"{int(left)} {int(top)} {int(width)} {int(height)} {x[4]}\n")
+    return filename
+
+
 # ------------------------------------------------------------------------------------------------ multi-GPU
 def gather_level_candidates(per_level, num_levels, group=None, dst=0, device=None):
     """Scale-sharded inference exchange step.  ``per_level``: {level_index: (boxes [n,4] f64, scores [n] f64)} for
