@@ -30,7 +30,8 @@ int tf_version(void);
  *  10: 1 = 3x3 weight gradients with one accumulator tile per CTA (default: two)
  *  11: 1 = stride-2 dgrad by zero insertion (old path)      12: 1 = inference conv3 without the fused shortcut epilogue
  *  13: 1 = tf_nms counts its IoU pair tests (tf_nms_sweep_stats)   14: 1/2/3 = tf_nms stops after sort / sweep / resolution
- *      (stage timing; the result is then invalid) */
+ *      (stage timing; the result is then invalid)
+ *  15: bit 0 / 1 / 2 = plain instead of streaming (ld.global.cs) loads in bn_apply / bn_bwd_apply / colreduce<1> (A/B) */
 int tf_debug_set(int key, int value);
 int tf_gemm_error_flag(int* value_host);         /* HOST out: non-zero if a tcgen05 pipeline wait timed out */
 

@@ -27,7 +27,9 @@ inline int ew_blocks(long long n, int per_thread = 1) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // streaming read (evict-first): the big activation / gradient tensors are touched once per pass and must not push the
 // per-channel coefficient vectors out of the (deliberately small, see prefer_shared_carveout) L1
-__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4s(const float* p, int streaming = 1) {
+    return streaming ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+}
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
@@ -73,7 +75,8 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                                                                const unsigned int* __restrict__ mask,
                                                                const float* __restrict__ mean,
                                                                const float* __restrict__ rstd, long long M, int C,
-                                                               float* __restrict__ partial, int slots, int descending) {
+                                                               float* __restrict__ partial, int slots, int descending,
+                                                               int streaming) {
     const int groups = C / 4;                       // float4 channel groups (16 .. 256, a power of two)
     const int lanes = EW_THREADS / groups;          // row lanes per block (1 .. 16)
     const int g = threadIdx.x / lanes, rl = threadIdx.x % lanes;
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(EW_THREADS) colreduce_kernel(const float* __re
                 for (int u = 0; u < 4; ++u) {
                     const long long row = descending ? M - 1 - (r + u * step) : r + u * step;
                     const long long i = row * C + g * 4;
-                    v[u] = ld4s(a + i); y[u] = ld4s(b + i); nib[u] = mask_nibble(mask, i);
+                    v[u] = ld4s(a + i, streaming); y[u] = ld4s(b + i, streaming); nib[u] = mask_nibble(mask, i);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -253,7 +256,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
                                                               const float* __restrict__ rscale,
                                                               const float* __restrict__ rshift, int relu, long long n4,
                                                               int C, float* __restrict__ out, float* __restrict__ out_lo,
-                                                              int mode, unsigned int* __restrict__ mask_out, int descending) {
+                                                              int mode, unsigned int* __restrict__ mask_out, int descending,
+                                                              int streaming) {
     // descending: walk the tensor from its end -- the GEMM that produced y wrote it front to back, so its tail is what
     // is still in L2, and the consumer GEMM then starts at the front, which this pass wrote last
     const long long n4_up = (n4 + 31) & ~31ll;          // whole warps iterate together (the mask needs shuffles)
@@ -271,10 +275,10 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
         const bool live = t < n4;
         float4 v = make_float4(0, 0, 0, 0);
         if (live) {
-            v = ld4s(y + i);
+            v = ld4s(y + i, streaming);
             v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
             if (res) {
-                float4 r = ld4s(res + i);
+                float4 r = ld4s(res + i, streaming);
                 if (rscale) { r.x = r.x * ra.x + rb.x; r.y = r.y * ra.y + rb.y; r.z = r.z * ra.z + rb.z; r.w = r.w * ra.w + rb.w; }
                 v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
                                                                   const float* __restrict__ rstd,
                                                                   const float* __restrict__ coef, long long n4, int C,
                                                                   float* __restrict__ dy, float* __restrict__ dy_lo,
-                                                                  float* __restrict__ gmask_out, int mode) {
+                                                                  float* __restrict__ gmask_out, int mode, int streaming) {
     // blockDim * 4 = 1024 floats per block row is a multiple of C: a thread's channel group is loop-invariant, so the five
     // per-channel vectors are read ONCE into registers (they used to be re-read from L1/L2 for every float4: 5 of the 8 loads
     // per iteration -- with the max-shared carveout the L1 is too small to keep them next to the streamed tensors)
@@ -313,8 +317,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
     // two independent float4 groups per iteration: all six tensor loads are issued before the first use
     for (; t + stride < n4; t += 2 * stride) {
         const long long i0 = t * 4, i1 = (t + stride) * 4;
-        float4 g0 = ld4s(dout + i0), g1 = ld4s(dout + i1);
-        const float4 v0 = ld4s(y + i0), v1 = ld4s(y + i1);
+        float4 g0 = ld4s(dout + i0, streaming), g1 = ld4s(dout + i1, streaming);
+        const float4 v0 = ld4s(y + i0, streaming), v1 = ld4s(y + i1, streaming);
         if (mask) { const unsigned int n0 = mask_nibble(mask, i0), n1 = mask_nibble(mask, i1); apply_mask(g0, n0); apply_mask(g1, n1); }
         else if (act) {
             const float4 o0 = ld4(act + i0), o1 = ld4(act + i1);
@@ -332,11 +336,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
     }
     for (; t < n4; t += stride) {
         const long long i = t * 4;
-        float4 g = ld4s(dout + i);
+        float4 g = ld4s(dout + i, streaming);
         if (mask) apply_mask(g, mask_nibble(mask, i));
         else if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
         if (gmask_out) st4(gmask_out + i, g);
-        const float4 v = ld4s(y + i);
+        const float4 v = ld4s(y + i, streaming);
         float4 r;
         r.x = c0.x * (g.x - c1.x - (v.x - mu.x) * rs.x * c2.x);
         r.y = c0.y * (g.y - c1.y - (v.y - mu.y) * rs.y * c2.y);
@@ -682,7 +686,7 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
     TF_REQUIRE(C >= 4 && C <= 1024 && (C & (C - 1)) == 0, "bn_apply: C=%d must be a power of two in [4, 1024]", C);
     const long long n4 = M * C / 4;
     bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out,
-                                                             tfg::debug_flag(9) & 1);
+                                                             tfg::debug_flag(9) & 1, !(tfg::debug_flag(15) & 1));
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -692,18 +696,18 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
     RC_CARVEOUT(colreduce_kernel<1>); RC_CARVEOUT(bn_bwd_finalize_kernel); RC_CARVEOUT(bn_bwd_apply_kernel);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS, !((tfg::debug_flag(9) >> 1) & 1));     // descending by default (measured -0.2 ms/step); tf_debug_set(9, 2): ascending
+    colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS, !((tfg::debug_flag(9) >> 1) & 1), !(tfg::debug_flag(15) & 4));     // descending by default (measured -0.2 ms/step); tf_debug_set(9, 2): ascending
     bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(slots, nb < BN_BWD_SLOTS ? nb : BN_BWD_SLOTS, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
     bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
-                                                                gmask_out, mode);
+                                                                gmask_out, mode, !(tfg::debug_flag(15) & 2));
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
 int column_stats(const float* y, long long M, int C, float* partial, int* nblk, cudaStream_t st) {
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0 && M > 0, "column_stats: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0);
+    colreduce_kernel<0><<<nb, EW_THREADS, 0, st>>>(y, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0, 0);
     TF_LAUNCH_CHECK();
     *nblk = nb;
     return TF_OK;
@@ -712,7 +716,7 @@ int column_sum(const float* a, long long M, int C, int Cout, float* out, float* 
     RC_CARVEOUT(colreduce_kernel<2>); RC_CARVEOUT(colsum_finalize_kernel);
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "column_sum: C=%d unsupported (power of two in [64, 1024])", C);
     const int nb = reduce_blocks(M, C);
-    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0);
+    colreduce_kernel<2><<<nb, EW_THREADS, 0, st>>>(a, nullptr, nullptr, nullptr, nullptr, nullptr, M, C, partial, 0, 0, 0);
     colsum_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(partial, nb, C, Cout, out, accumulate);
     TF_LAUNCH_CHECK();
     return TF_OK;
