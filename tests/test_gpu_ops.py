@@ -19,7 +19,7 @@ def _dev():
 def _nms(boxes, scores, thr, algo=0):
     from tinyfaces_b200 import ops
     d = _dev()
-    # algo: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep (tf_nms_algo); no fallback here: an overflow must show up
+    # algo: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep, 3 size-class grid (tf_nms_algo); no fallback here: an overflow must show up
     keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr, algo)
     k = int(count.item())
     assert k >= 0, "sort-and-sweep edge list overflow"
@@ -27,7 +27,7 @@ def _nms(boxes, scores, thr, algo=0):
 
 
 # ------------------------------------------------------------------------------------------- NMS
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_case_f32", "nms_edge", "nms_allequal"])
 def test_nms_golden_bit_exact(name, algo):
     """nms_edge / nms_allequal: NaN, +-0.0, +-inf scores, heavy ties, NaN coordinates (torch.sort order: NaN first, all NaNs
@@ -40,7 +40,7 @@ def test_nms_known_answers():
     with open(os.path.join(G, "nms_known.json")) as f:
         cases = json.load(f)["cases"]
     for c in cases:
-        for algo in (1, 2):
+        for algo in (1, 2, 3):
             k = _nms(np.array(c["boxes"], np.float64), np.array(c["scores"], np.float64), c["thr"], algo)
             assert k.tolist() == c["keep"], (c, algo)
     from tinyfaces_b200 import ops
@@ -49,7 +49,7 @@ def test_nms_known_answers():
     assert keep.numel() == 0 and keep.dtype == torch.int64 and int(count.item()) == 0
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("n,extent,thr", [(1, 10.0, 0.3), (63, 50.0, 0.3), (4097, 600.0, 0.3), (20000, 1500.0, 0.5),
                                           (40000, 1800.0, 0.3), (30000, 300.0, 0.3), (20000, 1200.0, 0.0)])
 def test_nms_vs_c_oracle(n, extent, thr, algo):
@@ -72,7 +72,7 @@ def test_nms_edge_semantics_float32_and_stream_order():
     side = torch.cuda.Stream(d)
     side.wait_stream(torch.cuda.current_stream(d))
     with torch.cuda.stream(side):
-        k1, c1 = ops.nms_device(b, s, 0.3, 2)
+        k1, c1 = ops.nms_device(b, s, 0.3, 3)
         k2, c2 = ops.nms_device(b.clone(), torch.full_like(s, 0.25), 0.3, 2)       # same workspace, back to back: stream order
     side.synchronize()
     assert np.array_equal(k1[: int(c1.item())].cpu().numpy(), g["keep"])
@@ -100,6 +100,44 @@ def test_nms_sweep_overflow_is_flagged_and_falls_back():
     torch.cuda.synchronize()
     k = ops.nms_keep(b, s, 0.3)             # (falls back by itself if the shared workspace is small enough to overflow too)
     assert np.array_equal(k.cpu().numpy(), nms_oracle.nms(boxes, scores, 0.3))
+
+
+@pytest.mark.parametrize("algo", [2, 3])
+@pytest.mark.parametrize("seed,n", [(0, 20000), (1, 6000)])
+def test_nms_multiscale_dense_vs_c_oracle(seed, n, algo):
+    """Pyramid-like candidates: box sizes from 3 px to 900 px (eight size classes) packed into a 1250 px image, negative
+    coordinates, a cluster of near-duplicates, a few degenerate / huge boxes -- the size-class grid and the 1-D sweep must
+    both return the oracle's keep indices."""
+    from oracle import nms_oracle
+    r = np.random.RandomState(seed)
+    size = np.exp(r.uniform(np.log(3.0), np.log(900.0), n))
+    asp = np.exp(r.uniform(-0.7, 0.7, n))
+    w, h = size * asp, size / asp
+    c = r.rand(n, 2) * 1250.0 - 100.0
+    boxes = np.stack([c[:, 0] - w / 2, c[:, 1] - h / 2, c[:, 0] + w / 2, c[:, 1] + h / 2], axis=1)
+    k = n // 10
+    boxes[:k] = boxes[k:2 * k] + r.randn(k, 4) * 0.5                      # near-duplicates: long suppression chains
+    boxes[-5:, 2] = boxes[-5:, 0]                                         # zero width
+    boxes[-8:-5, 2:] = boxes[-8:-5, :2] + 3000.0                          # larger than the image
+    scores = np.round(r.rand(n), 3)
+    got = _nms(boxes, scores, 0.3, algo)
+    assert np.array_equal(got, nms_oracle.nms(boxes, scores, 0.3))
+
+
+def test_nms_grid_flags_sizes_outside_its_classes():
+    """A box wider than 2^16 (or narrower than 2^-16) has no size class: the grid variant flags the result (-1) and nms_keep
+    falls back to the exact bit-matrix path."""
+    from oracle import nms_oracle, synth
+    from tinyfaces_b200 import ops
+    boxes, scores = synth.synthetic_boxes(5000, seed=4, extent=400.0)
+    boxes[7] = [0.0, 0.0, 2.0e5, 50.0]
+    boxes[9] = [10.0, 10.0, 10.0 + 1e-6, 10.0 + 1e-6]
+    d = _dev()
+    b, s = torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d)
+    keep, count = ops.nms_device(b, s, 0.3, 3)
+    assert int(count.item()) == -1
+    torch.cuda.synchronize()
+    assert np.array_equal(ops.nms_keep(b, s, 0.3).cpu().numpy(), nms_oracle.nms(boxes, scores, 0.3))
 
 
 def test_nms_large_n_property():
@@ -132,7 +170,7 @@ def test_nms_negative_threshold_and_ties_small():
     """thr < 0: every later box is suppressed (ovr = 0 > thr), as in the reference; handled by the bit-matrix path."""
     from oracle import nms_oracle, synth
     boxes, scores = synth.synthetic_boxes(700, seed=3, extent=200.0)
-    for algo in (0, 1, 2):
+    for algo in (0, 1, 2, 3):
         k = _nms(boxes, scores, -0.1, algo)
         assert np.array_equal(k, nms_oracle.nms(boxes, scores, -0.1)) and len(k) == 1
 

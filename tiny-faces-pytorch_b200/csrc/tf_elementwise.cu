@@ -250,6 +250,8 @@ __global__ void __launch_bounds__(32 * FIN_LANES) colsum_finalize_kernel(float* 
 }
 
 // out = act( y*scale + shift (+ res | + res*rscale + rshift) ); optional 1-bit ReLU mask of the result
+// HOIST: per-channel vectors in registers for the whole kernel (loop-invariant channel group) instead of re-read per float4
+template <bool HOIST>
 __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ scale,
                                                               const float* __restrict__ shift,
                                                               const float* __restrict__ res,
@@ -265,9 +267,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
     // a chunk is blockDim * 4 = 1024 consecutive floats, a multiple of C (a power of two <= 1024): the channel group of a
     // thread is the same in every chunk, so its scale / shift live in registers for the whole kernel
     const int c = (int)((threadIdx.x * 4) & (C - 1));
-    const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    float4 sc = make_float4(0, 0, 0, 0), sh = sc;
     float4 ra = make_float4(1.f, 1.f, 1.f, 1.f), rb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (res && rscale) { ra = ld4(rscale + c); rb = ld4(rshift + c); }
+    if (HOIST) {
+        sc = ld4(scale + c); sh = ld4(shift + c);
+        if (res && rscale) { ra = ld4(rscale + c); rb = ld4(rshift + c); }
+    }
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const long long t = (descending ? nchunks - 1 - ch : ch) * blockDim.x + threadIdx.x;
         if (t >= n4_up) continue;                       // (only whole warps drop out: n4_up and blockDim are multiples of 32)
@@ -276,9 +281,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
         float4 v = make_float4(0, 0, 0, 0);
         if (live) {
             v = ld4s(y + i, streaming);
+            if (!HOIST) { sc = ld4(scale + c); sh = ld4(shift + c); }
             v.x = v.x * sc.x + sh.x; v.y = v.y * sc.y + sh.y; v.z = v.z * sc.z + sh.z; v.w = v.w * sc.w + sh.w;
             if (res) {
                 float4 r = ld4s(res + i, streaming);
+                if (!HOIST && rscale) { ra = ld4(rscale + c); rb = ld4(rshift + c); }
                 if (rscale) { r.x = r.x * ra.x + rb.x; r.y = r.y * ra.y + rb.y; r.z = r.z * ra.z + rb.z; r.w = r.w * ra.w + rb.w; }
                 v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
             }
@@ -297,6 +304,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __res
 }
 
 // dy = coef0 * (g - coef1 - xhat*coef2),  g = dout (* [act > 0]);  optionally gmask_out = g (identity branch)
+template <bool HOIST>
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ dout,
                                                                   const float* __restrict__ act,
                                                                   const unsigned int* __restrict__ mask,
@@ -310,8 +318,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
     // per-channel vectors are read ONCE into registers (they used to be re-read from L1/L2 for every float4: 5 of the 8 loads
     // per iteration -- with the max-shared carveout the L1 is too small to keep them next to the streamed tensors)
     const int c = (int)((threadIdx.x * 4) & (C - 1));
-    const float4 mu = ld4(mean + c), rs = ld4(rstd + c);
-    const float4 c0 = ld4(coef + c), c1 = ld4(coef + C + c), c2 = ld4(coef + 2 * C + c);
+    float4 mu, rs, c0, c1, c2;
+    if (HOIST) { mu = ld4(mean + c); rs = ld4(rstd + c); c0 = ld4(coef + c); c1 = ld4(coef + C + c); c2 = ld4(coef + 2 * C + c); }
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // two independent float4 groups per iteration: all six tensor loads are issued before the first use
@@ -326,6 +334,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
             if (!(o1.x > 0.f)) g1.x = 0.f; if (!(o1.y > 0.f)) g1.y = 0.f; if (!(o1.z > 0.f)) g1.z = 0.f; if (!(o1.w > 0.f)) g1.w = 0.f;
         }
         if (gmask_out) { st4(gmask_out + i0, g0); st4(gmask_out + i1, g1); }
+        if (!HOIST) { mu = ld4(mean + c); rs = ld4(rstd + c); c0 = ld4(coef + c); c1 = ld4(coef + C + c); c2 = ld4(coef + 2 * C + c); }
         float4 r0, r1;
         r0.x = c0.x * (g0.x - c1.x - (v0.x - mu.x) * rs.x * c2.x); r0.y = c0.y * (g0.y - c1.y - (v0.y - mu.y) * rs.y * c2.y);
         r0.z = c0.z * (g0.z - c1.z - (v0.z - mu.z) * rs.z * c2.z); r0.w = c0.w * (g0.w - c1.w - (v0.w - mu.w) * rs.w * c2.w);
@@ -341,6 +350,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
         else if (act) { float4 o = ld4(act + i); if (!(o.x > 0.f)) g.x = 0.f; if (!(o.y > 0.f)) g.y = 0.f; if (!(o.z > 0.f)) g.z = 0.f; if (!(o.w > 0.f)) g.w = 0.f; }
         if (gmask_out) st4(gmask_out + i, g);
         const float4 v = ld4s(y + i, streaming);
+        if (!HOIST) { mu = ld4(mean + c); rs = ld4(rstd + c); c0 = ld4(coef + c); c1 = ld4(coef + C + c); c2 = ld4(coef + 2 * C + c); }
         float4 r;
         r.x = c0.x * (g.x - c1.x - (v.x - mu.x) * rs.x * c2.x);
         r.y = c0.y * (g.y - c1.y - (v.y - mu.y) * rs.y * c2.y);
@@ -685,8 +695,12 @@ int bn_apply(const float* y, const float* scale, const float* shift, const float
              cudaStream_t st) {
     TF_REQUIRE(C >= 4 && C <= 1024 && (C & (C - 1)) == 0, "bn_apply: C=%d must be a power of two in [4, 1024]", C);
     const long long n4 = M * C / 4;
-    bn_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out,
-                                                             tfg::debug_flag(9) & 1, !(tfg::debug_flag(15) & 1));
+    if (tfg::debug_flag(15) & 8)
+        bn_apply_kernel<true><<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out,
+                                                                       tfg::debug_flag(9) & 1, !(tfg::debug_flag(15) & 1));
+    else
+        bn_apply_kernel<false><<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(y, scale, shift, res, rscale, rshift, relu, n4, C, out, out_lo, mode, mask_out,
+                                                                        tfg::debug_flag(9) & 1, !(tfg::debug_flag(15) & 1));
     TF_LAUNCH_CHECK();
     return TF_OK;
 }
@@ -694,13 +708,17 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
                 const float* gamma, long long M, int C, float* dgamma, float* dbeta, float* dy, float* dy_lo,
                 float* gmask_out, int mode, float* slots /* [BN_BWD_SLOTS][2][C], zero on entry, left zeroed */, float* coef, cudaStream_t st) {
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
-    RC_CARVEOUT(colreduce_kernel<1>); RC_CARVEOUT(bn_bwd_finalize_kernel); RC_CARVEOUT(bn_bwd_apply_kernel);
+    RC_CARVEOUT(colreduce_kernel<1>); RC_CARVEOUT(bn_bwd_finalize_kernel); RC_CARVEOUT(bn_bwd_apply_kernel<true>); RC_CARVEOUT(bn_bwd_apply_kernel<false>);
     const int nb = reduce_blocks(M, C);
     colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS, !((tfg::debug_flag(9) >> 1) & 1), !(tfg::debug_flag(15) & 4));     // descending by default (measured -0.2 ms/step); tf_debug_set(9, 2): ascending
     bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(slots, nb < BN_BWD_SLOTS ? nb : BN_BWD_SLOTS, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;
-    bn_bwd_apply_kernel<<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
-                                                                gmask_out, mode, !(tfg::debug_flag(15) & 2));
+    if (tfg::debug_flag(15) & 16)          // A/B: per-channel vectors re-read per float4 (round-1 form)
+        bn_bwd_apply_kernel<false><<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
+                                                                           gmask_out, mode, !(tfg::debug_flag(15) & 2));
+    else
+        bn_bwd_apply_kernel<true><<<ew_blocks(n4, 2), EW_THREADS, 0, st>>>(dout, act, mask, y, save_mean, save_rstd, coef, n4, C, dy, dy_lo,
+                                                                          gmask_out, mode, !(tfg::debug_flag(15) & 2));
     TF_LAUNCH_CHECK();
     return TF_OK;
 }

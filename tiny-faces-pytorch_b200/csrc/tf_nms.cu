@@ -247,7 +247,7 @@ namespace tfnms {
 size_t sweep_workspace_bytes(int64_t n, int elem_bytes);
 template <typename T>
 int run_nms_sweep(const void* boxes, const void* scores, int64_t n, double thr, long long* keep, long long* num_keep,
-                  void* ws, size_t ws_bytes, cudaStream_t st);
+                  void* ws, size_t ws_bytes, cudaStream_t st, int use_grid);
 template <typename T>
 int sweep_stats(int64_t n, void* ws, size_t ws_bytes, long long* out4, cudaStream_t st);
 }
@@ -257,7 +257,7 @@ TF_API int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int ele
 
 // test hook: 0 = automatic choice, 1 = force the blocked bit-matrix path, 2 = force the sort-and-sweep path
 TF_API int tf_nms_set_algorithm(int algo) {
-    TF_REQUIRE(algo >= 0 && algo <= 2, "tf_nms_set_algorithm: bad value");
+    TF_REQUIRE(algo >= 0 && algo <= 3, "tf_nms_set_algorithm: bad value");
     g_nms_algo = algo;
     return TF_OK;
 }
@@ -276,22 +276,23 @@ TF_API int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_byt
     return tf_nms_algo(boxes, scores, n, elem_bytes, iou_threshold, g_nms_algo, keep, num_keep, workspace, workspace_bytes, stream);
 }
 
-// algorithm: 0 = automatic (sort-and-sweep for n >= 4096 and thr >= 0, else the blocked bit-matrix), 1 = blocked bit-matrix,
-// 2 = sort-and-sweep.  Purely stream-ordered (graph-capturable): the sort-and-sweep path reports an edge list that does
+// algorithm: 0 = automatic (size-class grid for n >= 4096 and thr >= 0, else the blocked bit-matrix), 1 = blocked bit-matrix,
+// 2 = candidate generation by a 1-D sort-and-sweep along x, 3 = by the size-class grid (both: parallel fixed-point resolution).  Purely stream-ordered (graph-capturable): the sort-and-sweep path reports an edge list that does
 // not fit the workspace as *num_keep = -1 ON THE DEVICE; the caller, who has to read the count anyway before it can use
 // `keep`, then calls again with algorithm 1 (exact for every input) or a larger workspace.
 TF_API int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int algorithm,
                        int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
     TF_REQUIRE(n >= 0 && n < (1ll << 31) && (elem_bytes == 8 || elem_bytes == 4), "tf_nms: bad args");
-    TF_REQUIRE(num_keep && algorithm >= 0 && algorithm <= 2, "tf_nms: num_keep is null / bad algorithm");
+    TF_REQUIRE(num_keep && algorithm >= 0 && algorithm <= 3, "tf_nms: num_keep is null / bad algorithm");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { TF_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st)); return TF_OK; }
     TF_REQUIRE(boxes && scores && keep && workspace, "tf_nms: null pointer");
-    const bool sweep = iou_threshold >= 0.0 && (algorithm == 2 || (algorithm == 0 && n >= SWEEP_MIN_N));
+    const bool sweep = iou_threshold >= 0.0 && (algorithm >= 2 || (algorithm == 0 && n >= SWEEP_MIN_N));
+    const int use_grid = algorithm != 2;             // automatic choice: the size-class grid
     if (sweep)
         return elem_bytes == 8
-            ? tfnms::run_nms_sweep<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st)
-            : tfnms::run_nms_sweep<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
+            ? tfnms::run_nms_sweep<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st, use_grid)
+            : tfnms::run_nms_sweep<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st, use_grid);
     if (elem_bytes == 8)
         return run_nms<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);
     return run_nms<float>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st);

@@ -106,6 +106,11 @@ def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nm
         if not overflow:
             try:
                 out["nms_stats"] = ops.nms_sweep_stats(n, 8, dev)
+                ev[0].record()
+                ops.nms_device(bx, sx, nms_thresh, 2)
+                ev[1].record()
+                torch.cuda.synchronize()
+                out["nms_ms_with_1d_sweep_candidates"] = ev[0].elapsed_time(ev[1])
             except Exception:  # noqa: BLE001
                 pass
         if base == 1250:
