@@ -318,7 +318,7 @@ def nms_report(dev, n, pk, with_cpu):
     bx, sc = synthetic.boxes(n, seed=0, extent=NMS_EXTENT_FACTOR * 40.0 * math.sqrt(n / 4.0))
     bxd, scd = bx.to(dev), sc.to(dev)
     t_all = _event_time(lambda: ops.nms_device(bxd, scd, 0.3), 10)
-    t_sweep1d = _event_time(lambda: ops.nms_device(bxd, scd, 0.3, 2), 10)          # candidate generation by the 1-D x sweep instead of the grid
+    t_grid = _event_time(lambda: ops.nms_device(bxd, scd, 0.3, 3), 10)             # candidate generation by the size-class grid instead
     keep, cnt = ops.nms_device(bxd, scd, 0.3)
     k = int(cnt.item())
     stages = {}
@@ -338,8 +338,9 @@ def nms_report(dev, n, pk, with_cpu):
                          "resolve": (stages["+resolve"] - stages["+sweep"]) * 1e3, "select": (t_all - stages["+resolve"]) * 1e3},
                conflict_edges=st["edges"], resolve_rounds=st["rounds"], iou_pair_tests=st["pair_tests"],
                pair_tests_per_s=st["pair_tests"] / t_all, all_pairs=n * (n - 1) // 2,
-               algorithm="size-class grid candidates + parallel fixed-point resolution (stream-ordered, no host sync)",
-               ms_with_1d_sweep_candidates=t_sweep1d * 1e3,
+               algorithm="shared-memory-tiled sort-and-sweep candidates (size-class grid above 3e5 boxes) + parallel fixed-point "
+                         "resolution; stream-ordered, no host sync",
+               ms_with_grid_candidates=t_grid * 1e3,
                algorithmic_bytes=nbytes, algorithmic_gbs=nbytes / t_all / 1e9, hbm_frac=nbytes / t_all / 1e9 / pk["hbm_gbs"],
                bound="latency / pair tests: %d dependent launches move %.0f MB -- the HBM roofline is not the limiter above N ~ 1e4 "
                      "(SURVEY 8d); boxes/s and pair tests/s are the honest figures" % (20, nbytes / 1e6))

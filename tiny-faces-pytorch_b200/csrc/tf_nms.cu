@@ -257,7 +257,7 @@ TF_API int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int ele
 
 // test hook: 0 = automatic choice, 1 = force the blocked bit-matrix path, 2 = force the sort-and-sweep path
 TF_API int tf_nms_set_algorithm(int algo) {
-    TF_REQUIRE(algo >= 0 && algo <= 3, "tf_nms_set_algorithm: bad value");
+    TF_REQUIRE(algo >= 0 && algo <= 4, "tf_nms_set_algorithm: bad value");
     g_nms_algo = algo;
     return TF_OK;
 }
@@ -283,12 +283,14 @@ TF_API int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_byt
 TF_API int tf_nms_algo(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int algorithm,
                        int64_t* keep, int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
     TF_REQUIRE(n >= 0 && n < (1ll << 31) && (elem_bytes == 8 || elem_bytes == 4), "tf_nms: bad args");
-    TF_REQUIRE(num_keep && algorithm >= 0 && algorithm <= 3, "tf_nms: num_keep is null / bad algorithm");
+    TF_REQUIRE(num_keep && algorithm >= 0 && algorithm <= 4, "tf_nms: num_keep is null / bad algorithm");
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { TF_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int64_t), st)); return TF_OK; }
     TF_REQUIRE(boxes && scores && keep && workspace, "tf_nms: null pointer");
     const bool sweep = iou_threshold >= 0.0 && (algorithm >= 2 || (algorithm == 0 && n >= SWEEP_MIN_N));
-    const int use_grid = algorithm != 2;             // automatic choice: the size-class grid
+    // candidate generation: 2 = tiled 1-D sweep, 3 = size-class grid, 4 = per-warp 1-D sweep (A/B); automatic: the tiled sweep up to
+    // 3*10^5 boxes, the grid above (measured on B200: the sweep's visits grow like N^2 / extent, the grid's like N)
+    const int use_grid = algorithm == 3 ? 1 : (algorithm == 4 ? -1 : (algorithm == 2 ? 0 : (n > 300000 ? 1 : 0)));
     if (sweep)
         return elem_bytes == 8
             ? tfnms::run_nms_sweep<double>(boxes, scores, n, iou_threshold, (long long*)keep, (long long*)num_keep, workspace, workspace_bytes, st, use_grid)

@@ -106,11 +106,14 @@ def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nm
         if not overflow:
             try:
                 out["nms_stats"] = ops.nms_sweep_stats(n, 8, dev)
-                ev[0].record()
-                ops.nms_device(bx, sx, nms_thresh, 2)
-                ev[1].record()
-                torch.cuda.synchronize()
-                out["nms_ms_with_1d_sweep_candidates"] = ev[0].elapsed_time(ev[1])
+                out["nms_ms_by_algorithm"] = {}
+                for algo, name in ((2, "tiled 1-D sweep"), (3, "size-class grid"), (4, "per-warp 1-D sweep (round-2 first version)")):
+                    ops.nms_device(bx, sx, nms_thresh, algo)
+                    ev[0].record()
+                    ops.nms_device(bx, sx, nms_thresh, algo)
+                    ev[1].record()
+                    torch.cuda.synchronize()
+                    out["nms_ms_by_algorithm"][name] = ev[0].elapsed_time(ev[1])
             except Exception:  # noqa: BLE001
                 pass
         if base == 1250:

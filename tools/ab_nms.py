@@ -10,7 +10,7 @@ from tinyfaces_b200._lib import lib
 dev = torch.device("cuda:0")
 def run(tag, b, s):
     out = dict(set=tag, n=int(b.shape[0]))
-    for algo in (3, 2):
+    for algo in (2, 3, 4):
         t = bench._event_time(lambda: ops.nms_device(b, s, 0.3, algo), 10)
         keep, cnt = ops.nms_device(b, s, 0.3, algo)
         out["ms_algo%d" % algo] = round(t * 1e3, 3); out["kept_algo%d" % algo] = int(cnt.item())
@@ -26,4 +26,4 @@ for n in (100000, 1000000):
 b, s = synthetic.boxes(100000, seed=0); run("random 61% kept (round-1 set)", b.to(dev), s.to(dev))
 m = inference_bench.make_calibrated_model(dev)
 r = inference_bench.run(m, base=1250, target_candidates=100000, reps=1)
-print(json.dumps({k: r[k] for k in ("candidates", "kept", "nms_ms", "nms_ms_with_1d_sweep_candidates", "nms_stats") if k in r}), flush=True)
+print(json.dumps({k: r[k] for k in ("candidates", "kept", "nms_ms", "nms_ms_by_algorithm", "nms_stats") if k in r}), flush=True)
