@@ -338,8 +338,8 @@ def nms_report(dev, n, pk, with_cpu):
                          "resolve": (stages["+resolve"] - stages["+sweep"]) * 1e3, "select": (t_all - stages["+resolve"]) * 1e3},
                conflict_edges=st["edges"], resolve_rounds=st["rounds"], iou_pair_tests=st["pair_tests"],
                pair_tests_per_s=st["pair_tests"] / t_all, all_pairs=n * (n - 1) // 2,
-               algorithm="shared-memory-tiled sort-and-sweep candidates (size-class grid above 3e5 boxes) + parallel fixed-point "
-                         "resolution; stream-ordered, no host sync",
+               algorithm="sort-and-sweep candidates (size-class grid above 3e5 boxes) + parallel fixed-point resolution; "
+                         "stream-ordered, no host sync",
                ms_with_grid_candidates=t_grid * 1e3,
                algorithmic_bytes=nbytes, algorithmic_gbs=nbytes / t_all / 1e9, hbm_frac=nbytes / t_all / 1e9 / pk["hbm_gbs"],
                bound="latency / pair tests: %d dependent launches move %.0f MB -- the HBM roofline is not the limiter above N ~ 1e4 "

@@ -40,12 +40,12 @@ int tf_gemm_error_flag(int* value_host);         /* HOST out: non-zero if a tcge
  * kept ORIGINAL indices in descending-score order; num_keep is a device int64.  Bit-identical to the CPU op:
  * stable descending sort, area (x2-x1)*(y2-y1), suppress iff inter/(a_i+a_j-inter) > thr. */
 int tf_nms_workspace_bytes(int64_t n, int elem_bytes, size_t* bytes_host);
-int tf_nms_set_algorithm(int algo);   /* test hook: 0 auto, 1 blocked bit-matrix, 2 tiled sweep, 3 size-class grid, 4 per-warp sweep */
+int tf_nms_set_algorithm(int algo);   /* test hook: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep, 3 size-class grid */
 int tf_nms(const void* boxes, const void* scores, int64_t n, int elem_bytes, double iou_threshold, int64_t* keep,
            int64_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
-/* tf_nms with an explicit algorithm (0 auto, 1 blocked bit-matrix; 2 / 3 / 4: conflict edges from the shared-memory-tiled 1-D
- * sweep / the size-class grid / the per-warp 1-D sweep, then parallel fixed-point resolution; auto = 2 for 4096 <= n <= 3e5,
- * 3 above, 1 below or when thr < 0).  Both entry
+/* tf_nms with an explicit algorithm (0 auto, 1 blocked bit-matrix; 2 / 3: conflict edges from a 1-D sort-and-sweep along x /
+ * from the size-class grid, then parallel fixed-point resolution; auto = 2 for 4096 <= n <= 3e5, 3 above, 1 below or when
+ * thr < 0).  Both entry
  * points only ENQUEUE work on `stream` (no host synchronisation, graph-capturable).  The sort-and-sweep path keeps its
  * conflict-edge list in the workspace (default capacity 128 edges per box; a larger workspace is used in full): if the
  * list overflows (or, for the grid, a box is larger than 2^16 / smaller than 2^-16), *num_keep is set to -1 on the device and

@@ -19,7 +19,7 @@ def _dev():
 def _nms(boxes, scores, thr, algo=0):
     from tinyfaces_b200 import ops
     d = _dev()
-    # algo: 0 auto, 1 blocked bit-matrix, 2 tiled sort-and-sweep, 3 size-class grid, 4 per-warp sweep (tf_nms_algo); no fallback here
+    # algo: 0 auto, 1 blocked bit-matrix, 2 sort-and-sweep, 3 size-class grid (tf_nms_algo); no fallback here
     keep, count = ops.nms_device(torch.from_numpy(boxes).to(d), torch.from_numpy(scores).to(d), thr, algo)
     k = int(count.item())
     assert k >= 0, "sort-and-sweep edge list overflow"
@@ -27,7 +27,7 @@ def _nms(boxes, scores, thr, algo=0):
 
 
 # ------------------------------------------------------------------------------------------- NMS
-@pytest.mark.parametrize("algo", [1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("name", ["nms_case0", "nms_case1", "nms_case2", "nms_case_f32", "nms_edge", "nms_allequal"])
 def test_nms_golden_bit_exact(name, algo):
     """nms_edge / nms_allequal: NaN, +-0.0, +-inf scores, heavy ties, NaN coordinates (torch.sort order: NaN first, all NaNs
@@ -40,7 +40,7 @@ def test_nms_known_answers():
     with open(os.path.join(G, "nms_known.json")) as f:
         cases = json.load(f)["cases"]
     for c in cases:
-        for algo in (1, 2, 3, 4):
+        for algo in (1, 2, 3):
             k = _nms(np.array(c["boxes"], np.float64), np.array(c["scores"], np.float64), c["thr"], algo)
             assert k.tolist() == c["keep"], (c, algo)
     from tinyfaces_b200 import ops
@@ -49,7 +49,7 @@ def test_nms_known_answers():
     assert keep.numel() == 0 and keep.dtype == torch.int64 and int(count.item()) == 0
 
 
-@pytest.mark.parametrize("algo", [1, 2, 3, 4])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("n,extent,thr", [(1, 10.0, 0.3), (63, 50.0, 0.3), (4097, 600.0, 0.3), (20000, 1500.0, 0.5),
                                           (40000, 1800.0, 0.3), (30000, 300.0, 0.3), (20000, 1200.0, 0.0)])
 def test_nms_vs_c_oracle(n, extent, thr, algo):
@@ -102,7 +102,7 @@ def test_nms_sweep_overflow_is_flagged_and_falls_back():
     assert np.array_equal(k.cpu().numpy(), nms_oracle.nms(boxes, scores, 0.3))
 
 
-@pytest.mark.parametrize("algo", [2, 3, 4])
+@pytest.mark.parametrize("algo", [2, 3])
 @pytest.mark.parametrize("seed,n", [(0, 20000), (1, 6000)])
 def test_nms_multiscale_dense_vs_c_oracle(seed, n, algo):
     """Pyramid-like candidates: box sizes from 3 px to 900 px (eight size classes) packed into a 1250 px image, negative

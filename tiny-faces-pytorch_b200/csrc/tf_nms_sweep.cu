@@ -86,6 +86,9 @@ __global__ void gather_x_kernel(const Box<T>* __restrict__ sb, const T* __restri
 // One WARP per box a (position p in x order): the 32 lanes test 32 consecutive x-successors per step, so dense
 // inputs (real detections overlap thousands of x-neighbours) stay parallel.  Conflicts go to the edge list as
 // (earlier rank, later rank); entries past the capacity are counted but not stored (the result is then flagged).
+// (A variant that staged the successor records of 8 consecutive boxes through shared memory -- one L2 read per block instead
+// of one per warp -- was measured and removed: 0.97 vs 0.85 ms at 10^5 random boxes, 7.4 vs 4.6 ms on dense pyramid candidates:
+// the block waits for its slowest warp and pays two barriers per tile, and the L2 is not what limits the per-warp version.)
 // One WARP per box a (position p in x order).  Phase 1 (cheap, every lane busy): the 32 lanes filter 32 consecutive
 // x-successors per step on the 16-byte records and push the survivors into a per-warp queue in shared memory.  Phase 2
 // (expensive, fp64 with a division): whenever 32 survivors are queued, every lane runs one exact IoU test.  Without the
@@ -168,71 +171,6 @@ __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ x
 }
 
 
-
-// The same sweep with the successor records staged through shared memory: the 8 warps of a block own 8 CONSECUTIVE boxes
-// of the x order, whose successor ranges overlap almost completely, so every 256-record tile is read from L2 once per
-// block instead of once per warp.  (The per-warp version above moved 16 B x ~180 M visits = 2.9 GB through L2 for 10^5
-// boxes -- it ran at the L2->SM bandwidth, not at the latency or the fp64 rate.)
-template <typename T>
-__global__ void __launch_bounds__(256) sweep_tiled_kernel(const Box<T>* __restrict__ xb, const T* __restrict__ xarea,
-                                                          const SweepRec* __restrict__ rec, int n,
-                                                          double thr, unsigned long long* __restrict__ scalars,
-                                                          int2* __restrict__ edges, unsigned long long cap, int count_pairs) {
-    __shared__ SweepRec tile[256];
-    __shared__ int queue[8][64];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * 8 + warp;           // this warp's box (position in x order)
-    int* wq = queue[warp];
-    bool done = p >= n;                            // warp-uniform
-    SweepRec ra = {0.f, 0.f, 0.f, 0};
-    Box<T> A = {};
-    T aa = 0;
-    float ax2 = 0.f;
-    int a = 0;
-    if (!done) { ra = rec[p]; a = ra.rank; A = xb[p]; aa = xarea[p]; ax2 = xkey_of(A.x2); if (!(ax2 == ax2)) done = true; }   // NaN x2: no candidates
-    unsigned int tested = 0;
-    int qn = 0;
-    for (int base = blockIdx.x * 8 + 1; base < n; base += 256) {
-        if (__syncthreads_and(done)) break;        // (also: every warp has finished with the previous tile)
-        if (base + (int)threadIdx.x < n) tile[threadIdx.x] = rec[base + threadIdx.x];
-        __syncthreads();
-        if (done) continue;
-        const int cnt = min(256, n - base);
-        for (int j = 0; j < cnt; j += 32) {
-            const int t = j + lane, q = base + t;
-            bool past = false, pass = false;
-            if (t < cnt) {
-                const SweepRec rq = tile[t];
-                past = !(rq.x1 <= ax2);            // x order: once past the x range, so is everything after
-                pass = !past && q > p && rq.ylo < ra.yhi && ra.ylo < rq.yhi;
-            }
-            const unsigned int m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-                if (pass) wq[qn + __popc(m & ((1u << lane) - 1u))] = q;
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    const int cand = wq[lane];
-                    const int spill = lane + 32 < qn ? wq[lane + 32] : 0;
-                    __syncwarp();
-                    if (lane + 32 < qn) wq[lane] = spill;
-                    qn -= 32;
-                    __syncwarp();
-                    sweep_exact<T>(xb, xarea, rec, A, aa, a, cand, true, thr, lane, scalars, edges, cap, tested);
-                }
-            }
-            if (__any_sync(0xffffffffu, past)) { done = true; break; }
-        }
-    }
-    if (qn > 0) {
-        const int cand = lane < qn ? wq[lane] : 0;
-        sweep_exact<T>(xb, xarea, rec, A, aa, a, cand, lane < qn, thr, lane, scalars, edges, cap, tested);
-    }
-    if (count_pairs) {
-        tested = (unsigned int)tf_warp_sum((int)tested);
-        if (lane == 0 && tested) atomicAdd(scalars + SC_PAIRS, (unsigned long long)tested);
-    }
-}
 
 template <typename T>
 __device__ __forceinline__ void grid_exact(const Box<T>* __restrict__ xb, const T* __restrict__ xarea, const int* __restrict__ gorder,
@@ -614,10 +552,7 @@ int run_nms_sweep(const void* boxes, const void* scores, int64_t n64, double thr
     gather_x_kernel<T><<<nb, 256, 0, st>>>(sb, area, xorder, xsorted, n, xb, xarea, rec);
     if (stop_after == 1) { TF_LAUNCH_CHECK(); return TF_OK; }
     const int sweep_blocks = (int)(((long long)n * 32 + 255) / 256);
-    if (use_grid < 0)          // algorithm 4: the per-warp sweep without shared-memory tiles (A/B)
-        sweep_kernel<T><<<sweep_blocks, 256, 0, st>>>(xb, xarea, rec, n, thr, scalars, edges0, (unsigned long long)plan.edge_cap, tfg::debug_flag(13));
-    else
-        sweep_tiled_kernel<T><<<(n + 7) / 8, 256, 0, st>>>(xb, xarea, rec, n, thr, scalars, edges0, (unsigned long long)plan.edge_cap, tfg::debug_flag(13));
+    sweep_kernel<T><<<sweep_blocks, 256, 0, st>>>(xb, xarea, rec, n, thr, scalars, edges0, (unsigned long long)plan.edge_cap, tfg::debug_flag(13));
     }
     if (stop_after == 2) { TF_LAUNCH_CHECK(); return TF_OK; }
     {

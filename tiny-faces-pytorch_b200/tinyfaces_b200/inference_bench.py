@@ -107,7 +107,7 @@ def run(model, base=1250, scales=(-2, -1, 0, 1, 2), target_candidates=100000, nm
             try:
                 out["nms_stats"] = ops.nms_sweep_stats(n, 8, dev)
                 out["nms_ms_by_algorithm"] = {}
-                for algo, name in ((2, "tiled 1-D sweep"), (3, "size-class grid"), (4, "per-warp 1-D sweep (round-2 first version)")):
+                for algo, name in ((2, "1-D sweep"), (3, "size-class grid")):
                     ops.nms_device(bx, sx, nms_thresh, algo)
                     ev[0].record()
                     ops.nms_device(bx, sx, nms_thresh, algo)
