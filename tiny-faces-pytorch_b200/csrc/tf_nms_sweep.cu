@@ -135,30 +135,39 @@ __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ x
     const float ax2 = xkey_of(A.x2);               // NaN: every comparison fails -> no candidates (such a box never conflicts)
     unsigned int tested = 0;
     int qn = 0;                                    // queued survivors (warp-uniform, < 32 at the top of every step)
-    for (int base = p + 1; base < n; base += 32) {
-        const int q = base + lane;
-        bool live = false, pass = false;
-        if (q < n) {
-            const SweepRec rq = rec[q];
-            live = rq.x1 <= ax2;                   // x order: once this fails, it fails for every later q
-            pass = live && rq.ylo < ra.yhi && ra.ylo < rq.yhi;         // widened float y ranges: a superset of the exact test
-        }
-        const unsigned int m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            if (pass) wq[qn + __popc(m & ((1u << lane) - 1u))] = q;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                const int cand = wq[lane];
-                const int spill = lane + 32 < qn ? wq[lane + 32] : 0;
+    // 64 successors per step (two records per lane, both loads issued before either is used): the loop is a chain of L2
+    // round trips -- the next records are only requested once the warp knows that the x range goes on -- so twice the
+    // records per trip is (nearly) twice the speed
+    for (int base = p + 1; base < n; base += 64) {
+        const int qa = base + lane, qb = base + 32 + lane;
+        SweepRec r0 = {0.f, 0.f, 0.f, 0}, r1 = r0;
+        if (qa < n) r0 = rec[qa];
+        if (qb < n) r1 = rec[qb];
+        const bool live0 = qa < n && r0.x1 <= ax2;         // x order: once this fails, it fails for every later q
+        const bool live1 = qb < n && r1.x1 <= ax2;
+        const bool pass0 = live0 && r0.ylo < ra.yhi && ra.ylo < r0.yhi;      // widened float y ranges: a superset of the exact test
+        const bool pass1 = live1 && r1.ylo < ra.yhi && ra.ylo < r1.yhi;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool pass = h ? pass1 : pass0;
+            const int q = h ? qb : qa;
+            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                if (pass) wq[qn + __popc(m & ((1u << lane) - 1u))] = q;
+                qn += __popc(m);
                 __syncwarp();
-                if (lane + 32 < qn) wq[lane] = spill;                  // move the overflow to the front
-                qn -= 32;
-                __syncwarp();
-                sweep_exact<T>(xb, xarea, rec, A, aa, a, cand, true, thr, lane, scalars, edges, cap, tested);
+                if (qn >= 32) {
+                    const int cand = wq[lane];
+                    const int spill = lane + 32 < qn ? wq[lane + 32] : 0;
+                    __syncwarp();
+                    if (lane + 32 < qn) wq[lane] = spill;                  // move the overflow to the front
+                    qn -= 32;
+                    __syncwarp();
+                    sweep_exact<T>(xb, xarea, rec, A, aa, a, cand, true, thr, lane, scalars, edges, cap, tested);
+                }
             }
         }
-        if (!__shfl_sync(0xffffffffu, (int)live, 31)) break;       // lane 31 past the x range: so is everything after
+        if (!__shfl_sync(0xffffffffu, (int)live1, 31)) break;      // lane 31 of the second group past the x range: so is everything after
     }
     if (qn > 0) {
         const int cand = lane < qn ? wq[lane] : 0;
