@@ -709,7 +709,11 @@ int bn_backward(const float* dout, const float* act, const unsigned int* mask, c
                 float* gmask_out, int mode, float* slots /* [BN_BWD_SLOTS][2][C], zero on entry, left zeroed */, float* coef, cudaStream_t st) {
     TF_REQUIRE(C >= 64 && C <= 1024 && (C & (C - 1)) == 0, "bn_backward: C=%d unsupported (power of two in [64, 1024])", C);
     RC_CARVEOUT(colreduce_kernel<1>); RC_CARVEOUT(bn_bwd_finalize_kernel); RC_CARVEOUT(bn_bwd_apply_kernel<true>); RC_CARVEOUT(bn_bwd_apply_kernel<false>);
-    const int nb = reduce_blocks(M, C);
+    int nb = reduce_blocks(M, C);
+    if (tfg::debug_flag(15) & 32) {          // A/B: twice the blocks (the slot accumulation does not depend on the block count)
+        const int lanes = EW_THREADS / (C / 4);
+        nb = (int)std::min<long long>(std::max<long long>((M + (long long)lanes * 4 - 1) / ((long long)lanes * 4), 1), 2 * COLREDUCE_MAX_BLOCKS);
+    }
     colreduce_kernel<1><<<nb, EW_THREADS, 0, st>>>(dout, y, act, mask, save_mean, save_rstd, M, C, slots, BN_BWD_SLOTS, !((tfg::debug_flag(9) >> 1) & 1), !(tfg::debug_flag(15) & 4));     // descending by default (measured -0.2 ms/step); tf_debug_set(9, 2): ascending
     bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_LANES), 0, st>>>(slots, nb < BN_BWD_SLOTS ? nb : BN_BWD_SLOTS, C, M, gamma, save_rstd, dgamma, dbeta, coef);
     const long long n4 = M * C / 4;

@@ -135,25 +135,31 @@ __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ x
     const float ax2 = xkey_of(A.x2);               // NaN: every comparison fails -> no candidates (such a box never conflicts)
     unsigned int tested = 0;
     int qn = 0;                                    // queued survivors (warp-uniform, < 32 at the top of every step)
-    // 64 successors per step (two records per lane, both loads issued before either is used): the loop is a chain of L2
-    // round trips -- the next records are only requested once the warp knows that the x range goes on -- so twice the
-    // records per trip is (nearly) twice the speed
-    for (int base = p + 1; base < n; base += 64) {
-        const int qa = base + lane, qb = base + 32 + lane;
-        SweepRec r0 = {0.f, 0.f, 0.f, 0}, r1 = r0;
-        if (qa < n) r0 = rec[qa];
-        if (qb < n) r1 = rec[qb];
-        const bool live0 = qa < n && r0.x1 <= ax2;         // x order: once this fails, it fails for every later q
-        const bool live1 = qb < n && r1.x1 <= ax2;
-        const bool pass0 = live0 && r0.ylo < ra.yhi && ra.ylo < r0.yhi;      // widened float y ranges: a superset of the exact test
-        const bool pass1 = live1 && r1.ylo < ra.yhi && ra.ylo < r1.yhi;
+    // SWEEP_W * 32 successors per step (SWEEP_W records per lane, all loads issued before any is used): the loop is a chain of
+    // L2 round trips -- the next records are only requested once the warp knows that the x range goes on -- so more
+    // records per trip is fewer trips (measured at 10^5 boxes: 32 per step 0.45 ms, 64 per step 0.28 ms)
+    constexpr int SWEEP_W = 4;
+    for (int base = p + 1; base < n; base += 32 * SWEEP_W) {
+        SweepRec r[SWEEP_W];
+        bool pass[SWEEP_W], live_last = false;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const bool pass = h ? pass1 : pass0;
-            const int q = h ? qb : qa;
-            const unsigned int m = __ballot_sync(0xffffffffu, pass);
+        for (int h = 0; h < SWEEP_W; ++h) {
+            const int q = base + 32 * h + lane;
+            r[h] = SweepRec{0.f, 0.f, 0.f, 0};
+            if (q < n) r[h] = rec[q];
+        }
+#pragma unroll
+        for (int h = 0; h < SWEEP_W; ++h) {
+            const int q = base + 32 * h + lane;
+            const bool live = q < n && r[h].x1 <= ax2;                           // x order: once this fails, it fails for every later q
+            pass[h] = live && r[h].ylo < ra.yhi && ra.ylo < r[h].yhi;            // widened float y ranges: a superset of the exact test
+            if (h == SWEEP_W - 1) live_last = live;
+        }
+#pragma unroll
+        for (int h = 0; h < SWEEP_W; ++h) {
+            const unsigned int m = __ballot_sync(0xffffffffu, pass[h]);
             if (m) {
-                if (pass) wq[qn + __popc(m & ((1u << lane) - 1u))] = q;
+                if (pass[h]) wq[qn + __popc(m & ((1u << lane) - 1u))] = base + 32 * h + lane;
                 qn += __popc(m);
                 __syncwarp();
                 if (qn >= 32) {
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(256) sweep_kernel(const Box<T>* __restrict__ x
                 }
             }
         }
-        if (!__shfl_sync(0xffffffffu, (int)live1, 31)) break;      // lane 31 of the second group past the x range: so is everything after
+        if (!__shfl_sync(0xffffffffu, (int)live_last, 31)) break;  // lane 31 of the last group past the x range: so is everything after
     }
     if (qn > 0) {
         const int cand = lane < qn ? wq[lane] : 0;

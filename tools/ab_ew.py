@@ -8,12 +8,12 @@ import bench
 from tinyfaces_b200._lib import lib
 dev = torch.device("cuda:0")
 pk = bench.peaks()
-for flag in (0, 16, 0, 16):
+for flag in (0, 32, 0, 32):
     lib().tf_debug_set(15, flag)
     for r in bench.elementwise_classes(dev, pk):
         if "backward" in r["name"]:
             print(json.dumps(dict(flag=flag, name=r["name"][:24], us=round(r["us"], 1), frac=round(r["frac_of_hbm_peak"], 3))), flush=True)
-for flag in (0, 16, 0, 16, 0, 16):
+for flag in (0, 32, 0, 32):
     lib().tf_debug_set(15, flag)
     st = bench.build_step(dev, 8, 960, 1280, "fast", 0, None)
     ms = bench.timed_steps(st["step"], 10, 3, 1, dev) / 10
