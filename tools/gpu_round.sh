@@ -9,6 +9,6 @@ if [ "$2" == "ncu" ]; then
   NCU="ncu --clock-control none"
   timeout 600 $NCU --metrics gpu__time_duration.sum -c 3000 --csv --log-file gpurun_out/launches_r2.csv \
       python bench.py --profile-mode --steps 1 --warmup 1 > gpurun_out/ncu_launches_r2.log 2>&1; tail -1 gpurun_out/ncu_launches_r2.log
-  timeout 400 $NCU --set full --import-source on -k "regex:bn_bwd_apply_kernel|colreduce_kernel<1>" --launch-skip 200 --launch-count 8 -f -o gpurun_out/prof_ewbwd_r2 \
+  timeout 400 $NCU --set full --import-source on -k "regex:bn_bwd_apply_kernel|colreduce_kernel" --launch-skip 238 --launch-count 8 -f -o gpurun_out/prof_ewbwd_r2 \
       python bench.py --profile-mode --steps 1 --warmup 1 > gpurun_out/ncu_ewbwd_r2.log 2>&1; tail -1 gpurun_out/ncu_ewbwd_r2.log
 fi
