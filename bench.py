@@ -446,7 +446,7 @@ def _watchdog(deadline_s):
                 print(json.dumps(line), flush=True)
             except Exception:  # noqa: BLE001
                 pass
-        os._exit(0 if _PROGRESS["line"] is not None else 3)
+        os._exit(0)
     t = threading.Thread(target=run, daemon=True)
     t.start()
 
@@ -690,6 +690,20 @@ def main():
             line["nms"] = nms_report(dev, args.nms_n, pk, with_cpu=(world == 1 and not args.no_cpu_baseline))
         except Exception as ex:  # noqa: BLE001
             line["nms"] = dict(error=str(ex)[:300])
+        # ---- training-target generation: 63x63x25 cells x 12 ground-truth boxes
+        try:
+            from tinyfaces_b200 import inference_bench as ib
+            from tinyfaces_b200.targets import DataProcessor
+            tp = DataProcessor((500, 500), (63, 63), 0.7, 0.3, ib.load_templates()[:, :4], rf=ib.RF, device=dev, jitter="device")
+            r = np.random.RandomState(0)
+            xy = r.rand(12, 2) * 400
+            gt = np.concatenate([xy, xy + 10 + r.rand(12, 2) * 120], axis=1)
+            pad = tp.get_padding([10, 10, 490, 490])
+            t_t = _event_time(lambda: tp.get_heatmaps_device(gt, pad), 10)
+            line["targets"] = dict(workload="DataProcessor.get_heatmaps: 63x63x25 cells x 12 boxes (incl. the host->device copies of boxes / mask)",
+                                   gpu_ms=t_t * 1e3, reference_note="the reference's compute_dense_overlap is a 4-deep Python loop: ~0.15 s per box here")
+        except Exception as ex:  # noqa: BLE001
+            line["targets"] = dict(error=str(ex)[:200])
         # ---- pyramid inference (BASELINE.json configs[2])
         if not args.no_inference and world == 1:
             try:
@@ -710,10 +724,18 @@ def main():
             except Exception as ex:  # noqa: BLE001
                 line["cpu_baseline"] = dict(error=str(ex)[:200])
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    _PROGRESS["line"] = None                      # the line is out: the watchdog must not print a second one
+    sys.stdout.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # leave together, then exit without tearing the process group down: destroy_process_group() can block for minutes
+        # while CUDA graphs that captured NCCL kernels are still being released
+        try:
+            dist.barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
