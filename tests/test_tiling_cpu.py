@@ -29,19 +29,23 @@ def test_bands_cover_the_level_with_enough_halo(H, nb):
 
 
 def test_job_plan_balances_the_five_level_pyramid():
-    from tinyfaces_b200.evaluation import plan_jobs
+    from tinyfaces_b200.evaluation import JOB_FIXED_MS, JOB_MS_PER_MPIX, plan_jobs
     shapes = [(312, 312), (625, 625), (1250, 1250), (2500, 2500), (5000, 5000)]
-    total = sum(h * w for h, w in shapes)
+
+    def cost(h, w):
+        return JOB_FIXED_MS + JOB_MS_PER_MPIX * h * w / 1e6          # the planner's estimate of a tile's forward time
+    total = sum(cost(h, w) for h, w in shapes)
     for world in (1, 2, 4, 8):
         jobs = plan_jobs(shapes, world, spatial=True)
         assert [j[0] for j in jobs] == sorted(j[0] for j in jobs) and {j[0] for j in jobs} == set(range(5))
-        load = [0] * world
+        load = [0.0] * world
         for lv, bi, r0, r1, y0, y1, owner in jobs:
             assert 0 <= owner < world
-            load[owner] += (y1 - y0) * shapes[lv][1]
+            load[owner] += cost(y1 - y0, shapes[lv][1])
         speedup = total / max(load)
         assert speedup >= {1: 1.0, 2: 1.6, 4: 2.6, 8: 4.1}[world] - 1e-9, (world, speedup)
-    # level sharding alone is capped near 1.33x by the 5000^2 level (25 M of 33.3 M pixels)
+        assert plan_jobs(shapes, world, spatial=True) is jobs          # cached
+    # level sharding alone is capped by the 5000^2 level (23.5 of 31 estimated ms)
     jobs = plan_jobs(shapes, 8, spatial=False)
     assert len(jobs) == 5
 
