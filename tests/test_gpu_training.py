@@ -76,38 +76,42 @@ def test_flat_store_layout_and_gradients_equal_autograd_path():
 
 
 def test_flat_sgd_matches_torch_sgd_and_steplr():
-    """3 + 3 steps with momentum 0.9, weight decay 5e-4, the four lr groups of model.py:67-87 and a StepLR(2, 0.1):
-    torch.optim.SGD + StepLR on the autograd path vs tf_sgd_step + tf_steplr_update on the flat path."""
+    """5 steps with momentum 0.9, weight decay 5e-4, the four lr groups of model.py:67-87 and a StepLR(2, 0.1):
+    torch.optim.SGD + StepLR vs tf_sgd_step + tf_steplr_update on the flat store, both fed the SAME gradients (those of the
+    flat model's backward: two independent backwards differ by the run-to-run noise of the atomically accumulated
+    weight gradients, which is not what this test is about -- test_graphed_train_step_matches_eager covers that)."""
     from tinyfaces_b200.models.loss import DetectionCriterion
     from tinyfaces_b200.optim import FlatSGD
-    from tinyfaces_b200.trainer import train_step
     a, b = _model(), _model()
     start = {k: p.detach().clone() for k, p in a.named_parameters()}
     lr = 2e-6
     oa = torch.optim.SGD(a.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4)
     sched = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.1)
     ob = FlatSGD(b, b.learnable_parameters(lr), momentum=0.9, weight_decay=5e-4, bucket_bytes=16 << 20)
-    ca, cb = DetectionCriterion(25, sampler="device", seed=5), DetectionCriterion(25, sampler="device", seed=5)
+    cb = DetectionCriterion(25, sampler="device", seed=5)
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
     for step in range(5):
         x, cm, rm = _batch(2, 64, 96, 20 + step)
-        la = train_step(a, ca, oa, x, cm.clone(), rm)
-        lb = train_step(b, cb, ob, x, cm.clone(), rm)
-        assert abs(float(la) - float(lb)) <= 2e-3 * abs(float(la)), (step, float(la), float(lb))
+        ob.zero_grad()
+        loss = cb(b(x), cm.clone(), rm)
+        loss.backward()
+        assert np.isfinite(float(loss))
+        for k, p in pb.items():
+            pa[k].grad = None if p.grad is None else p.grad.detach().clone()
+        oa.step()
+        ob.step()
         sched.step()
         ob.steplr(2, 0.1)
     torch.cuda.synchronize()
     assert abs(float(ob.lr_scale) - 0.01) < 1e-7 and int(ob.epoch) == 5
-    pb = dict(b.named_parameters())
-    for k, p in a.named_parameters():
+    for k, p in pa.items():
         moved = float((p.detach() - start[k]).abs().max())
         d = _maxdiff(p.detach(), pb[k].detach())
         ulp = 1.2e-7 * float(p.detach().abs().max())                   # both updates are rounded to fp32 at every step
-        assert d <= 2e-3 * moved + 4 * ulp + 1e-12, (k, d, moved)      # relative to how far the optimizer moved the tensor
+        assert d <= 1e-4 * moved + 4 * ulp + 1e-12, (k, d, moved)      # relative to how far the optimizer moved the tensor
         if k.startswith("model.fc") or k == "score4_upsample.weight":
             assert moved == 0.0 and d == 0.0                           # untouched by both (grad None / lr 0)
-    # BN running statistics are not the optimizer's business but must agree too
-    sa, sb = a.state_dict(), b.state_dict()
-    assert _maxdiff(sa["model.layer3.22.bn3.running_var"], sb["model.layer3.22.bn3.running_var"]) <= 1e-5
+    assert float((pa["model.conv1.weight"].detach() - start["model.conv1.weight"]).abs().max()) > 0.0
 
 
 def test_sgd_kernel_against_formula():

@@ -78,7 +78,7 @@ struct Model {
     // when a dgrad GEMM of the chain and a weight-gradient GEMM of the side stream are both ready, the block scheduler
     // hands the SMs to the chain first (both kernels need a whole SM's shared memory, so they cannot co-reside).
     cudaStream_t chain = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr, ev_region[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_pack = nullptr, ev_pack_dgrad = nullptr, ev_region[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};
     // wgrad_mode 0: weight gradient forked before its dgrad is enqueued; 1: forked before, enqueued after the dgrad;
     //            2: deferred -- a block's three weight gradients are enqueued when the NEXT block's bn3 backward
     //               (the longest HBM-bound stretch of the chain, ~6 passes over a 1024-channel tensor) starts
@@ -94,7 +94,7 @@ struct Model {
     int side_dev = -1;                    // device the internal streams / events were created on
     void destroy_side() {
         if (!side) return;
-        cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_pack);
+        cudaStreamDestroy(side); cudaStreamDestroy(chain); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); cudaEventDestroy(ev_pack); cudaEventDestroy(ev_pack_dgrad);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_region[i]); cudaEventDestroy(ev_chain[i]); }
         side = nullptr; chain = nullptr;
     }
@@ -109,6 +109,7 @@ struct Model {
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_pack, cudaEventDisableTiming));
+        TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_pack_dgrad, cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_region[i], cudaEventDisableTiming));
         for (int i = 0; i < 2; ++i) TF_CHECK_CUDA(cudaEventCreateWithFlags(&ev_chain[i], cudaEventDisableTiming));
         int least = 0, greatest = 0;
@@ -454,9 +455,10 @@ struct Model {
             ConvP h4; h4.w = s4_w; h4.cin = 1024; h4.cout = Cn; h4.k = 1;
             prepack_add(h3, Cp, 512, 0); prepack_add(h4, Cp, 1024, 0);
             RC(prepack_flush(ps));
+            if (aside && !ar.dry) TF_CHECK_CUDA(cudaEventRecord(ev_pack, side));          // layer1 waits for the fprop weights only
             if (training) {
                 RC(prepack_dgrad_weights(ps));
-                if (aside && !ar.dry) TF_CHECK_CUDA(cudaEventRecord(ev_pack, side));
+                if (aside && !ar.dry) TF_CHECK_CUDA(cudaEventRecord(ev_pack_dgrad, side));   // joined at the end of the forward
             }
             pack_pending = aside && !ar.dry;
         }
@@ -533,7 +535,7 @@ struct Model {
             for (int k = 0; k < 2; ++k) { pp[k] = ar.f(mx); pp_lo[k] = mode == 2 ? ar.f(mx) : nullptr; }
         }
         const size_t scratch_mark = ar.off;
-        if (pack_pending) { TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_pack, 0)); pack_pending = false; }   // packed weights are ready
+        if (pack_pending) TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_pack, 0));   // packed fprop weights are ready
         const float* cur = pool; const float* cur_lo = pool_lo;
         int ch = Hp, cw = Wp;
         for (size_t i = 0; i < blocks.size(); ++i) {
@@ -558,6 +560,8 @@ struct Model {
             RC(tfg::conv_fprop(h, st));
             RC(tfe::head_combine_fwd(s3, s4, up, B, H3, W3, H4, W4, Cn, Cp, out_nchw, st));
         }
+        // the dgrad weights were packed on the side stream behind the whole forward: join it (free by now)
+        if (pack_pending) { TF_CHECK_CUDA(cudaStreamWaitEvent(st, ev_pack_dgrad, 0)); pack_pending = false; }
         fwd_mark = ar.off;
         return TF_OK;
     }
