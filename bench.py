@@ -641,6 +641,15 @@ def main():
                 line["fast_out_rel_err"] = fe
                 del ps
                 torch.cuda.empty_cache()
+                # the same forward with the TF32 backward of `fast` (precision="mixed"): outputs identical to `parity`
+                ms_ = build_step(dev, B_PER_GPU, H_IMG, W_IMG, "mixed", rank, None)
+                mms = timed_steps(ms_["step"], 5, 2, 1, dev) / 5
+                line["mixed_mode"] = dict(arithmetic="forward 3xTF32 (= parity: same score map), backward GEMMs 1xTF32 on the hi parts",
+                                          ms_per_step=mms, images_per_s=B_PER_GPU / (mms / 1e3), cuda_graph=ms_["graphed"] is not None,
+                                          gradient_gate="tests/test_gpu_baseline_shapes.py, tests/test_gpu_model.py: weight gradients "
+                                                        "within rel-L2 3e-2 of the reference's fp32 autograd, like parity")
+                del ms_
+                torch.cuda.empty_cache()
             except Exception as ex:  # noqa: BLE001
                 line["parity_mode"] = dict(error=str(ex)[:300])
         # ---- rooflines: every layer-3 GEMM class alone; the headline `roofline` is the class with the largest time per step

@@ -154,7 +154,8 @@ int tf_pyramid_level(const float* img, int H, int W, int Ho, int Wo, const int* 
 /* ---- whole-model executor: replaces DetectionModel.forward (tinyfaces/models/model.py:89-128) and the backward
  * autograd derives from it (tinyfaces/trainer.py:86).  params / grads: HOST arrays of tf_model_num_params()
  * device pointers in tf_model_param_name() order (reference state_dict names; OIHW weights, BN vectors).
- * mode: 1 = fast (1xTF32), 2 = parity (3xTF32).  x [B,3,H,W] and out [B,5T,H/8,W/8] are NCHW fp32. */
+ * mode: 1 = fast (1xTF32), 2 = parity (3xTF32), 3 = mixed (the forward of mode 2, the backward GEMMs with single TF32
+ * products on the hi parts of the saved operands).  x [B,3,H,W] and out [B,5T,H/8,W/8] are NCHW fp32. */
 int tf_model_create(int num_templates, void** handle_host);
 int tf_model_destroy(void* handle);
 int tf_model_num_params(void* handle);

@@ -111,7 +111,7 @@ def _train_case(name, precision, with_grads):
 
 
 def _gate(rec, precision):
-    if precision == "parity":
+    if precision in ("parity", "mixed"):      # mixed = parity's forward + the TF32 backward: same gates
         assert rec["out_max"] < 1e-3 and rec["out_l2"] < 1e-3 and rec["norm_rel"] < 1e-3 and rec["chan_sum"] < 1e-3, rec
         assert rec["run_var_bn1"] < 1e-4 and rec["run_mean_l3"] < 1e-3 and rec["run_var_l3"] < 1e-3, rec
         grads = [v for k, v in rec.items() if k.startswith("grad:")]
@@ -121,12 +121,12 @@ def _gate(rec, precision):
         assert rec["out_max"] < 3e-2 and rec["out_l2"] < 3e-2 and rec["run_var_bn1"] < 1e-3, rec
 
 
-@pytest.mark.parametrize("precision", ["parity", "fast"])
+@pytest.mark.parametrize("precision", ["parity", "mixed", "fast"])
 def test_cfg1_train_500(precision):
     _gate(_train_case("cfg1_train", precision, True), precision)
 
 
-@pytest.mark.parametrize("precision", ["parity", "fast"])
+@pytest.mark.parametrize("precision", ["parity", "mixed", "fast"])
 def test_cfg2_b1_train_960x1280(precision):
     _gate(_train_case("cfg2_b1_train", precision, True), precision)
 

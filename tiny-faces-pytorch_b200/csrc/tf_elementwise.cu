@@ -31,7 +31,9 @@ __device__ __forceinline__ float4 ld4s(const float* p, int streaming = 1) {
     return streaming ? __ldcs(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
 }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float hi_part(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// hi half of the exact (hi, lo) TF32 split x = hi + lo: x ROUNDED to TF32 (not truncated), so that hi alone is an unbiased
+// TF32 operand (precision "mixed" runs its backward GEMMs on the hi parts only) and |lo| <= 2^-12 |x|; x - hi is exact in fp32
+__device__ __forceinline__ float hi_part(float x) { return tf_round_tf32(x); }
 
 // ReLU masks are kept as 1 bit per element (element i -> bit i%32 of word i/32) so that the backward passes do not
 // have to re-read the activation tensor: 4 consecutive elements (one float4) = one nibble.

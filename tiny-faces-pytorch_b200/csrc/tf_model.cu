@@ -408,6 +408,10 @@ struct Model {
     }
 
     bool pack_pending = false;
+    // API mode 3 ("mixed"): 3xTF32 forward (mode == 2: outputs inside the 1e-3 tolerance, exact ReLU masks / statistics) with the
+    // single-product TF32 backward of mode 1 -- the saved (hi, lo) activations and weights are used through their hi parts only
+    bool fast_bwd = false;
+    int bmode() const { return (mode == 2 && fast_bwd) ? 1 : mode; }
     // every dgrad (transposed, tap-flipped) weight of the backward pass, one launch
     int prepack_dgrad_weights(cudaStream_t st) {
         jobs.clear(); jobs_total = 0;
@@ -575,9 +579,9 @@ struct Model {
         const long long M = (long long)u.B * u.Ho * u.Wo;
         const int C = u.bn.C;
         *dy = ar.f((size_t)M * C);
-        *dy_lo = mode == 2 ? ar.f((size_t)M * C) : nullptr;
+        *dy_lo = bmode() == 2 ? ar.f((size_t)M * C) : nullptr;
         if (!ar.dry) RC(tfe::bn_backward(dout, nullptr, mask, u.y, u.mean, u.rstd, P(u.bn.gamma), M, C, G(grads, u.bn.gamma), G(grads, u.bn.beta),
-                                         *dy, *dy_lo, gmask_out, mode, bwd_slots, coef, st));
+                                         *dy, *dy_lo, gmask_out, bmode(), bwd_slots, coef, st));
         return TF_OK;
     }
     // conv backward of unit u given dy at (Ho, Wo): weight gradient (always) and input gradient into dx
@@ -647,7 +651,7 @@ struct Model {
         // G = dout * [out > 0]: it feeds the downsample BN when there is one; with an identity shortcut it is never
         // materialised -- the conv1 dgrad's residual epilogue adds the masked dout itself (TMA-loaded boxes; -0.5 ms/step
         // against "dx starts as G, written by the BN-backward pass, and the dgrad reduce-adds onto it" = tf_debug_set(8, 2))
-        const bool fuse_g = !has_ds && s.u1.c.k == 1 && s.u1.c.stride == 1 && mode == 1 && tfg::debug_flag(8) != 2;
+        const bool fuse_g = !has_ds && s.u1.c.k == 1 && s.u1.c.stride == 1 && bmode() == 1 && tfg::debug_flag(8) != 2;
         float* g = has_ds ? ar.f((size_t)Mo * C4) : (fuse_g ? nullptr : dx);
         RC(unit_bn_bwd(s.u3, dout, s.omask, g, &dy3, &dy3_lo, grads, st));
         const long long M2o = (long long)s.B * s.u2.Ho * s.u2.Wo;
@@ -700,7 +704,7 @@ struct Model {
         float* ds3 = ar.f((size_t)M3 * Cp); float* ds4 = ar.f((size_t)M4 * Cp);
         // parity mode: the head gradients are exact (hi, lo) splits too, so that the head dgrad / wgrad GEMMs run the same
         // 3xTF32 products as the trunk (round 1 fed them single TF32 operands: 5e-4 on every gradient below the heads)
-        float* ds3_lo = mode == 2 ? ar.f((size_t)M3 * Cp) : nullptr; float* ds4_lo = mode == 2 ? ar.f((size_t)M4 * Cp) : nullptr;
+        float* ds3_lo = bmode() == 2 ? ar.f((size_t)M3 * Cp) : nullptr; float* ds4_lo = bmode() == 2 ? ar.f((size_t)M4 * Cp) : nullptr;
         if (!ar.dry) {
             TF_CHECK_CUDA(cudaMemsetAsync(bwd_slots, 0, (size_t)tfe::BN_BWD_SLOTS * 2 * 1024 * sizeof(float), st));   // every BN backward leaves it zeroed
             RC(tfe::head_combine_bwd(dout_nchw, up, B, H3, W3, H4, W4, Cn, Cp, ds3, ds4, st, ds3_lo, ds4_lo));
@@ -833,10 +837,10 @@ TF_API int tf_model_output_shape(void* handle, int H, int W, int* H3, int* W3) {
 }
 // Workspace needed by forward (+ backward when training) for this shape / mode (dry run of the same code path).
 TF_API int tf_model_workspace_bytes(void* handle, int B, int H, int W, int training, int mode, size_t* bytes) {
-    TF_REQUIRE(handle && bytes && B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_workspace_bytes: bad args");
+    TF_REQUIRE(handle && bytes && B > 0 && H >= 16 && W >= 16 && mode >= 1 && mode <= 3, "tf_model_workspace_bytes: bad args");
     Model* m = reinterpret_cast<Model*>(handle);
     m->plan_training = -1;                       // any explicit query invalidates the cached plan of tf_model_forward
-    m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode;
+    m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode == 3 ? 2 : mode; m->fast_bwd = mode == 3;
     m->ar = Arena(); m->ar.dry = true; m->ar.base = nullptr;
     RC(m->forward(nullptr, nullptr, nullptr));
     if (training) RC(m->backward(nullptr, nullptr, nullptr));
@@ -849,7 +853,7 @@ TF_API int tf_model_workspace_bytes(void* handle, int B, int H, int W, int train
 TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, const void* const* params, int training,
                             int mode, float bn_momentum, float* out, void* workspace, size_t workspace_bytes, void* stream) {
     TF_REQUIRE(handle && x && params && out && workspace, "tf_model_forward: null pointer");
-    TF_REQUIRE(B > 0 && H >= 16 && W >= 16 && (mode == 1 || mode == 2), "tf_model_forward: bad shape/mode");
+    TF_REQUIRE(B > 0 && H >= 16 && W >= 16 && mode >= 1 && mode <= 3, "tf_model_forward: bad shape/mode");
     Model* m = reinterpret_cast<Model*>(handle);
     size_t need;
     if (m->plan_B == B && m->plan_H == H && m->plan_W == W && m->plan_training == training && m->plan_mode == mode &&
@@ -860,7 +864,7 @@ TF_API int tf_model_forward(void* handle, const float* x, int B, int H, int W, c
         m->plan_B = B; m->plan_H = H; m->plan_W = W; m->plan_training = training; m->plan_mode = mode; m->plan_need = need;
         m->plan_epoch = tfg::debug_epoch();
     }
-    m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode;
+    m->B = B; m->H = H; m->W = W; m->training = training; m->mode = mode == 3 ? 2 : mode; m->fast_bwd = mode == 3;
     if (workspace_bytes < need) { tf_set_error("tf_model_forward: workspace %zu < required %zu", workspace_bytes, need); return TF_ERR_WORKSPACE; }
     m->params.assign(params, params + m->names.size()); m->momentum = bn_momentum;
     m->ar = Arena(); m->ar.dry = false; m->ar.base = reinterpret_cast<char*>(workspace); m->ar.cap = workspace_bytes;

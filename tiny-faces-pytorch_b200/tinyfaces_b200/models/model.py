@@ -13,7 +13,9 @@ Restrictions that differ from an ordinary nn.Module (both raise instead of compu
     (torch.backends.cudnn.allow_tf32 defaults to True); measured against the fp32 CPU reference on the conditioned
     synthetic weights its score map is off by ~5e-3 (max-norm) and its weight gradients by 20-30 % rel-L2 (error
     amplification of the untrained net).  "parity" = 3xTF32 (fp32-equivalent products): score map within
-    1e-3, ~2x the step time, 2x the activation memory.
+    1e-3, ~2x the step time, 2x the activation memory.  "mixed" = the 3xTF32 forward of "parity" (same score map, exact
+    ReLU masks and batch statistics) with the single-product TF32 backward of "fast" (what cuDNN's TF32 default does to
+    the reference's own backward on CUDA); inference-only use is identical to "parity".
 """
 import ctypes
 
@@ -25,7 +27,7 @@ from torchvision.models import ResNet101_Weights, resnet101
 from .. import _lib
 from .._lib import check, lib, stream_ptr
 
-PRECISION = {"fast": 1, "parity": 2}
+PRECISION = {"fast": 1, "parity": 2, "mixed": 3}
 
 
 class _Executor:
