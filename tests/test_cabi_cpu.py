@@ -42,6 +42,17 @@ def test_model_param_table_matches_reference_state_dict_names():
     sz = ctypes.c_size_t()
     assert lib.tf_model_workspace_bytes(h, 8, 960, 1280, 1, 1, ctypes.byref(sz)) == 0
     assert 10 * 2 ** 30 < sz.value < 60 * 2 ** 30
+    # the three precision modes: fast < mixed (3xTF32 forward, no lo halves in the backward) < parity; eval needs far less
+    by_mode = {}
+    for mode in (1, 2, 3):
+        assert lib.tf_model_workspace_bytes(h, 8, 960, 1280, 1, mode, ctypes.byref(sz)) == 0
+        by_mode[mode] = sz.value
+    assert by_mode[1] < by_mode[3] < by_mode[2] < 60 * 2 ** 30
+    assert lib.tf_model_workspace_bytes(h, 8, 960, 1280, 0, 3, ctypes.byref(sz)) == 0
+    ev3 = sz.value
+    assert lib.tf_model_workspace_bytes(h, 8, 960, 1280, 0, 2, ctypes.byref(sz)) == 0
+    assert ev3 == sz.value < by_mode[1]                                                 # inference: mixed == parity
+    assert lib.tf_model_workspace_bytes(h, 8, 960, 1280, 1, 4, ctypes.byref(sz)) != 0     # unknown mode
     h3, w3 = ctypes.c_int(), ctypes.c_int()
     for (H, W, e) in [(500, 500, (63, 63)), (960, 1280, (120, 160)), (5000, 5000, (625, 625)), (1250, 1250, (157, 157))]:
         assert lib.tf_model_output_shape(h, H, W, ctypes.byref(h3), ctypes.byref(w3)) == 0
