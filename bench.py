@@ -309,6 +309,22 @@ def elementwise_classes(dev, pk):
     return rows
 
 
+def nms_by_n(dev, sizes=(1000, 10000, 100000, 1000000)):
+    """SURVEY 8d's NMS-only sweep: the synthetic float64 set of nms_report at N = 1e3 .. 1e6 (same density: ~25 % kept)."""
+    from tinyfaces_b200 import ops, synthetic
+    rows = []
+    for n in sizes:
+        bx, sc = synthetic.boxes(n, seed=0, extent=NMS_EXTENT_FACTOR * 40.0 * math.sqrt(n / 4.0))
+        bxd, scd = bx.to(dev), sc.to(dev)
+        t = _event_time(lambda: ops.nms_device(bxd, scd, 0.3), 10)
+        _, cnt = ops.nms_device(bxd, scd, 0.3)
+        k = int(cnt.item())
+        rows.append(dict(n=n, ms=t * 1e3, boxes_per_s=n / t, kept_frac=k / n if k >= 0 else None,
+                         candidates="bit-matrix blocks" if n < 4096 else ("1-D sweep" if n <= 300000 else "size-class grid")))
+        del bxd, scd
+    return rows
+
+
 def nms_report(dev, n, pk, with_cpu):
     """tf_nms on n synthetic float64 boxes (centres U(0,S)^2 with S chosen so that ~25 % survive, sizes U(10,70)^2, 1 %
     exact duplicates): end-to-end time, stage breakdown (the library stops after a stage under tf_debug_set(14, k)),
@@ -699,6 +715,10 @@ def main():
             line["nms"] = nms_report(dev, args.nms_n, pk, with_cpu=(world == 1 and not args.no_cpu_baseline))
         except Exception as ex:  # noqa: BLE001
             line["nms"] = dict(error=str(ex)[:300])
+        try:
+            line["nms_by_n"] = nms_by_n(dev)
+        except Exception as ex:  # noqa: BLE001
+            line["nms_by_n"] = dict(error=str(ex)[:300])
         # ---- training-target generation: 63x63x25 cells x 12 ground-truth boxes
         try:
             from tinyfaces_b200 import inference_bench as ib
